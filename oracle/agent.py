@@ -1,0 +1,213 @@
+"""Batched skill-chaining agent, CPU oracle.  TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Restates skill chaining (the paper named in /root/reference/README.md:2; the reference has no
+code) for a batch of envs in lock-step, as BASELINE.json configs[1..4] need it:
+"full skill chaining (up to 4 options + logistic initiation classifiers)" and the
+"option-graph (multiple chains merging at shared subgoal initiation sets)" variant.
+SURVEY.md appendix A.5 / A.6.
+
+Option slots 0..K-1.  Slots 0..n_active-1 are ACTIVE (trained classifier, executable only inside
+their initiation set); slot g = n_active is GESTATING (initiation set = everywhere, it is the
+learner that reaches for the newest target event); later slots are unused.  Slot K-1 is never
+promoted, so a gestating option always exists as the fallback.
+  parents[k]: bit j set -> the initiation set of option j is a target of option k;
+              bit 31 (GOAL_BIT) -> the task goal is a target of option k.
+  chain mode: parents[g] = {g-1} (GOAL for g = 0).  graph mode: parents[g] = all active | GOAL.
+
+One agent step t, for every env (this is the definition the fused GPU pipeline mirrors):
+  1. s2, r_env, env_done = env.step(a)
+  2. I_k(s2) = active[k] and sigmoid(theta_k . psi(s2)) >= 0.5, for all k
+  3. hit   = (GOAL in parents[o] and env_done) or any_j(j in parents[o] and I_j(s2))
+     t_opt += 1; ep_steps += 1
+     term  = env_done or hit or t_opt >= option_timeout or (active[o] and not I_o(s2))
+             or ep_steps >= max_episode_steps
+     r     = r_env + (option_bonus if hit and not env_done)
+  4. a2 = eps-greedy(Q_o(s2, .); Philox(seed; env, t, STREAM_ACTION))
+  5. Sarsa(lambda) update of option o with (s, a, r, s2, a2, done=term)
+  6. where term: append (option start position, label = hit) to option o's example ring;
+     n_success[o] += hit, n_fail[o] += not hit
+  7. where env_done or episode timed out: env reset to a start state, ep_steps = 0
+  8. where term: o' = first active k with I_k(s_next), else g;  t_opt = 0; start position = s_next
+                 a' = eps-greedy(Q_o'(s_next, .); Philox(seed; env, t, STREAM_RESELECT))
+     else:       o' = o, a' = a2
+  9. every sync_interval steps: OptionSet.apply()
+manage() is the low-rate controller: when the gestating option has collected enough successes its
+classifier is fit on its examples, it becomes active and the next slot starts gestating.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .option import OptionSet, epsilon_greedy
+from .philox import STREAM_ACTION
+from .pinball import PinballEnv, PinballMap
+
+f32 = np.float32
+GOAL_BIT = np.uint32(1 << 31)
+STREAM_RESELECT = 2
+
+
+@dataclass
+class AgentConfig:
+    map: str = "easy"
+    batch: int = 1
+    order: int = 3
+    max_options: int = 4
+    gamma: float = 0.99
+    lam: float = 0.9
+    alpha: float = 1e-3
+    epsilon: float = 0.05
+    sync_interval: int = 1
+    seed: int = 0
+    env_offset: int = 0
+    option_bonus: float = 1000.0
+    option_timeout: int = 250
+    max_episode_steps: int = 2000
+    gestation_successes: int = 32
+    example_capacity: int = 4096
+    clf_steps: int = 200
+    clf_lr: float = 1.0
+    graph: bool = False
+
+
+class SkillChainAgent:
+    def __init__(self, cfg, pmap=None):
+        self.cfg = cfg
+        self.map = pmap if pmap is not None else PinballMap.from_name(cfg.map)
+        B, K = cfg.batch, cfg.max_options
+        self.env = PinballEnv(self.map, B, seed=cfg.seed, env_offset=cfg.env_offset)
+        self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon,
+                                 cfg.seed, cfg.env_offset)
+        self.active = np.zeros(K, dtype=bool)
+        self.parents = np.zeros(K, dtype=np.uint32)
+        self.parents[0] = GOAL_BIT
+        self.n_active = 0
+        self.t = 0
+        self.option = np.zeros(B, dtype=np.int32)
+        self.t_opt = np.zeros(B, dtype=np.int32)
+        self.ep_steps = np.zeros(B, dtype=np.int32)
+        self.start_xy = self.env.state[:, :2].copy()
+        self.ex_xy = np.zeros((K, cfg.example_capacity, 2), dtype=np.float32)
+        self.ex_label = np.zeros((K, cfg.example_capacity), dtype=np.uint8)
+        self.ex_count = np.zeros(K, dtype=np.int64)
+        self.n_success = np.zeros(K, dtype=np.int64)
+        self.n_fail = np.zeros(K, dtype=np.int64)
+        self.episodes = np.zeros(B, dtype=np.int64)
+        self.goals = np.zeros(B, dtype=np.int64)
+        self.ep_return = np.zeros(B, dtype=np.float64)
+        self.last_return = np.full(B, np.nan)
+        self.last_delta = np.zeros(B, dtype=np.float32)
+        self.action = self.options.act(self.env.state, self.option, step=0xFFFFFFFF, stream=STREAM_RESELECT)
+
+    # -- helpers ------------------------------------------------------------------------------
+    def initiation_bits(self, state):
+        """uint32 (B,): bit k set iff option k is active and its classifier accepts the state."""
+        I = self.options.initiation(state) & self.active[None, :]
+        w = (np.uint32(1) << np.arange(self.options.K, dtype=np.uint32))[None, :]
+        return (I * w).sum(axis=1).astype(np.uint32)
+
+    def choose_option(self, bits):
+        """First active option whose initiation set holds, else the gestating slot."""
+        K = self.options.K
+        g = min(self.n_active, K - 1)
+        out = np.full(bits.shape, g, dtype=np.int32)
+        for k in range(K - 1, -1, -1):
+            out = np.where((bits >> np.uint32(k)) & np.uint32(1) != 0, k, out)
+        return out.astype(np.int32)
+
+    # -- one lock-step agent step -------------------------------------------------------------
+    def step(self):
+        cfg, env, opts = self.cfg, self.env, self.options
+        t = self.t
+        B = cfg.batch
+        idx = np.arange(B)
+        s = env.state.copy()
+        a, o = self.action, self.option
+        s2, r_env, env_done, _ = env.step(a)
+        bits = self.initiation_bits(s2)
+        pm = self.parents[o]
+        hit = (((pm & GOAL_BIT) != 0) & env_done) | ((bits & pm & ~GOAL_BIT) != 0)
+        self.t_opt += 1
+        self.ep_steps += 1
+        in_own = ((bits >> o.astype(np.uint32)) & np.uint32(1)) != 0
+        left = self.active[o] & ~in_own
+        ep_timeout = (self.ep_steps >= cfg.max_episode_steps) & ~env_done
+        term = env_done | hit | (self.t_opt >= cfg.option_timeout) | left | ep_timeout
+        r = (r_env + np.where(hit & ~env_done, f32(cfg.option_bonus), f32(0.0))).astype(np.float32)
+        a2 = opts.act(s2, o, step=t, stream=STREAM_ACTION)
+        delta = opts.update(s, a, r, s2, a2, term, o)
+        self.last_delta = delta
+        self.ep_return += r_env
+        for b in np.nonzero(term)[0]:
+            k = o[b]
+            slot = self.ex_count[k] % cfg.example_capacity
+            self.ex_xy[k, slot] = self.start_xy[b]
+            self.ex_label[k, slot] = 1 if hit[b] else 0
+            self.ex_count[k] += 1
+            if hit[b]:
+                self.n_success[k] += 1
+            else:
+                self.n_fail[k] += 1
+        reset = env_done | ep_timeout
+        if reset.any():
+            env.reset(mask=reset, step=t)
+            self.episodes[reset] += 1
+            self.goals[env_done] += 1
+            self.last_return[reset] = self.ep_return[reset]
+            self.ep_return[reset] = 0
+            self.ep_steps[reset] = 0
+        s_next = env.state
+        a_next, o_next = a2.copy(), o.copy()
+        if term.any():
+            bits_next = self.initiation_bits(s_next)
+            o_sel = self.choose_option(bits_next)
+            o_next = np.where(term, o_sel, o).astype(np.int32)
+            Q = opts.q(s_next, o_next)
+            a_sel = epsilon_greedy(Q, opts.epsilon, opts.seed, opts.env_ids, t, STREAM_RESELECT)
+            a_next = np.where(term, a_sel, a2).astype(np.int32)
+            self.t_opt[term] = 0
+            self.start_xy[term] = s_next[term, :2]
+        self.option, self.action = o_next, a_next
+        opts.tick()
+        self.t += 1
+        if self.t % cfg.sync_interval == 0:
+            opts.apply()
+        return dict(state=s_next.copy(), reward=r, env_done=env_done, term=term, hit=hit, delta=delta,
+                    option=o_next.copy(), action=a_next.copy())
+
+    # -- low-rate controller ------------------------------------------------------------------
+    def examples(self, k):
+        n = int(min(self.ex_count[k], self.cfg.example_capacity))
+        return self.ex_xy[k, :n].copy(), self.ex_label[k, :n].copy()
+
+    def manage(self):
+        """Promote the gestating option once it has enough successes.  Returns True on promotion."""
+        cfg, K = self.cfg, self.options.K
+        g = self.n_active
+        if g >= K - 1 or self.n_success[g] < cfg.gestation_successes:
+            return False
+        X, y = self.examples(g)
+        self.options.theta[g] = 0
+        self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
+        self.active[g] = True
+        self.n_active += 1
+        n = self.n_active
+        if cfg.graph:
+            self.parents[n] = np.uint32((1 << n) - 1) | GOAL_BIT
+        else:
+            self.parents[n] = np.uint32(1 << (n - 1))
+        return True
+
+    def run_episode(self, max_steps=2000, manage_every=64):
+        """Step until every env has finished at least one more episode, or `max_steps` steps."""
+        base = self.episodes.copy()
+        steps = 0
+        while steps < max_steps and (self.episodes == base).any():
+            self.step()
+            steps += 1
+            if steps % manage_every == 0:
+                self.manage()
+        fin = self.episodes > base
+        return dict(steps=steps, finished=int(fin.sum()), goals=int(self.goals.sum()),
+                    mean_return=float(np.nanmean(self.last_return[fin])) if fin.any() else float("nan"),
+                    n_active=int(self.n_active), env_steps=steps * self.cfg.batch)
