@@ -1,0 +1,176 @@
+/* scg_b200.h - C ABI of the B200-native Pinball / skill-chaining hot path.
+ *
+ * The reference repository (joedownard/skill-chaining-with-graphs) ships no code and therefore
+ * no FFI: /root/reference/README.md:1-2 is the whole repository.  The interface each entry point
+ * "replaces" is the Python interface of the committed CPU oracle that stands in for the reference
+ * (BASELINE.json north_star: "env.reset/step, Option.initiation/act/update,
+ * SkillChainAgent.run_episode").  Each declaration cites the oracle function it mirrors.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t value (> 0) on a CUDA failure, or one
+ *     of the SCG_E* codes (< 0) on a bad argument; scg_error_string() describes any of them
+ *   - the library never allocates or frees caller buffers; all `float*` / `int*` arguments are
+ *     DEVICE pointers unless the function name ends in `_host`
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default)
+ *   - no function synchronises the device except the `_host` variants, scg_map_create and
+ *     the scratch (re)allocation inside scg_ctx_create
+ *   - one host thread drives one context; entry points are re-entrant, not internally locked
+ *   - actions: 0 +x, 1 +y, 2 -x, 3 -y, 4 none;  A = 5;  F = (order+1)^4;  orders 1..5
+ *   - state is structure-of-arrays: x[B], y[B], vx[B], vy[B] (fp32)
+ */
+#ifndef SCG_B200_H
+#define SCG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCG_N_ACTIONS 5
+#define SCG_N_PSI 6
+#define SCG_MAX_OPTIONS 16
+#define SCG_MAX_ORDER 5
+#define SCG_GOAL_BIT 0x80000000u
+
+/* flags word written by the step (oracle/pinball.py pack_flags) */
+#define SCG_FLAG_DONE 1
+#define SCG_FLAG_KIND_SHIFT 1   /* 0 none, 1 reflection, 2 reversal (last collision of the step) */
+#define SCG_FLAG_EDGE_SHIFT 8   /* edge index inside its obstacle, 8 bits */
+#define SCG_FLAG_OBST_SHIFT 16  /* obstacle (polygon) index, 12 bits */
+
+/* Philox stream ids: counter = (global env id, step, stream, 0), key = seed */
+#define SCG_STREAM_ACTION 0
+#define SCG_STREAM_RESET 1
+#define SCG_STREAM_RESELECT 2
+
+#define SCG_EINVAL (-1)   /* bad argument */
+#define SCG_ENOMEM (-2)   /* host allocation failed */
+#define SCG_ELIMIT (-3)   /* map / order / K exceeds a compiled-in limit */
+
+typedef struct scg_map scg_map_t; /* opaque: edge table + broad-phase grid, host and device copies */
+typedef struct scg_ctx scg_ctx_t; /* opaque: device scratch for the Sarsa(lambda) reduction */
+
+const char *scg_error_string(int code);
+int scg_version(void);
+
+/* ---- map ---------------------------------------------------------------------------------
+ * mirrors oracle/pinball.py PinballMap.__init__ (edge table) - same fp32 formulas, same order.
+ * verts: n_verts x 2 fp32 HOST; poly_start: n_poly+1 HOST offsets into verts; starts: n_starts x 2.
+ * grid_n: broad-phase grid resolution (power of two, <= 128; 0 = default 64). */
+int scg_map_create(const float *verts, const int *poly_start, int n_poly, float ball_r, float tx,
+                   float ty, float tr, const float *starts, int n_starts, int grid_n, scg_map_t **out);
+int scg_map_destroy(scg_map_t *map);
+int scg_map_num_edges(const scg_map_t *map);
+int scg_map_num_candidates(const scg_map_t *map);
+int scg_map_edge_table(const scg_map_t *map, float *edges_out /* HOST [E][8] */,
+                       int *obstacle_out /* HOST [E] */, int *local_out /* HOST [E] */);
+/* broad-phase grid, for tests: cell_start HOST [G*G+1], cand HOST [n_cand] */
+int scg_map_grid(const scg_map_t *map, int *grid_n_out, int *cell_start_out, int *cand_out);
+
+/* ---- K1: batched Pinball step -------------------------------------------------------------
+ * mirrors oracle/pinball.py step_scalar / PinballEnv.step.  Out arrays may alias the inputs.
+ * cull != 0 uses the broad-phase grid (bit-identical results); 0 tests every edge. */
+int scg_step(const scg_map_t *map, int B, const float *x, const float *y, const float *vx,
+             const float *vy, const int *action, float *x2, float *y2, float *vx2, float *vy2,
+             float *reward, int *flags, int cull, void *stream);
+/* mirrors PinballEnv.reset(mask, step): masked envs go to a start position with zero velocity */
+int scg_reset(const scg_map_t *map, int B, const uint8_t *mask /* may be NULL = all */, float *x,
+              float *y, float *vx, float *vy, uint64_t seed, uint32_t step, uint32_t env_offset,
+              void *stream);
+/* HOST-buffer variant of scg_step (state in, state/reward/flags out; copies included) */
+int scg_step_host(const scg_map_t *map, int B, float *state_soa /* HOST [4][B] in/out */,
+                  const int *action /* HOST */, float *reward /* HOST */, int *flags /* HOST */,
+                  void *stream);
+
+/* ---- K2: Fourier features, Q evaluation, action selection, TD error ------------------------
+ * mirrors oracle/fourier.py FourierBasis.features, oracle/option.py OptionSet.q / act / td_error.
+ * W is [K][A][F]; Wt is the packed copy [K][F][8] made by scg_pack_weights (or scg_apply). */
+int scg_features(int order, int B, const float *x, const float *y, const float *vx, const float *vy,
+                 float *phi /* [B][F] */, void *stream);
+int scg_pack_weights(int order, int K, const float *W, float *Wt, void *stream);
+int scg_q_eval(int order, int K, int B, const float *x, const float *y, const float *vx,
+               const float *vy, const int *option, const float *Wt, float *Q /* [B][A] */, void *stream);
+int scg_select(int B, const float *Q /* [B][A] */, float epsilon, uint64_t seed, uint32_t step,
+               uint32_t stream_id, uint32_t env_offset, int *action, void *stream);
+int scg_td_error(int order, int K, int B, const float *x, const float *y, const float *vx,
+                 const float *vy, const int *a, const float *r, const float *x2, const float *y2,
+                 const float *vx2, const float *vy2, const int *a2, const uint8_t *done,
+                 const int *option, const float *Wt, float gamma, float *delta, void *stream);
+
+/* ---- K3: Sarsa(lambda) eligibility traces and weight-delta accumulation --------------------
+ * mirrors oracle/option.py OptionSet.update (trace part) and OptionSet.apply.
+ * trace is [B][A][F]; dW [K][A][F] and cnt [K] accumulate over the sync window. */
+int scg_ctx_create(int order, int K, scg_ctx_t **out);
+int scg_ctx_destroy(scg_ctx_t *ctx);
+int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const float *y, const float *vx,
+                     const float *vy, const int *a, const int *option, const float *delta,
+                     const uint8_t *done, const uint8_t *mask /* may be NULL */, float gamma_lambda,
+                     float *trace, float *dW, int *cnt, void *stream);
+int scg_apply(int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
+              int window_steps, void *stream);
+
+/* ---- K4: initiation classifiers --------------------------------------------------------------
+ * mirrors oracle/option.py OptionSet.initiation_prob / clf_grad / fit_initiation. */
+int scg_clf_eval(int B, const float *x, const float *y, const float *theta /* [K][6] */, int K,
+                 float *p /* [B][K] */, void *stream);
+int scg_clf_grad(int N, const float *X /* [N][2] */, const uint8_t *y, const float *theta_k /* [6] */,
+                 float *grad /* [6], overwritten */, void *stream);
+int scg_clf_fit(int N, const float *X, const uint8_t *y, float *theta_k /* [6] in/out */, int steps,
+                float lr, void *stream);
+
+/* ---- fused agent step (K1 -> K2 + K4 -> K3), mirrors oracle/agent.py SkillChainAgent.step ---- */
+typedef struct scg_agent {
+    /* sizes and hyper-parameters */
+    int32_t B, K, order, n_active;
+    uint32_t active_mask, env_offset, step, example_capacity;
+    uint64_t seed;
+    float gamma, lambda, epsilon, option_bonus;
+    int32_t option_timeout, max_episode_steps, cull, reserved0;
+    /* per-env state (device) */
+    float *x, *y, *vx, *vy;          /* current state s */
+    float *x2, *y2, *vx2, *vy2;      /* scratch for s'; holds the next state after the call */
+    int32_t *action, *option, *t_opt, *ep_steps;
+    float *start_xy;                 /* [B][2] position where the current option execution began */
+    float *ep_return;                /* [B] running task return */
+    float *reward; int32_t *flags;   /* [B] outputs of the env step */
+    float *delta;                    /* [B] TD errors of this step */
+    float *rec;                      /* [B][12] update records (K2 -> K3) */
+    float *trace;                    /* [B][A][F] */
+    /* per-option state (device) */
+    float *W, *Wt, *theta, *dW;      /* [K][A][F], [K][F][8], [K][6], [K][A][F] */
+    int32_t *cnt;                    /* [K] */
+    uint32_t *parents;               /* [K] */
+    float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */
+    int32_t *ex_count, *n_success, *n_fail; /* [K] */
+    /* global statistics (device): [0] episodes, [1] goals, [2] sum of finished returns (float bits) */
+    int32_t *stats;
+} scg_agent_t;
+
+/* One lock-step agent step.  After it returns, (x2,y2,vx2,vy2) hold the next state: the caller
+ * swaps the two state sets (scg_agent_swap does it on the struct) before the next call. */
+int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag, void *stream);
+void scg_agent_swap(scg_agent_t *ag);
+
+/* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
+ * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]
+ * host->device, runs the fused step, copies next state, reward, flags, next action and TD error
+ * device->host and waits for them.  Traces and weights stay resident on the device. */
+int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag,
+                        const float *h_state_soa, const int *h_action, float *h_state2_soa,
+                        float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
+
+/* Per-kernel device timing of scg_agent_step with CUDA events on the launch stream.
+ * scg_profile_begin arms it (up to max_steps steps are recorded); scg_profile_end waits for the
+ * recorded events and returns the summed milliseconds of each stage:
+ * ms[0] K1 step, ms[1] K2+K4 control, ms[2] K3 trace sweep, ms[3] dW reduction; *steps = steps seen. */
+int scg_profile_begin(scg_ctx_t *ctx, int max_steps);
+int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [4] */, int *steps);
+
+/* kernel launch counter (this library's launches since load), for bench.py's gpu_launches */
+uint64_t scg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCG_B200_H */

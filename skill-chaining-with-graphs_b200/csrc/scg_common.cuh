@@ -1,0 +1,247 @@
+// scg_common.cuh - shared device/host helpers for the sm_100a Pinball / skill-chaining kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/scg_b200.h"
+
+#define SCG_A SCG_N_ACTIONS
+#define SCG_WT_STRIDE 8  // packed weights: [K][F][8] (5 actions + 3 pad) -> two 16-byte loads per feature
+#define SCG_REC_FLOATS 12
+#define SCG_NUM_SMS 148
+
+// update record (K2 -> K3), 48 bytes per env:
+//   [0..7]  cos/sin(pi * s_hat_j), j = 0..3 of the state the update is for
+//   [8]     delta        [9] meta bits        [10],[11] unused
+#define SCG_META_ACTIVE (1u << 31)
+#define SCG_META_ZERO_AFTER (1u << 16)
+
+extern uint64_t g_scg_launches;  // host-side launch counter (scg_api.cu)
+
+#define SCG_CUDA_OK(expr)                      \
+    do {                                       \
+        cudaError_t _e = (expr);               \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+#define SCG_LAUNCH_CHECK()                     \
+    do {                                       \
+        ++g_scg_launches;                      \
+        cudaError_t _e = cudaGetLastError();   \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+// run `...` with `constexpr int N1 = order + 1` for the supported orders
+#define DISPATCH_ORDER(order, ...)                              \
+    switch (order) {                                            \
+        case 1: { constexpr int N1 = 2; __VA_ARGS__; } break;   \
+        case 2: { constexpr int N1 = 3; __VA_ARGS__; } break;   \
+        case 3: { constexpr int N1 = 4; __VA_ARGS__; } break;   \
+        case 4: { constexpr int N1 = 5; __VA_ARGS__; } break;   \
+        case 5: { constexpr int N1 = 6; __VA_ARGS__; } break;   \
+        default: return SCG_ELIMIT;                             \
+    }
+
+static inline int scg_pow4(int n1) { return n1 * n1 * n1 * n1; }
+
+// ---- map blob ------------------------------------------------------------------------------
+// One contiguous, 16-byte aligned block in global memory, bulk-copied into shared memory by the
+// step kernel.  Sections (byte offsets in the header):
+//   edges_a: float4[E]  (x1, y1, dx, dy)
+//   edges_b: float4[E]  (inv_len2, nx, ny, bits(obstacle << 8 | local))
+//   cells:   uint32[G*G] (start << 8 | count) into cand
+//   cand:    uint16[n_cand] edge indices, ascending within a cell
+//   starts:  float2[n_starts]
+struct ScgMapHeader {
+    int32_t n_edges, grid_n, n_cand, n_starts;
+    float ball_r, h, r2, tx;
+    float ty, tr2, grid_f, pad0;
+    int32_t off_edges_a, off_edges_b, off_cells, off_cand;
+    int32_t off_starts, blob_bytes, pad1, pad2;
+};
+static_assert(sizeof(ScgMapHeader) == 80, "header layout");
+
+struct scg_map {
+    ScgMapHeader hdr;
+    unsigned char *h_blob;  // host copy
+    unsigned char *d_blob;  // device copy
+    float *h_edges;         // [E][8] oracle-format table
+    int *h_obst, *h_local;  // [E]
+    int *h_cell_start;      // [G*G+1]
+    int *h_cand;            // [n_cand]
+};
+
+struct scg_ctx {
+    int order, K, F;
+    int n_partials;      // CTAs of the trace kernel
+    float *d_partial;    // [n_partials][K][A*F]
+    float *d_rec;        // records for the standalone scg_sarsa_update, grown on demand
+    int rec_capacity;
+    // optional per-kernel timing of scg_agent_step (scg_profile_begin / scg_profile_end)
+    cudaEvent_t *prof_ev;  // [prof_cap][5]
+    int prof_cap, prof_n, prof_on;
+};
+
+#ifdef __CUDACC__
+// ---- Philox4x32-10 (matches oracle/philox.py) -------------------------------------------------
+__device__ __forceinline__ uint4 scg_philox(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float scg_u01(uint32_t v) { return (float)(v >> 8) * 5.9604644775390625e-08f; }
+__device__ __forceinline__ uint4 scg_draw(uint64_t seed, uint32_t env, uint32_t step, uint32_t stream) {
+    return scg_philox(make_uint4(env, step, stream, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// epsilon-greedy (oracle/option.py epsilon_greedy): explore iff u0 < eps, then min(int(u1*5), 4);
+// otherwise the first maximal action.
+__device__ __forceinline__ int scg_eps_greedy(const float q[SCG_A], float eps, uint4 rnd) {
+    int best = 0;
+    float bq = q[0];
+#pragma unroll
+    for (int a = 1; a < SCG_A; ++a)
+        if (q[a] > bq) { bq = q[a]; best = a; }
+    float u0 = scg_u01(rnd.x), u1 = scg_u01(rnd.y);
+    int ra = min((int)__fmul_rn(u1, (float)SCG_A), SCG_A - 1);
+    return (u0 < eps) ? ra : best;
+}
+
+// ---- complex helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ float2 scg_cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// normalised state (oracle/fourier.py FourierBasis.normalise)
+__device__ __forceinline__ void scg_normalise(float x, float y, float vx, float vy, float s[4]) {
+    s[0] = x;
+    s[1] = y;
+    s[2] = __fmul_rn(__fadd_rn(vx, 2.0f), 0.25f);
+    s[3] = __fmul_rn(__fadd_rn(vy, 2.0f), 0.25f);
+}
+
+// z_j = exp(i pi s_hat_j), j = 0..3
+__device__ __forceinline__ void scg_phasors(float x, float y, float vx, float vy, float2 z[4]) {
+    float s[4];
+    scg_normalise(x, y, vx, vy, s);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sincospif(s[j], &z[j].y, &z[j].x);
+}
+
+// Q_o(s, .) for one env: nested loops over the multi-index with running phasor products
+// (cos(pi c.s) = Re prod_j z_j^{c_j}); the innermost dimension uses a register table.
+// Wt_o points at the packed weights of the env's option: [F][8].
+template <int N1>
+__device__ __forceinline__ void scg_q_one(const float2 z[4], const float *__restrict__ Wt_o, float q[SCG_A]) {
+    float2 p3[N1];
+    p3[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
+#pragma unroll
+    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
+    const float4 *w = reinterpret_cast<const float4 *>(Wt_o);
+    float2 z0 = make_float2(1.f, 0.f);
+    for (int c0 = 0; c0 < N1; ++c0) {
+        float2 z01 = z0;
+        for (int c1 = 0; c1 < N1; ++c1) {
+            float2 z012 = z01;
+            for (int c2 = 0; c2 < N1; ++c2) {
+#pragma unroll
+                for (int c3 = 0; c3 < N1; ++c3) {
+                    float phi = fmaf(z012.x, p3[c3].x, -z012.y * p3[c3].y);
+                    float4 wa = __ldg(w), wb = __ldg(w + 1);
+                    w += 2;
+                    q[0] = fmaf(wa.x, phi, q[0]);
+                    q[1] = fmaf(wa.y, phi, q[1]);
+                    q[2] = fmaf(wa.z, phi, q[2]);
+                    q[3] = fmaf(wa.w, phi, q[3]);
+                    q[4] = fmaf(wb.x, phi, q[4]);
+                }
+                z012 = scg_cmul(z012, z[2]);
+            }
+            z01 = scg_cmul(z01, z[1]);
+        }
+        z0 = scg_cmul(z0, z[0]);
+    }
+}
+
+// Same for two states sharing the weight loads: q1 = Q_o(s1, .), q2 = Q_o(s2, .)
+template <int N1>
+__device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4], const float *__restrict__ Wt_o,
+                                           float qa[SCG_A], float qb[SCG_A]) {
+    float2 pa[N1], pb[N1];
+    pa[0] = pb[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < N1; ++c) {
+        pa[c] = scg_cmul(pa[c - 1], za[3]);
+        pb[c] = scg_cmul(pb[c - 1], zb[3]);
+    }
+#pragma unroll
+    for (int a = 0; a < SCG_A; ++a) qa[a] = qb[a] = 0.f;
+    const float4 *w = reinterpret_cast<const float4 *>(Wt_o);
+    float2 a0 = make_float2(1.f, 0.f), b0 = a0;
+    for (int c0 = 0; c0 < N1; ++c0) {
+        float2 a01 = a0, b01 = b0;
+        for (int c1 = 0; c1 < N1; ++c1) {
+            float2 a012 = a01, b012 = b01;
+            for (int c2 = 0; c2 < N1; ++c2) {
+#pragma unroll
+                for (int c3 = 0; c3 < N1; ++c3) {
+                    float fa = fmaf(a012.x, pa[c3].x, -a012.y * pa[c3].y);
+                    float fb = fmaf(b012.x, pb[c3].x, -b012.y * pb[c3].y);
+                    float4 wa = __ldg(w), wb = __ldg(w + 1);
+                    w += 2;
+                    qa[0] = fmaf(wa.x, fa, qa[0]);
+                    qa[1] = fmaf(wa.y, fa, qa[1]);
+                    qa[2] = fmaf(wa.z, fa, qa[2]);
+                    qa[3] = fmaf(wa.w, fa, qa[3]);
+                    qa[4] = fmaf(wb.x, fa, qa[4]);
+                    qb[0] = fmaf(wa.x, fb, qb[0]);
+                    qb[1] = fmaf(wa.y, fb, qb[1]);
+                    qb[2] = fmaf(wa.z, fb, qb[2]);
+                    qb[3] = fmaf(wa.w, fb, qb[3]);
+                    qb[4] = fmaf(wb.x, fb, qb[4]);
+                }
+                a012 = scg_cmul(a012, za[2]);
+                b012 = scg_cmul(b012, zb[2]);
+            }
+            a01 = scg_cmul(a01, za[1]);
+            b01 = scg_cmul(b01, zb[1]);
+        }
+        a0 = scg_cmul(a0, za[0]);
+        b0 = scg_cmul(b0, zb[0]);
+    }
+}
+
+// initiation bits (oracle/agent.py initiation_bits): bit k iff active and theta_k . psi(x, y) >= 0
+// (sigmoid(z) >= 0.5  <=>  z >= 0).
+__device__ __forceinline__ uint32_t scg_init_bits(const float *__restrict__ theta, int K, uint32_t active_mask,
+                                                  float x, float y) {
+    uint32_t bits = 0;
+    float xx = x * x, xy = x * y, yy = y * y;
+    for (int k = 0; k < K; ++k) {
+        if (!((active_mask >> k) & 1u)) continue;
+        const float *t = theta + k * SCG_N_PSI;
+        float zz = __ldg(t);
+        zz = fmaf(__ldg(t + 1), x, zz);
+        zz = fmaf(__ldg(t + 2), y, zz);
+        zz = fmaf(__ldg(t + 3), xx, zz);
+        zz = fmaf(__ldg(t + 4), xy, zz);
+        zz = fmaf(__ldg(t + 5), yy, zz);
+        if (zz >= 0.f) bits |= (1u << k);
+    }
+    return bits;
+}
+
+__device__ __forceinline__ float scg_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif  // __CUDACC__

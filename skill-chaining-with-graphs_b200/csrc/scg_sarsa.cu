@@ -1,0 +1,326 @@
+// scg_sarsa.cu - K3, the Sarsa(lambda) eligibility-trace sweep and weight-delta accumulation (sm_100a).
+//
+// Mirrors oracle/option.py OptionSet.update (trace part) and OptionSet.apply; the reference has
+// no code (/root/reference/README.md:1-2).  Per env b executing option o with action a:
+//     e_b <- gamma*lambda e_b ;  e_b[a] += phi(s_b) ;  dW[o] += delta_b e_b ;  e_b <- 0 if done_b
+//
+// This is the HBM-bound kernel of the pipeline: the dense trace is A*F fp32 per env, read and
+// written once per env-step => 8*A*F (+48 record) algorithmic bytes per env-step.
+//
+// Design: one CTA sweeps one env at a time; thread t owns the same 16-byte chunk(s) of every env's
+// trace, i.e. a fixed set of (action, feature) entries.  Because ownership is exclusive, the CTA's
+// dW accumulator (shared memory, [K][A*F]) is updated with plain read-modify-write - no atomics, no
+// barriers inside the env loop.  phi(s_b) is rebuilt in registers from the four phasors the
+// record carries (only by the threads that own row a), so the only HBM traffic is the trace itself
+// plus a 48-byte record per env.  Two envs are in flight per CTA for memory-level parallelism.
+// At the end each CTA writes its accumulator to a scratch slab; k_reduce folds the slabs into dW.
+#include <algorithm>
+
+#include "scg_common.cuh"
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+__device__ __forceinline__ float4 vscale(float4 v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
+__device__ __forceinline__ float vscale(float v, float s) { return v * s; }
+__device__ __forceinline__ float4 vfma(float s, float4 a, float4 c) {
+    return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+__device__ __forceinline__ float vfma(float s, float a, float c) { return fmaf(s, a, c); }
+__device__ __forceinline__ float4 vzero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// z^c for 0 <= c < 8 from (z, z^2, z^4) with selects (no dynamic register indexing)
+__device__ __forceinline__ float2 cpow_sel(float2 z1, float2 z2, float2 z4, int c) {
+    float2 r = (c & 1) ? z1 : make_float2(1.f, 0.f);
+    if (c & 2) r = scg_cmul(r, z2);
+    if (c & 4) r = scg_cmul(r, z4);
+    return r;
+}
+
+struct Phasors {
+    float2 z1[4], z2[4], z4[4];
+};
+__device__ __forceinline__ Phasors make_phasors(float4 r0, float4 r1) {
+    Phasors p;
+    p.z1[0] = make_float2(r0.x, r0.y); p.z1[1] = make_float2(r0.z, r0.w);
+    p.z1[2] = make_float2(r1.x, r1.y); p.z1[3] = make_float2(r1.z, r1.w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        p.z2[j] = scg_cmul(p.z1[j], p.z1[j]);
+        p.z4[j] = scg_cmul(p.z2[j], p.z2[j]);
+    }
+    return p;
+}
+// phi for the feature whose base-N1 digits are packed 4 bits each (c0 lowest nibble)
+__device__ __forceinline__ float phi_digits(const Phasors &p, uint32_t d) {
+    float2 a = cpow_sel(p.z1[0], p.z2[0], p.z4[0], d & 15);
+    float2 b = cpow_sel(p.z1[1], p.z2[1], p.z4[1], (d >> 4) & 15);
+    float2 c = cpow_sel(p.z1[2], p.z2[2], p.z4[2], (d >> 8) & 15);
+    float2 e = cpow_sel(p.z1[3], p.z2[3], p.z4[3], (d >> 12) & 15);
+    float2 ab = scg_cmul(a, b), ce = scg_cmul(c, e);
+    return fmaf(ab.x, ce.x, -ab.y * ce.y);
+}
+template <int N1>
+__device__ __forceinline__ uint32_t pack_digits(int f) {
+    int c3 = f % N1; f /= N1;
+    int c2 = f % N1; f /= N1;
+    int c1 = f % N1; f /= N1;
+    return (uint32_t)f | ((uint32_t)c1 << 4) | ((uint32_t)c2 << 8) | ((uint32_t)c3 << 12);
+}
+
+__device__ __forceinline__ float4 add_phi(float4 e, const Phasors &p, const uint32_t d[4]) {
+    e.x += phi_digits(p, d[0]); e.y += phi_digits(p, d[1]);
+    e.z += phi_digits(p, d[2]); e.w += phi_digits(p, d[3]);
+    return e;
+}
+__device__ __forceinline__ float add_phi(float e, const Phasors &p, const uint32_t d[1]) { return e + phi_digits(p, d[0]); }
+
+template <int N1, int VEC, int CPT, int NT>
+__global__ void __launch_bounds__(NT) k_trace(int B, int K, const float4 *__restrict__ rec, float *trace,
+                                              float *__restrict__ partial, float gl) {
+    using V = typename VecT<VEC>::type;
+    constexpr int F = N1 * N1 * N1 * N1;
+    constexpr int AF = SCG_A * F;
+    constexpr int NCH = AF / VEC;
+    static_assert(AF % VEC == 0, "vector width must divide the trace");
+    static_assert(VEC == 1 || F % VEC == 0, "a vector must not straddle action rows");
+    static_assert(NT * CPT >= NCH, "not enough threads");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V *acc = reinterpret_cast<V *>(smem_raw);  // [K][NCH]
+
+    // per-thread constants: which (row, features) each owned chunk covers
+    int row[CPT];
+    uint32_t dig[CPT][VEC];
+    bool own[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        int c = threadIdx.x + i * NT;
+        own[i] = c < NCH;
+        int e0 = (own[i] ? c : 0) * VEC;
+        row[i] = e0 / F;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) dig[i][v] = pack_digits<N1>((e0 + v) % F);
+    }
+    for (int i = threadIdx.x; i < K * NCH; i += NT) {
+        if constexpr (VEC == 4) acc[i] = vzero4(); else acc[i] = 0.f;
+    }
+    __syncthreads();
+
+    const int stride = gridDim.x;
+    for (int b0 = blockIdx.x; b0 < B; b0 += 2 * stride) {
+        int bb[2] = {b0, b0 + stride};
+        float4 r0[2], r1[2], r2[2];
+        V e[2][CPT];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            live[u] = bb[u] < B;
+            if (live[u]) {
+                const float4 *rp = rec + (size_t)bb[u] * 3;
+                r0[u] = __ldg(rp); r1[u] = __ldg(rp + 1); r2[u] = __ldg(rp + 2);
+                live[u] = (__float_as_uint(r2[u].y) & SCG_META_ACTIVE) != 0;
+            }
+            if (live[u]) {
+                const V *tp = reinterpret_cast<const V *>(trace + (size_t)bb[u] * AF);
+#pragma unroll
+                for (int i = 0; i < CPT; ++i)
+                    if (own[i]) e[u][i] = tp[threadIdx.x + i * NT];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            uint32_t meta = __float_as_uint(r2[u].y);
+            float delta = r2[u].x;
+            int a = meta & 7, o = (meta >> 8) & 0xFF;
+            bool zero_after = (meta & SCG_META_ZERO_AFTER) != 0;
+            Phasors ph = make_phasors(r0[u], r1[u]);
+            V *tp = reinterpret_cast<V *>(trace + (size_t)bb[u] * AF);
+            V *ap = acc + (size_t)o * NCH;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                if (!own[i]) continue;
+                int c = threadIdx.x + i * NT;
+                V v = vscale(e[u][i], gl);
+                if (row[i] == a) v = add_phi(v, ph, dig[i]);
+                ap[c] = vfma(delta, v, ap[c]);
+                if (zero_after) {
+                    if constexpr (VEC == 4) v = vzero4(); else v = 0.f;
+                }
+                tp[c] = v;
+            }
+        }
+    }
+    __syncthreads();
+    V *out = reinterpret_cast<V *>(partial + (size_t)blockIdx.x * K * AF);
+    for (int i = threadIdx.x; i < K * NCH; i += NT) out[i] = acc[i];
+}
+
+// dW[j] += sum over slabs; grid (ceil(n/256), slices); a few atomics per address.
+__global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const float *__restrict__ partial,
+                                                float *__restrict__ dW) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float s = 0.f;
+    for (int p = blockIdx.y; p < n_partials; p += gridDim.y) s += partial[(size_t)p * n + j];
+    atomicAdd(dW + j, s);
+}
+
+__global__ void k_make_rec(int B, const float *__restrict__ x, const float *__restrict__ y,
+                           const float *__restrict__ vx, const float *__restrict__ vy, const int *__restrict__ a,
+                           const int *__restrict__ option, const float *__restrict__ delta,
+                           const uint8_t *__restrict__ done, const uint8_t *__restrict__ mask, int K,
+                           float4 *__restrict__ rec, int *__restrict__ cnt) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        bool act = !mask || mask[b];
+        float2 z[4];
+        scg_phasors(x[b], y[b], vx[b], vy[b], z);
+        int o = min(max(option[b], 0), K - 1);
+        uint32_t meta = (uint32_t)(a[b] & 7) | ((uint32_t)o << 8) | (done[b] ? SCG_META_ZERO_AFTER : 0u) |
+                        (act ? SCG_META_ACTIVE : 0u);
+        rec[(size_t)b * 3 + 0] = make_float4(z[0].x, z[0].y, z[1].x, z[1].y);
+        rec[(size_t)b * 3 + 1] = make_float4(z[2].x, z[2].y, z[3].x, z[3].y);
+        rec[(size_t)b * 3 + 2] = make_float4(delta[b], __uint_as_float(meta), 0.f, 0.f);
+        if (act) atomicAdd(cnt + o, 1);
+    }
+}
+
+// W += (alpha * alpha_scale_f) * (dW * (steps / cnt_k));  refresh the packed copy;  dW <- 0
+template <int N1>
+__global__ void k_apply(int K, float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ dW,
+                        const int *__restrict__ cnt, float alpha, float steps) {
+    constexpr int F = N1 * N1 * N1 * N1;
+    int n = K * SCG_A * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int f = i % F, ka = i / F, a = ka % SCG_A, k = ka / SCG_A;
+        int c = cnt[k];
+        float w = W[i];
+        if (c > 0) {
+            int d = f, ss = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { int q = d % N1; ss += q * q; d /= N1; }
+            float as = (ss == 0) ? 1.0f : (float)(1.0 / sqrt((double)ss));
+            float scale = __fdiv_rn(steps, (float)c);
+            w = __fadd_rn(w, __fmul_rn(__fmul_rn(alpha, as), __fmul_rn(dW[i], scale)));
+            W[i] = w;
+        }
+        Wt[((size_t)k * F + f) * SCG_WT_STRIDE + a] = w;
+        dW[i] = 0.f;
+    }
+}
+__global__ void k_zero_int(int n, int *p) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+// ---- launch plumbing ----------------------------------------------------------------------------
+template <int N1, int VEC, int CPT, int NT>
+static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, float gl, cudaStream_t st) {
+    size_t smem = (size_t)ctx->K * SCG_A * ctx->F * sizeof(float);
+    auto kern = k_trace<N1, VEC, CPT, NT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) return SCG_ELIMIT;
+    int grid = std::min(std::min(B, SCG_NUM_SMS * per_sm), ctx->n_partials);
+    grid = std::max(grid, 1);
+    kern<<<grid, NT, smem, st>>>(B, ctx->K, rec, trace, ctx->d_partial, gl);
+    SCG_LAUNCH_CHECK();
+    return grid;
+}
+
+// returns the number of slabs written (> 0) or an error (<= 0 means error code negated... see below)
+// ev2: optional two events, recorded after the sweep and after the reduction
+int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float gl, float *dW, cudaStream_t st,
+                     cudaEvent_t *ev2 = nullptr) {
+    int grid = 0;
+    const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+    switch (ctx->order) {
+        case 1: grid = launch_trace_t<2, 4, 1, 32>(ctx, B, r4, trace, gl, st); break;
+        case 2: grid = launch_trace_t<3, 1, 2, 224>(ctx, B, r4, trace, gl, st); break;
+        case 3: grid = launch_trace_t<4, 4, 1, 320>(ctx, B, r4, trace, gl, st); break;
+        case 4: grid = launch_trace_t<5, 1, 4, 800>(ctx, B, r4, trace, gl, st); break;
+        case 5: grid = launch_trace_t<6, 4, 2, 832>(ctx, B, r4, trace, gl, st); break;
+        default: return SCG_ELIMIT;
+    }
+    if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
+    if (ev2) SCG_CUDA_OK(cudaEventRecord(ev2[0], st));
+    int n = ctx->K * SCG_A * ctx->F;
+    dim3 g((n + 255) / 256, std::min(grid, 32));
+    k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
+    SCG_LAUNCH_CHECK();
+    if (ev2) SCG_CUDA_OK(cudaEventRecord(ev2[1], st));
+    return 0;
+}
+
+extern "C" int scg_ctx_create(int order, int K, scg_ctx_t **out) {
+    if (!out) return SCG_EINVAL;
+    if (order < 1 || order > SCG_MAX_ORDER || K < 1 || K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
+    scg_ctx *c = (scg_ctx *)calloc(1, sizeof(scg_ctx));
+    if (!c) return SCG_ENOMEM;
+    c->order = order; c->K = K; c->F = scg_pow4(order + 1);
+    size_t slab = (size_t)K * SCG_A * c->F * sizeof(float);
+    if (slab > 200 * 1024) {  // the CTA accumulator must fit in shared memory
+        free(c);
+        return SCG_ELIMIT;
+    }
+    c->n_partials = SCG_NUM_SMS * 8;
+    cudaError_t e = cudaMalloc((void **)&c->d_partial, slab * c->n_partials);
+    if (e != cudaSuccess) {
+        free(c);
+        return (int)e;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
+    if (!c) return 0;
+    if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_rec) cudaFree(c->d_rec);
+    for (int i = 0; i < 5 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
+    free(c->prof_ev);
+    free(c);
+    return 0;
+}
+
+extern "C" int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const float *y, const float *vx,
+                                const float *vy, const int *a, const int *option, const float *delta,
+                                const uint8_t *done, const uint8_t *mask, float gamma_lambda, float *trace, float *dW,
+                                int *cnt, void *stream) {
+    if (!ctx || B < 0) return SCG_EINVAL;
+    if (B == 0) return 0;
+    if (!x || !y || !vx || !vy || !a || !option || !delta || !done || !trace || !dW || !cnt) return SCG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B > ctx->rec_capacity) {
+        if (ctx->d_rec) cudaFree(ctx->d_rec);
+        ctx->d_rec = nullptr; ctx->rec_capacity = 0;
+        SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_rec, (size_t)B * SCG_REC_FLOATS * sizeof(float)));
+        ctx->rec_capacity = B;
+    }
+    int grid = std::max(1, std::min((B + 255) / 256, SCG_NUM_SMS * 8));
+    k_make_rec<<<grid, 256, 0, st>>>(B, x, y, vx, vy, a, option, delta, done, mask, ctx->K,
+                                     reinterpret_cast<float4 *>(ctx->d_rec), cnt);
+    SCG_LAUNCH_CHECK();
+    return scg_launch_trace(ctx, B, ctx->d_rec, trace, gamma_lambda, dW, st);
+}
+
+extern "C" int scg_apply(int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha, int window_steps,
+                         void *stream) {
+    if (K < 1 || K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
+    if (!W || !Wt || !dW || !cnt) return SCG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    float steps = (float)std::max(window_steps, 1);
+    int F = scg_pow4(order + 1);
+    int grid = std::max(1, std::min((K * SCG_A * F + 255) / 256, SCG_NUM_SMS * 8));
+    DISPATCH_ORDER(order, k_apply<N1><<<grid, 256, 0, st>>>(K, W, Wt, dW, cnt, alpha, steps));
+    SCG_LAUNCH_CHECK();
+    k_zero_int<<<1, 32, 0, st>>>(K, cnt);
+    SCG_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,395 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): single-step transitions bit-identical in collision
+(obstacle, edge) indices and terminal flags, next state within 1e-5 relative (we get bit-exact);
+Q values, TD errors and classifier probabilities within 1e-4 relative after a fixed number of
+updates on the same seeded transition batch.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.pinball import step_batched
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+@pytest.fixture(scope="module")
+def scg():
+    import skill_chaining_with_graphs_b200 as m
+    m.load_library()
+    return m
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+def _states(omap, n, seed, near_walls=False):
+    rng = np.random.default_rng(seed)
+    S = omap.sample_free_states(rng, n)
+    if near_walls:
+        # concentrate positions within ~1.5 ball radii of a random edge so most steps collide
+        e = omap.edges[rng.integers(0, omap.n_edges, n)]
+        t = rng.uniform(0, 1, n).astype(np.float32)
+        off = rng.uniform(-1.5, 1.5, n).astype(np.float32) * omap.ball_r
+        S[:, 0] = e[:, 0] + t * e[:, 2] + off * e[:, 5]
+        S[:, 1] = e[:, 1] + t * e[:, 3] + off * e[:, 6]
+    A = rng.integers(0, 5, n).astype(np.int32)
+    return S, A
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["easy", "hard"])
+def test_edge_table_matches_oracle(scg, name):
+    omap = oracle.PinballMap.from_name(name)
+    gmap = scg.PinballMap.from_name(name)
+    edges, obst, local = gmap.edge_table()
+    assert np.array_equal(edges.view(np.uint32), omap.edges.view(np.uint32))
+    assert np.array_equal(obst, omap.edge_obstacle)
+    assert np.array_equal(local, omap.edge_local)
+
+
+@pytest.mark.parametrize("name,near", [("easy", False), ("easy", True), ("hard", False), ("hard", True)])
+@pytest.mark.parametrize("cull", [True, False])
+def test_step_bit_exact(scg, torch, name, near, cull):
+    omap = oracle.PinballMap.from_name(name)
+    gmap = scg.PinballMap.from_name(name)
+    B = 20000
+    S, A = _states(omap, B, seed=11 + near, near_walls=near)
+    env = scg.PinballEnv(gmap, B, cull=cull)
+    env.reset(states=S)
+    ns, r, done, hit = env.step(torch.as_tensor(A).cuda())
+    ons, orr, ofl = step_batched(omap, S, A)
+    odone, okind, oobst, oedge = oracle.unpack_flags(ofl)
+    assert np.array_equal(env.flags.cpu().numpy(), ofl)
+    assert np.array_equal(done.cpu().numpy(), odone)
+    assert np.array_equal(hit.cpu().numpy(), np.stack([okind, oobst, oedge], axis=1))
+    assert np.array_equal(ns.cpu().numpy().view(np.uint32), ons.view(np.uint32))
+    assert np.array_equal(r.cpu().numpy(), orr)
+    if near:
+        assert (okind != 0).mean() > 0.2      # the case really exercises collisions
+
+
+def test_step_goal_and_bounds_cases(scg, torch):
+    omap = oracle.PinballMap.from_name("easy")
+    gmap = scg.PinballMap.from_name("easy")
+    tx, ty, tr = (float(v) for v in omap.target)
+    S = np.array([
+        [tx - 0.05, ty, 1.0, 0.0],       # flies into the goal
+        [tx, ty, 0.0, 0.0],              # starts inside the goal
+        [1.5, 0.5, 0.0, 0.0],            # outside the unit square: clamp, brute-force edge path
+        [-0.2, -0.3, 0.0, 0.0],
+        [0.5, 0.5, 0.0, 0.0],            # at rest in open space
+        [0.2, 0.9, 1.0, 1.0],            # start position, fast
+    ], dtype=np.float32)
+    for a in range(5):
+        A = np.full(len(S), a, dtype=np.int32)
+        env = scg.PinballEnv(gmap, len(S))
+        env.reset(states=S)
+        ns, r, done, hit = env.step(torch.as_tensor(A).cuda())
+        ons, orr, ofl = step_batched(omap, S, A)
+        assert np.array_equal(ns.cpu().numpy().view(np.uint32), ons.view(np.uint32))
+        assert np.array_equal(env.flags.cpu().numpy(), ofl)
+        assert np.array_equal(r.cpu().numpy(), orr)
+
+
+def test_step_empty_and_bad_actions(scg, torch):
+    gmap = scg.PinballMap.from_name("easy")
+    env = scg.PinballEnv(gmap, 0)
+    ns, r, done, hit = env.step(torch.zeros(0, dtype=torch.int32).cuda())
+    assert ns.shape == (0, 4)
+    env = scg.PinballEnv(gmap, 4)
+    with pytest.raises(ValueError):
+        env.step(torch.tensor([0, 1, 5, 2], dtype=torch.int32).cuda())
+    with pytest.raises(ValueError):
+        env.step(torch.tensor([0, 1], dtype=torch.int32).cuda())
+
+
+def test_step_host_path_matches_device_path(scg, torch):
+    omap = oracle.PinballMap.from_name("hard")
+    gmap = scg.PinballMap.from_name("hard")
+    B = 5000
+    S, A = _states(omap, B, seed=5)
+    env = scg.PinballEnv(gmap, B)
+    env.reset(states=S)
+    ns, r, done, hit = env.step(A)          # NumPy in -> host path
+    ons, orr, ofl = step_batched(omap, S, A)
+    assert isinstance(ns, np.ndarray)
+    assert np.array_equal(ns.view(np.uint32), ons.view(np.uint32))
+    assert np.array_equal(r, orr)
+
+
+def test_step_trajectory_roundtrip_many_steps(scg, torch):
+    """50 consecutive steps: GPU and oracle stay bit-identical because each step is."""
+    omap = oracle.PinballMap.from_name("easy")
+    gmap = scg.PinballMap.from_name("easy")
+    B = 2000
+    S, _ = _states(omap, B, seed=9)
+    rng = np.random.default_rng(1)
+    env = scg.PinballEnv(gmap, B)
+    env.reset(states=S)
+    cur = S.copy()
+    for t in range(50):
+        A = rng.integers(0, 5, B).astype(np.int32)
+        ns, r, done, hit = env.step(torch.as_tensor(A).cuda())
+        cur, orr, ofl = step_batched(omap, cur, A)
+        assert np.array_equal(ns.cpu().numpy().view(np.uint32), cur.view(np.uint32)), f"diverged at step {t}"
+
+
+def test_reset_matches_oracle(scg, torch):
+    omap = oracle.PinballMap(0.02, (0.9, 0.2, 0.04), [(0.2, 0.9), (0.5, 0.5), (0.1, 0.3)],
+                             [p.tolist() for p in oracle.PinballMap.from_name("easy").polygons])
+    gmap = scg.PinballMap(0.02, (0.9, 0.2, 0.04), [(0.2, 0.9), (0.5, 0.5), (0.1, 0.3)],
+                          [p.tolist() for p in omap.polygons])
+    B = 1000
+    oenv = oracle.PinballEnv(omap, B, seed=42, env_offset=7)
+    genv = scg.PinballEnv(gmap, B, seed=42, env_offset=7)
+    mask = np.random.default_rng(0).random(B) < 0.5
+    o = oenv.reset(mask=mask, step=5)
+    g = genv.reset(mask=mask, step=5)
+    assert np.array_equal(g.cpu().numpy(), o)
+    assert len(np.unique(o[:, 0])) == 3
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_features_match_oracle(scg, torch, order):
+    omap = oracle.PinballMap.from_name("easy")
+    S, _ = _states(omap, 512, seed=order)
+    S[:, 2:] *= 1.4                                          # exercise the sqrt(2) velocity range
+    phi = scg.FourierBasis(order).features(S).cpu().numpy()
+    ophi = oracle.FourierBasis(order).features(S)
+    assert phi.shape == ophi.shape
+    assert np.abs(phi - ophi).max() < 2e-5
+
+
+@pytest.mark.parametrize("order,K", [(3, 1), (3, 4), (5, 8), (2, 3)])
+def test_q_select_td_match_oracle(scg, torch, order, K):
+    omap = oracle.PinballMap.from_name("easy")
+    B = 3000
+    rng = np.random.default_rng(order * 10 + K)
+    S, A = _states(omap, B, seed=3)
+    S2, A2 = _states(omap, B, seed=4)
+    opt = rng.integers(0, K, B).astype(np.int32)
+    oset = oracle.OptionSet(K, order, B, gamma=0.97, seed=5, env_offset=100, epsilon=0.3)
+    gset = scg.OptionSet(K, order, B, gamma=0.97, seed=5, env_offset=100, epsilon=0.3)
+    W = (rng.standard_normal(oset.W.shape) * 0.05).astype(np.float32)
+    oset.W[:] = W
+    gset.set_weights(W)
+    oQ = oset.q(S, opt)
+    gQ = gset.q(S, opt).cpu().numpy()
+    assert rel_err(gQ, oQ) < RTOL
+    # selection: identical uniforms; feed the ORACLE's Q so argmax cannot flip on rounding
+    oa = oracle.option.epsilon_greedy(oQ, oset.epsilon, 5, oset.env_ids, 17, 0)
+    ga = gset.select(torch.as_tensor(oQ).cuda(), 17, 0).cpu().numpy()
+    assert np.array_equal(ga, oa)
+    r = rng.standard_normal(B).astype(np.float32)
+    done = rng.random(B) < 0.2
+    od = oset.td_error(S, A, r, S2, A2, done, opt)
+    gd = gset.td_error(S, A, r, S2, A2, done, opt).cpu().numpy()
+    assert rel_err(gd, od) < RTOL
+
+
+# ---- K3 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,K", [(3, 4), (1, 2), (2, 2), (4, 2), (5, 8)])
+def test_sarsa_updates_match_oracle(scg, torch, order, K):
+    """N updates on a fixed seeded transition batch with a sync every 2 steps: Q values, TD errors,
+    traces, dW and weights all within 1e-4 relative of the oracle."""
+    omap = oracle.PinballMap.from_name("easy")
+    B = 257 if order >= 4 else 1500
+    rng = np.random.default_rng(100 + order)
+    hp = dict(gamma=0.95, lam=0.8, alpha=0.05, seed=1)
+    oset = oracle.OptionSet(K, order, B, **hp)
+    gset = scg.OptionSet(K, order, B, **hp)
+    W = (rng.standard_normal(oset.W.shape) * 0.05).astype(np.float32)
+    oset.W[:] = W
+    gset.set_weights(W)
+    for it in range(6):
+        S, A = _states(omap, B, seed=20 + it)
+        S2, A2 = _states(omap, B, seed=40 + it)
+        opt = rng.integers(0, K, B).astype(np.int32)
+        r = rng.standard_normal(B).astype(np.float32)
+        done = rng.random(B) < 0.15
+        mask = None if it % 2 == 0 else (rng.random(B) < 0.8)
+        od = oset.update(S, A, r, S2, A2, done, opt, mask=mask)
+        gd = gset.update(S, A, r, S2, A2, done, opt, mask=mask).cpu().numpy()
+        oset.tick(); gset.tick()
+        assert rel_err(gd, od) < RTOL, f"TD error, update {it}"
+        assert rel_err(gset.trace.cpu().numpy(), oset.trace) < RTOL, f"trace, update {it}"
+        assert np.array_equal(gset.cnt.cpu().numpy(), oset.cnt), f"cnt, update {it}"
+        assert rel_err(gset.dW.cpu().numpy(), oset.dW) < RTOL, f"dW, update {it}"
+        if it % 2 == 1:
+            oset.apply(); gset.apply()
+            assert rel_err(gset.W.cpu().numpy(), oset.W) < RTOL, f"W after apply, update {it}"
+            assert float(gset.dW.abs().max()) == 0.0 and int(gset.cnt.sum()) == 0
+    S, _ = _states(omap, B, seed=99)
+    opt = rng.integers(0, K, B).astype(np.int32)
+    assert rel_err(gset.q(S, opt).cpu().numpy(), oset.q(S, opt)) < RTOL
+
+
+def test_sarsa_b1_classical(scg, torch):
+    """B = 1, sync every step: the classical Sarsa(lambda) rule."""
+    omap = oracle.PinballMap.from_name("easy")
+    hp = dict(gamma=0.9, lam=0.7, alpha=0.1, seed=1)
+    oset = oracle.OptionSet(1, 3, 1, **hp)
+    gset = scg.OptionSet(1, 3, 1, **hp)
+    gset.pack()
+    for it in range(5):
+        S, A = _states(omap, 1, seed=it)
+        S2, A2 = _states(omap, 1, seed=50 + it)
+        r = np.array([-1.0 - it], dtype=np.float32)
+        done = np.array([it == 4])
+        o = np.zeros(1, dtype=np.int32)
+        od = oset.update(S, A, r, S2, A2, done, o)
+        gd = gset.update(S, A, r, S2, A2, done, o).cpu().numpy()
+        oset.tick(); gset.tick(); oset.apply(); gset.apply()
+        assert rel_err(gd, od) < RTOL
+        assert rel_err(gset.W.cpu().numpy(), oset.W) < RTOL
+    assert float(gset.trace.abs().max()) == 0.0      # done on the last update zeroed the trace
+
+
+# ---- K4 ------------------------------------------------------------------------------------------
+def test_classifier_eval_grad_fit_match_oracle(scg, torch):
+    rng = np.random.default_rng(8)
+    K, B = 4, 4000
+    oset = oracle.OptionSet(K, 1, 1)
+    gset = scg.OptionSet(K, 1, 1)
+    theta = rng.standard_normal((K, 6)).astype(np.float32) * 2
+    oset.theta[:] = theta
+    gset.theta.copy_(torch.as_tensor(theta))
+    S = rng.random((B, 4)).astype(np.float32)
+    assert rel_err(gset.initiation_prob(S).cpu().numpy(), oset.initiation_prob(S)) < RTOL
+    X = rng.random((1000, 2)).astype(np.float32)
+    y = ((X[:, 0] - 0.6) ** 2 + (X[:, 1] - 0.4) ** 2 < 0.08).astype(np.uint8)
+    assert rel_err(gset.clf_grad(2, X, y).cpu().numpy(), oset.clf_grad(2, X, y)) < RTOL
+    oset.theta[1] = 0
+    gset.theta[1].zero_()
+    ot = oset.fit_initiation(1, X, y, steps=150, lr=2.0)
+    gt = gset.fit_initiation(1, X, y, steps=150, lr=2.0).cpu().numpy()
+    assert rel_err(gt, ot) < RTOL
+    op = oset.initiation_prob(np.concatenate([X, np.zeros_like(X)], axis=1))[:, 1]
+    gp = gset.initiation_prob(np.concatenate([X, np.zeros_like(X)], axis=1))[:, 1].cpu().numpy()
+    assert rel_err(gp, op) < RTOL
+
+
+# ---- fused agent step ------------------------------------------------------------------------------
+def _paired_agents(scg, torch, B, order, K, name, seed, **kw):
+    omap = oracle.PinballMap.from_name(name)
+    gmap = scg.PinballMap.from_name(name)
+    cfg = dict(map=name, batch=B, order=order, max_options=K, seed=seed, **kw)
+    S, A = _states(omap, B, seed=seed)
+    oag = oracle.SkillChainAgent(oracle.AgentConfig(**cfg), omap)
+    oag.env.reset(states=S)
+    oag.start_xy = oag.env.state[:, :2].copy()
+    gag = scg.SkillChainAgent(scg.AgentConfig(**cfg), gmap, initial_states=S)
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal(oag.options.W.shape) * 0.5).astype(np.float32)
+    oag.options.W[:] = W
+    gag.options.set_weights(W)
+    oag.action = A.copy()
+    gag.action.copy_(torch.as_tensor(A))
+    return oag, gag
+
+
+def test_agent_step_matches_oracle_one_step(scg, torch):
+    """One fused step from identical state and weights, with two active options so termination,
+    option reward, example recording, reset and re-selection all fire."""
+    B, K = 6000, 4
+    oag, gag = _paired_agents(scg, torch, B, 3, K, "easy", 2, sync_interval=3, option_timeout=3, epsilon=0.2)
+    theta = np.zeros((K, 6), dtype=np.float32)
+    theta[0] = [-1.0, 2.0, 0.0, 0.0, 0.0, 0.0]       # x >= 0.5
+    theta[1] = [-0.6, 0.0, 2.0, 0.0, 0.0, 0.0]       # y >= 0.3
+    for ag_active in (oag,):
+        ag_active.options.theta[:] = theta
+        ag_active.active[:2] = True
+        ag_active.n_active = 2
+        ag_active.parents[1] = 1
+        ag_active.parents[2] = 2
+    gag.options.theta.copy_(torch.as_tensor(theta))
+    gag.active_mask, gag.n_active = 3, 2
+    gag.parents_host[1], gag.parents_host[2] = 1, 2
+    gag._push_parents()
+    rng = np.random.default_rng(0)
+    opt = rng.integers(0, 3, B).astype(np.int32)
+    oag.option = opt.copy()
+    gag.option.copy_(torch.as_tensor(opt))
+    tq = rng.integers(0, 3, B).astype(np.int32)      # some envs are at the option timeout
+    oag.t_opt = tq.copy()
+    gag.t_opt.copy_(torch.as_tensor(tq))
+    out = oag.step()
+    gag.step()
+    torch.cuda.synchronize()
+    assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+    assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
+    assert np.array_equal(gag.option.cpu().numpy(), out["option"])
+    # actions come from an argmax over Q: compare where the oracle's top-2 gap is not a rounding tie
+    Q = oag.options.q(out["state"], out["option"])
+    top2 = np.sort(Q, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3 * np.abs(Q).max()
+    ga = gag.action.cpu().numpy()
+    assert clear.mean() > 0.9
+    assert np.array_equal(ga[clear], out["action"][clear])
+    assert np.array_equal(gag.t_opt.cpu().numpy(), oag.t_opt)
+    assert np.array_equal(gag.ep_steps.cpu().numpy(), oag.ep_steps)
+    assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success)
+    assert np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
+    assert np.array_equal(gag.ex_count.cpu().numpy(), oag.ex_count)
+    assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
+    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL
+    assert out["term"].sum() > 100 and out["hit"].sum() > 10
+    for k in range(K):                                # same example multiset per option
+        n = int(oag.ex_count[k])
+        ox = np.concatenate([oag.ex_xy[k, :n], oag.ex_label[k, :n, None].astype(np.float32)], axis=1)
+        gx = np.concatenate([gag.ex_xy[k, :n].cpu().numpy(),
+                             gag.ex_label[k, :n, None].cpu().numpy().astype(np.float32)], axis=1)
+        assert np.array_equal(ox[np.lexsort(ox.T)], gx[np.lexsort(gx.T)])
+
+
+def test_agent_multi_step_statistics(scg, torch):
+    """Several fused steps including a sync: weights stay close to the oracle's (trajectories can
+    differ only through argmax near-ties, which the tiny weights make rare)."""
+    B = 3000
+    oag, gag = _paired_agents(scg, torch, B, 3, 2, "easy", 4, sync_interval=2, epsilon=0.0, alpha=1e-4)
+    for _ in range(4):
+        oag.step()
+        gag.step()
+    torch.cuda.synchronize()
+    same = (gag.state.cpu().numpy() == oag.env.state).all(axis=1).mean()
+    assert same > 0.98
+    assert rel_err(gag.options.W.cpu().numpy(), oag.options.W) < 5e-3
+
+
+def test_agent_run_and_manage_promotes_option(scg, torch):
+    """The controller promotes the gestating option after enough successes and wires parents."""
+    B = 4096
+    gmap = scg.PinballMap.from_name("easy")
+    cfg = scg.AgentConfig(map="easy", batch=B, order=3, max_options=3, gestation_successes=8, option_timeout=40,
+                          sync_interval=4, epsilon=0.3)
+    rng = np.random.default_rng(0)
+    tx, ty, tr = gmap.target
+    S = np.zeros((B, 4), dtype=np.float32)                 # start next to the goal so hits happen
+    S[:, 0] = tx + rng.uniform(-0.12, 0.02, B)
+    S[:, 1] = ty + rng.uniform(-0.1, 0.1, B)
+    ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
+    for _ in range(48):
+        ag.step()
+    c = ag.counters()
+    assert c["n_success"][0] >= 8 and c["goals"] >= 8
+    assert ag.manage() is True
+    assert ag.n_active == 1 and ag.active_mask == 1 and int(ag.parents_host[1]) == 1
+    for _ in range(8):
+        ag.step()
+    torch.cuda.synchronize()
+    assert int((ag.option == 1).sum()) > 0                 # the new gestating option is being executed
