@@ -25,99 +25,148 @@ struct ControlArgs {
 };
 
 template <int N1>
-__global__ void __launch_bounds__(128) k_agent_control(const __grid_constant__ ControlArgs args) {
+__global__ void __launch_bounds__(32 * N1) k_agent_control(const __grid_constant__ ControlArgs args) {
     constexpr int F = N1 * N1 * N1 * N1;
+    __shared__ float zsh[2][4][2][32];           // [state][dim][cos, sin][lane]
+    __shared__ float part[N1][2 * SCG_A][32];    // [warp][q value][lane]
     const scg_agent_t &g = args.ag;
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(args.map_blob);
     const int K = g.K;
     const int gest = min(g.n_active, K - 1);
-    const float gl_unused = 0.f; (void)gl_unused;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < g.B; b += gridDim.x * blockDim.x) {
-        const uint32_t env = g.env_offset + (uint32_t)b;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < g.B; base += gridDim.x * 32) {
+        const bool valid = base + lane < g.B;
+        const int b = valid ? base + lane : g.B - 1;
         float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
         float nx = g.x2[b], ny = g.y2[b], nvx = g.vx2[b], nvy = g.vy2[b];
-        int a = g.action[b], o = g.option[b];
-        float r_env = g.reward[b];
-        bool env_done = (g.flags[b] & SCG_FLAG_DONE) != 0;
-        // 2-3: initiation bits of s2, termination, option reward
-        uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
-        uint32_t pm = g.parents[o];
-        bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
-        int t_opt = g.t_opt[b] + 1, ep = g.ep_steps[b] + 1;
-        bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
-        bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
-        bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
-        float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
-        // 4: Q_o(s, .) and Q_o(s2, .), a2, TD error
-        float2 za[4], zb[4];
-        scg_phasors(sx, sy, svx, svy, za);
-        scg_phasors(nx, ny, nvx, nvy, zb);
-        float qa[SCG_A], qb[SCG_A];
-        scg_q_pair<N1>(za, zb, g.Wt + (size_t)o * F * SCG_WT_STRIDE, qa, qb);
-        int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_ACTION));
-        float qsa = 0.f, qs2 = 0.f;
+        const int o = g.option[b];
+        // phasors of s and s2: warp w evaluates dimensions w, w + N1, ... and shares them
+        {
+            float sa[4], sb[4];
+            scg_normalise(sx, sy, svx, svy, sa);
+            scg_normalise(nx, ny, nvx, nvy, sb);
 #pragma unroll
-        for (int i = 0; i < SCG_A; ++i) {
-            qsa = (i == a) ? qa[i] : qsa;
-            qs2 = (i == a2) ? qb[i] : qs2;
+            for (int d = 0; d < 4; ++d) {
+                if (d % N1 == w) {
+                    float sn, cs;
+                    sincospif(sa[d], &sn, &cs);
+                    zsh[0][d][0][lane] = cs; zsh[0][d][1][lane] = sn;
+                    sincospif(sb[d], &sn, &cs);
+                    zsh[1][d][0][lane] = cs; zsh[1][d][1][lane] = sn;
+                }
+            }
         }
-        float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
-        g.delta[b] = delta;
-        // 5: hand the update to K3
-        float4 *rec = reinterpret_cast<float4 *>(g.rec) + (size_t)b * 3;
-        uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
-        rec[0] = make_float4(za[0].x, za[0].y, za[1].x, za[1].y);
-        rec[1] = make_float4(za[2].x, za[2].y, za[3].x, za[3].y);
-        rec[2] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
-        {   // cnt[o] += 1, one atomic per (warp, option)
-            uint32_t peers = __match_any_sync(__activemask(), o);
-            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(g.cnt + o, __popc(peers));
+        __syncthreads();
+        float2 za[4], zb[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            za[d] = make_float2(zsh[0][d][0][lane], zsh[0][d][1][lane]);
+            zb[d] = make_float2(zsh[1][d][0][lane], zsh[1][d][1][lane]);
         }
-        float ret = g.ep_return[b] + r_env;
-        // 6: example for option o's initiation classifier
-        if (term) {
-            int slot = atomicAdd(g.ex_count + o, 1) % (int)g.example_capacity;
-            size_t ei = (size_t)o * g.example_capacity + slot;
-            g.ex_xy[2 * ei] = g.start_xy[2 * b];
-            g.ex_xy[2 * ei + 1] = g.start_xy[2 * b + 1];
-            g.ex_label[ei] = hit ? 1 : 0;
-            atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
+        // 4a: this warp's share of Q_o(s, .) and Q_o(s2, .)
+        {
+            float qa[SCG_A], qb[SCG_A];
+            scg_q_pair_c0<N1>(w, za, zb, g.Wt + (size_t)o * F * SCG_WT_STRIDE, qa, qb);
+#pragma unroll
+            for (int i = 0; i < SCG_A; ++i) {
+                part[w][i][lane] = qa[i];
+                part[w][SCG_A + i][lane] = qb[i];
+            }
         }
-        // 7: env reset
-        bool reset = env_done || ep_timeout;
-        if (reset) {
-            uint4 rr = scg_draw(g.seed, env, g.step, SCG_STREAM_RESET);
-            int ns = mh->n_starts;
-            int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
-            const float2 *starts = reinterpret_cast<const float2 *>(args.map_blob + mh->off_starts);
-            float2 s0 = starts[pick];
-            nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
-            atomicAdd(g.stats + 0, 1);
-            if (env_done) atomicAdd(g.stats + 1, 1);
-            atomicAdd(reinterpret_cast<float *>(g.stats + 2), ret);
-            ret = 0.f;
-            ep = 0;
-            g.x2[b] = nx; g.y2[b] = ny; g.vx2[b] = nvx; g.vy2[b] = nvy;
+        __syncthreads();
+        if (w == 0 && valid) {
+            float qa[SCG_A], qb[SCG_A];
+#pragma unroll
+            for (int i = 0; i < SCG_A; ++i) {
+                float s0 = part[0][i][lane], s1 = part[0][SCG_A + i][lane];
+#pragma unroll
+                for (int ww = 1; ww < N1; ++ww) {
+                    s0 += part[ww][i][lane];
+                    s1 += part[ww][SCG_A + i][lane];
+                }
+                qa[i] = s0; qb[i] = s1;
+            }
+            const uint32_t env = g.env_offset + (uint32_t)b;
+            const int a = g.action[b];
+            const float r_env = g.reward[b];
+            const bool env_done = (g.flags[b] & SCG_FLAG_DONE) != 0;
+            // 2-3: initiation bits of s2, termination, option reward
+            uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
+            uint32_t pm = g.parents[o];
+            bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
+            int t_opt = g.t_opt[b] + 1, ep = g.ep_steps[b] + 1;
+            bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
+            bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
+            bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
+            float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
+            // 4b: a2, TD error
+            int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_ACTION));
+            float qsa = 0.f, qs2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < SCG_A; ++i) {
+                qsa = (i == a) ? qa[i] : qsa;
+                qs2 = (i == a2) ? qb[i] : qs2;
+            }
+            float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
+            g.delta[b] = delta;
+            // 5: hand the update to K3
+            float4 *rec = reinterpret_cast<float4 *>(g.rec) + (size_t)b * 3;
+            uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
+            rec[0] = make_float4(za[0].x, za[0].y, za[1].x, za[1].y);
+            rec[1] = make_float4(za[2].x, za[2].y, za[3].x, za[3].y);
+            rec[2] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
+            {   // cnt[o] += 1, one atomic per (warp, option)
+                uint32_t peers = __match_any_sync(__activemask(), o);
+                if ((__ffs(peers) - 1) == lane) atomicAdd(g.cnt + o, __popc(peers));
+            }
+            float ret = g.ep_return[b] + r_env;
+            // 6: example for option o's initiation classifier
+            if (term) {
+                int eslot = atomicAdd(g.ex_count + o, 1) % (int)g.example_capacity;
+                size_t ei = (size_t)o * g.example_capacity + eslot;
+                g.ex_xy[2 * ei] = g.start_xy[2 * b];
+                g.ex_xy[2 * ei + 1] = g.start_xy[2 * b + 1];
+                g.ex_label[ei] = hit ? 1 : 0;
+                atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
+            }
+            // 7: env reset
+            bool reset = env_done || ep_timeout;
+            if (reset) {
+                uint4 rr = scg_draw(g.seed, env, g.step, SCG_STREAM_RESET);
+                int ns = mh->n_starts;
+                int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
+                const float2 *starts = reinterpret_cast<const float2 *>(args.map_blob + mh->off_starts);
+                float2 s0 = starts[pick];
+                nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
+                atomicAdd(g.stats + 0, 1);
+                if (env_done) atomicAdd(g.stats + 1, 1);
+                atomicAdd(reinterpret_cast<float *>(g.stats + 2), ret);
+                ret = 0.f;
+                ep = 0;
+                g.x2[b] = nx; g.y2[b] = ny; g.vx2[b] = nvx; g.vy2[b] = nvy;
+            }
+            g.ep_return[b] = ret;
+            g.ep_steps[b] = ep;
+            // 8: option re-selection (rare: this lane walks all F features of the new option alone)
+            int o_next = o, a_next = a2;
+            if (term) {
+                uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
+                o_next = bn ? (__ffs(bn) - 1) : gest;
+                float2 zn[4];
+                if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
+                else { zn[0] = zb[0]; zn[1] = zb[1]; zn[2] = zb[2]; zn[3] = zb[3]; }
+                float qn[SCG_A];
+                scg_q_one<N1>(zn, g.Wt + (size_t)o_next * F * SCG_WT_STRIDE, qn);
+                a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_RESELECT));
+                t_opt = 0;
+                g.start_xy[2 * b] = nx;
+                g.start_xy[2 * b + 1] = ny;
+            }
+            g.t_opt[b] = t_opt;
+            g.option[b] = o_next;
+            g.action[b] = a_next;
         }
-        g.ep_return[b] = ret;
-        g.ep_steps[b] = ep;
-        // 8: option re-selection
-        int o_next = o, a_next = a2;
-        if (term) {
-            uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
-            o_next = bn ? (__ffs(bn) - 1) : gest;
-            float2 zn[4];
-            scg_phasors(nx, ny, nvx, nvy, zn);
-            float qn[SCG_A];
-            scg_q_one<N1>(zn, g.Wt + (size_t)o_next * F * SCG_WT_STRIDE, qn);
-            a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_RESELECT));
-            t_opt = 0;
-            g.start_xy[2 * b] = nx;
-            g.start_xy[2 * b + 1] = ny;
-        }
-        g.t_opt[b] = t_opt;
-        g.option[b] = o_next;
-        g.action[b] = a_next;
+        __syncthreads();
     }
 }
 
@@ -137,8 +186,8 @@ extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, const scg_ag
     ControlArgs args;
     args.ag = *ag;
     args.map_blob = map->d_blob;
-    int grid = std::max(1, std::min((ag->B + 127) / 128, SCG_NUM_SMS * 16));
-    DISPATCH_ORDER(ag->order, k_agent_control<N1><<<grid, 128, 0, st>>>(args));
+    int grid = std::max(1, std::min((ag->B + 31) / 32, SCG_NUM_SMS * 32));
+    DISPATCH_ORDER(ag->order, k_agent_control<N1><<<grid, 32 * N1, 0, st>>>(args));
     SCG_LAUNCH_CHECK();
     if (ev) SCG_CUDA_OK(cudaEventRecord(ev[2], st));
     return scg_launch_trace(ctx, ag->B, ag->rec, ag->trace, ag->gamma * ag->lambda, ag->dW, st, ev ? ev + 3 : nullptr);

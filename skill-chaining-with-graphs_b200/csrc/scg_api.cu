@@ -7,7 +7,7 @@ extern "C" const char *scg_error_string(int code) {
     if (code == 0) return "ok";
     if (code == SCG_EINVAL) return "scg: invalid argument";
     if (code == SCG_ENOMEM) return "scg: host allocation failed";
-    if (code == SCG_ELIMIT) return "scg: size exceeds a compiled-in limit (order 1..5, K <= 16, K*5*F*4 <= 200 KiB)";
+    if (code == SCG_ELIMIT) return "scg: size exceeds a compiled-in limit (order 1..5, K <= 16, K*5*F*4 <= 227 KiB)";
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "scg: unknown error";
 }

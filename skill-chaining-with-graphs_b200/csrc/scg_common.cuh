@@ -239,6 +239,58 @@ __device__ __forceinline__ uint32_t scg_init_bits(const float *__restrict__ thet
     return bits;
 }
 
+// ---- one warp per leading multi-index digit ---------------------------------------------------
+// The hot control kernel runs N1 warps over the same 32 envs: warp w sums the features whose
+// multi-index has c0 = w (a quarter of them at order 3), lane l is env l.  Every lane of a warp
+// reads the same packed-weight address (one L1 wavefront when the 32 envs share an option), and
+// N1 times more threads than one-per-env keep the FP32 pipe fed at B = 65,536.  The partial Q
+// vectors meet in shared memory.
+template <int N1>
+__device__ __forceinline__ void scg_q_pair_c0(int c0, const float2 za[4], const float2 zb[4],
+                                              const float *__restrict__ Wt_o, float qa[SCG_A], float qb[SCG_A]) {
+    float2 pa[N1], pb[N1];
+    pa[0] = pb[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < N1; ++c) {
+        pa[c] = scg_cmul(pa[c - 1], za[3]);
+        pb[c] = scg_cmul(pb[c - 1], zb[3]);
+    }
+#pragma unroll
+    for (int a = 0; a < SCG_A; ++a) qa[a] = qb[a] = 0.f;
+    float2 a01 = make_float2(1.f, 0.f), b01 = a01;
+    for (int i = 0; i < c0; ++i) {          // z0^c0 (c0 is warp-uniform)
+        a01 = scg_cmul(a01, za[0]);
+        b01 = scg_cmul(b01, zb[0]);
+    }
+    const float4 *w = reinterpret_cast<const float4 *>(Wt_o) + 2 * (c0 * N1 * N1 * N1);
+    for (int c1 = 0; c1 < N1; ++c1) {
+        float2 a012 = a01, b012 = b01;
+        for (int c2 = 0; c2 < N1; ++c2) {
+#pragma unroll
+            for (int c3 = 0; c3 < N1; ++c3) {
+                float fa = fmaf(a012.x, pa[c3].x, -a012.y * pa[c3].y);
+                float fb = fmaf(b012.x, pb[c3].x, -b012.y * pb[c3].y);
+                float4 wa = __ldg(w), wb = __ldg(w + 1);
+                w += 2;
+                qa[0] = fmaf(wa.x, fa, qa[0]);
+                qa[1] = fmaf(wa.y, fa, qa[1]);
+                qa[2] = fmaf(wa.z, fa, qa[2]);
+                qa[3] = fmaf(wa.w, fa, qa[3]);
+                qa[4] = fmaf(wb.x, fa, qa[4]);
+                qb[0] = fmaf(wa.x, fb, qb[0]);
+                qb[1] = fmaf(wa.y, fb, qb[1]);
+                qb[2] = fmaf(wa.z, fb, qb[2]);
+                qb[3] = fmaf(wa.w, fb, qb[3]);
+                qb[4] = fmaf(wb.x, fb, qb[4]);
+            }
+            a012 = scg_cmul(a012, za[2]);
+            b012 = scg_cmul(b012, zb[2]);
+        }
+        a01 = scg_cmul(a01, za[1]);
+        b01 = scg_cmul(b01, zb[1]);
+    }
+}
+
 __device__ __forceinline__ float scg_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
