@@ -188,7 +188,8 @@ class SkillChainAgent:
             return False
         X, y = self.examples(g)
         self.options.theta[g] = 0
-        self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
+        if len(X):
+            self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
         self.active[g] = True
         self.n_active += 1
         n = self.n_active

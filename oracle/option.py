@@ -18,6 +18,17 @@ Batched semantics (definition):
     then zeroes dW, cnt.  With B = 1 and a sync every step this is classical Sarsa(lambda).
   * multi-GPU: dW and cnt are summed over ranks before apply() (sharding-invariant).
 
+Windowed (forward-view) form, `OptionSet(..., windowed=True)`: because the
+weights are frozen between syncs, the TD errors of a window do not depend on the traces, so the
+per-step sweep "decay e, add phi, dW += delta e" can be replaced by recording (s, a, delta, done,
+option) per step and, at the end of the window, for each env over its recorded steps i = 0..n-1
+      G_i = delta_i + (0 if done_i else gamma*lambda * G_{i+1}),  G_n = 0
+      dW[o_i][a_i] += G_i phi(s_i) ;   dW[o_0] += gamma*lambda * G_0 * e_start
+      e_end = (0 if any done else (gamma*lambda)^n) e_start + sum_i c_i phi(s_i) (x) a_i,
+      c_i = (gamma*lambda)^(n-1-i) if no done at any step >= i else 0
+  which is algebraically the same sum (tests/test_oracle_option.py checks the two forms equal).
+  It assumes what the agent guarantees: an env changes option only after a step with done = True.
+
 Initiation classifier of option k: p = sigmoid(theta_k . psi(x, y)), psi = (1, x, y, x^2, xy, y^2);
 I_k(s) = p >= 0.5.  fit: theta -= lr * mean_i (p_i - y_i) psi_i, a fixed number of steps.
 """
@@ -59,8 +70,10 @@ class OptionSet:
     per-env traces (B, A, F), window accumulators dW (K, A, F) / cnt (K,)."""
 
     def __init__(self, n_options, order, batch, gamma=0.99, lam=0.9, alpha=1e-3, epsilon=0.05,
-                 seed=0, env_offset=0):
+                 seed=0, env_offset=0, windowed=False):
         self.K = int(n_options)
+        self.windowed = bool(windowed)
+        self._win = []
         self.basis = FourierBasis(order)
         self.F = self.basis.n_features
         self.B = int(batch)
@@ -113,6 +126,11 @@ class OptionSet:
             mask = np.ones(B, dtype=bool)
         delta = self.td_error(s, a, r, s2, a2, done, option_ids)
         delta = np.where(mask, delta, f32(0.0)).astype(np.float32)
+        if self.windowed:
+            self._win.append((np.array(s, dtype=np.float32).reshape(B, 4), a.astype(np.int32).copy(), delta.copy(),
+                              done.copy(), option_ids.astype(np.int32).copy(), np.asarray(mask, dtype=bool).copy()))
+            self.cnt += np.bincount(option_ids[mask], minlength=self.K)[: self.K]
+            return delta
         phi = self.basis.features(s)
         gl = f32(self.gamma * self.lam)
         sel = np.nonzero(mask)[0]
@@ -127,12 +145,63 @@ class OptionSet:
         self.trace[sel[done[sel]]] = 0
         return delta
 
+    def flush(self):
+        """Windowed mode: fold the recorded steps into dW and the traces (see module docstring)."""
+        if not self._win:
+            return
+        T, B = len(self._win), self.B
+        gl = np.float64(f32(self.gamma * self.lam))
+        act = np.stack([w[5] for w in self._win])                  # (T, B)
+        dn = np.stack([w[3] for w in self._win]) & act
+        dl = np.stack([w[2] for w in self._win]).astype(np.float64)
+        G = np.zeros((T + 1, B))
+        c = np.zeros((T, B))
+        cc = np.ones(B)
+        dead = np.zeros(B, dtype=bool)
+        nxt = np.zeros(B)
+        for t in range(T - 1, -1, -1):
+            a_t = act[t]
+            g = dl[t] + np.where(dn[t], 0.0, gl * nxt)
+            G[t] = np.where(a_t, g, nxt)
+            nxt = G[t]
+            dead |= dn[t]
+            c[t] = np.where(a_t & ~dead, cc, 0.0)
+            cc = np.where(a_t, cc * gl, cc)
+        e_scale = np.where(dead, 0.0, cc)
+        # carry-in: the trace at the window start belongs to the option of the env's first recorded step
+        first = np.argmax(act, axis=0)
+        has = act.any(axis=0)
+        o0 = np.stack([w[4] for w in self._win])[first, np.arange(B)]
+        carry = np.where(has, gl * G[0], 0.0)
+        e0 = self.trace.astype(np.float64)
+        for k in range(self.K):
+            mk = has & (o0 == k)
+            if mk.any():
+                self.dW[k] += np.tensordot(carry[mk], e0[mk], axes=(0, 0))
+        e = e0 * e_scale[:, None, None]
+        idx = np.arange(B)
+        for t in range(T):
+            s_t, a_t, _, _, o_t, m_t = self._win[t]
+            phi = self.basis.features(s_t).astype(np.float64)
+            for k in range(self.K):
+                mk = m_t & (o_t == k)
+                if not mk.any():
+                    continue
+                for a in range(N_ACTIONS):
+                    mka = mk & (a_t == a)
+                    if mka.any():
+                        self.dW[k, a] += G[t][mka] @ phi[mka]
+            e[idx, a_t] += np.where(m_t, c[t], 0.0)[:, None] * phi
+        self.trace[:] = e.astype(np.float32)
+        self._win = []
+
     def tick(self):
         """Call once per env step of the window (after update)."""
         self.window_steps += 1
 
     def apply(self, dW=None, cnt=None):
         """Fold the window's accumulated delta into W (after any cross-rank sum)."""
+        self.flush()
         dW = self.dW if dW is None else dW
         cnt = self.cnt if cnt is None else cnt
         steps = max(self.window_steps, 1)

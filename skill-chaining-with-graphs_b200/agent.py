@@ -19,6 +19,7 @@ from . import _lib
 from ._lib import check, ptr, AgentStruct, GOAL_BIT, N_ACTIONS
 from .option import OptionSet
 from .pinball import PinballMap
+from .sync import allreduce_deltas
 
 
 @dataclass
@@ -183,11 +184,7 @@ class SkillChainAgent:
     def sync(self):
         """All-reduce the window's dW / cnt over ranks (if any) and apply."""
         o = self.options
-        if self.pg is not None or (self.torch.distributed.is_available() and self.torch.distributed.is_initialized()
-                                   and self.torch.distributed.get_world_size() > 1):
-            dist = self.torch.distributed
-            dist.all_reduce(o.dW, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(o.cnt, op=dist.ReduceOp.SUM, group=self.pg)
+        allreduce_deltas(o.dW, o.cnt, self.pg)
         o.apply()
 
     # -- low-rate controller ---------------------------------------------------------------------
