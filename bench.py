@@ -4,16 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one lock-step agent step over the whole env batch: env step (K1) -> initiation
-classifiers + Q evaluation + eps-greedy + TD error (K2+K4) -> Sarsa(lambda) trace sweep and weight
-delta accumulation (K3), with the weight apply / cross-GPU allreduce every `sync_interval` steps.
+A "step" is one lock-step agent step over the whole env batch: ONE fused kernel does env step (K1) ->
+initiation classifiers + Q evaluation + eps-greedy + TD error (K2+K4) -> 32-byte step record; every
+`sync_interval` steps the window's records are folded into the traces and weight deltas by one
+Sarsa(lambda) sweep (K3, forward-view form), followed by the cross-GPU allreduce and the weight apply.
 Workload at every N: BASELINE.json configs[1] per GPU - Pinball 'easy', 65,536 envs, order-3 Fourier
 basis, 4 option slots with 2 active logistic initiation classifiers (weak scaling: each rank owns
 its own 65,536-env slice).  Synthetic data: random free-space start states, random-init weights.
 
 Prints ONE JSON line (rank 0).  `value` = env-steps of all ranks / max-over-ranks device time with
 state resident in HBM; `e2e` = same through SkillChainAgent.step_host (host buffers, H2D and D2H
-inside the timed region); `roofline` = the trace-sweep kernel's algorithmic bytes / its CUDA-event
+inside the timed region); `roofline` = the window trace-sweep kernel's algorithmic bytes / its CUDA-event
 time against the measured HBM copy peak; `cpu_baseline` = the NumPy oracle timed on this box.
 --impl reference times the stand-in reference (the NumPy oracle: the reference repository has no
 code) on all host cores for the same metric.
@@ -51,8 +52,8 @@ def config_json(args, n_gpus):
         "envs_per_gpu": args.batch, "global_envs": args.batch * n_gpus, "order": args.order,
         "options": args.options, "sync_interval": args.sync_interval, "map": args.map,
         "parallelism": f"env-sharded x{n_gpus}, allreduce(dW, cnt) every sync interval",
-        "l2": f"per-step working set {args.batch * 5 * F * 4 / 2**20:.0f} MiB of traces per GPU > 126 MiB L2 "
-              "(inputs larger than L2; no explicit flush)",
+        "l2": f"traces {args.batch * 5 * F * 4 / 2**20:.0f} MiB per GPU > 126 MiB L2, swept once per window between 8 "
+              "step kernels (inputs larger than L2; no explicit flush)",
     }
 
 
@@ -213,31 +214,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        ag.step()
+    ag.run(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # ---- timed region: exactly K steps, device-resident ----
     launches0 = lib.scg_launch_count()
-    ag.profile_begin(args.steps)
+    ag.profile_begin(4 * args.steps + 16)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        ag.step()
+    ag.run(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    stage_ms, prof_steps = ag.profile_end()
+    kind_ms, kind_n = ag.profile_end()
     launches = lib.scg_launch_count() - launches0
     # ---- e2e: same K steps through the host-buffer API ----
     hs = ag.s.cpu().numpy().copy()
     ha = ag.action.cpu().numpy().copy()
     for _ in range(3):
         s2, r, f, a2, d = ag.step_host(hs, ha)
-        hs, ha = s2.copy(), a2.copy()
+        hs, ha = s2, a2
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -259,15 +258,18 @@ def run_ours(args):
             peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-        bytes_per_env = 8 * 5 * F + 48                 # trace read + write, plus the 48-byte record
-        k3_ms = stage_ms[2] / max(prof_steps, 1)
+        T = ag.win_cap
+        bytes_per_env = 8 * 5 * F + 32 * T              # trace read + write once per window, T 32-byte records
+        avg = lambda k: kind_ms[k] / kind_n[k] if kind_n[k] else 0.0
+        k3_ms = avg(1)
         achieved = B * bytes_per_env / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-        step_ms = sum(stage_ms) / max(prof_steps, 1)
+        tot_ms = sum(kind_ms)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch") if tj.get("kernel") == "k_window" else None
             except Exception:
                 traffic = None
         line = {
@@ -275,13 +277,15 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_json(args, world),
-            "roofline": {"kernel": "k_trace (K3 Sarsa(lambda) trace sweep)", "bound": "hbm", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"kernel": "k_window (K3 Sarsa(lambda) trace sweep, forward-view window form)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": which, "algorithmic_bytes_per_launch": B * bytes_per_env,
-                         "avg_launch_ms": k3_ms, "share_of_step": (k3_ms / step_ms) if step_ms else None},
-            "stages_ms_per_step": {"k1_step": stage_ms[0] / max(prof_steps, 1),
-                                   "k2_k4_control": stage_ms[1] / max(prof_steps, 1),
-                                   "k3_trace": k3_ms, "dw_reduce": stage_ms[3] / max(prof_steps, 1)},
+                         "bytes_per_env_step": bytes_per_env / T, "window_steps": T,
+                         "avg_launch_ms": k3_ms, "launches": kind_n[1],
+                         "share_of_step": (kind_ms[1] / tot_ms) if tot_ms else None},
+            "stages_ms_per_step": {"fused_step_k1_k2_k4": kind_ms[0] / args.steps, "k3_window_sweep": kind_ms[1] / args.steps,
+                                   "dw_reduce": kind_ms[2] / args.steps, "apply": kind_ms[3] / args.steps,
+                                   "fused_step_avg_launch_ms": avg(0)},
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": B * ag.HOST_H2D_BYTES_PER_ENV,
                     "d2h_bytes_per_step": B * ag.HOST_D2H_BYTES_PER_ENV,

@@ -85,7 +85,8 @@ int scg_step_host(const scg_map_t *map, int B, float *state_soa /* HOST [4][B] i
 
 /* ---- K2: Fourier features, Q evaluation, action selection, TD error ------------------------
  * mirrors oracle/fourier.py FourierBasis.features, oracle/option.py OptionSet.q / act / td_error.
- * W is [K][A][F]; Wt is the packed copy [K][F][8] made by scg_pack_weights (or scg_apply). */
+ * W is [K][A][F]; Wt is the packed copy [F][K][8] (feature-major, 5 actions + 3 pad per option) made
+ * by scg_pack_weights (or scg_apply). */
 int scg_features(int order, int B, const float *x, const float *y, const float *vx, const float *vy,
                  float *phi /* [B][F] */, void *stream);
 int scg_pack_weights(int order, int K, const float *W, float *Wt, void *stream);
@@ -119,26 +120,35 @@ int scg_clf_grad(int N, const float *X /* [N][2] */, const uint8_t *y, const flo
 int scg_clf_fit(int N, const float *X, const uint8_t *y, float *theta_k /* [6] in/out */, int steps,
                 float lr, void *stream);
 
-/* ---- fused agent step (K1 -> K2 + K4 -> K3), mirrors oracle/agent.py SkillChainAgent.step ---- */
+/* ---- fused agent pipeline, mirrors oracle/agent.py SkillChainAgent.step ------------------------
+ * One step = ONE kernel: env step (K1) -> initiation bits of s' (K4) -> termination / option reward ->
+ * Q_o(s', .) (K2) -> eps-greedy a' -> TD error -> 32-byte step record -> env reset -> option re-selection.
+ * Q_o(s, a) is carried from the previous step (q_carry) while the weights are unchanged.
+ * Sarsa(lambda) runs in the windowed (forward-view) form of oracle/option.py OptionSet.flush: the step
+ * records of up to win_cap steps are folded into dW and the per-env traces by ONE trace sweep per
+ * window (scg_agent_flush), so the dense traces are read and written once per window, not per step. */
+#define SCG_WIN_MAX 32
 typedef struct scg_agent {
     /* sizes and hyper-parameters */
     int32_t B, K, order, n_active;
     uint32_t active_mask, env_offset, step, example_capacity;
     uint64_t seed;
     float gamma, lambda, epsilon, option_bonus;
-    int32_t option_timeout, max_episode_steps, cull, reserved0;
+    int32_t option_timeout, max_episode_steps, cull, carry_valid;
+    float alpha; int32_t window_steps, win_cap, win_len;
     /* per-env state (device) */
     float *x, *y, *vx, *vy;          /* current state s */
-    float *x2, *y2, *vx2, *vy2;      /* scratch for s'; holds the next state after the call */
+    float *x2, *y2, *vx2, *vy2;      /* the other state buffer: a step writes s' here, then the two swap */
     int32_t *action, *option, *t_opt, *ep_steps;
     float *start_xy;                 /* [B][2] position where the current option execution began */
     float *ep_return;                /* [B] running task return */
     float *reward; int32_t *flags;   /* [B] outputs of the env step */
     float *delta;                    /* [B] TD errors of this step */
-    float *rec;                      /* [B][12] update records (K2 -> K3) */
-    float *trace;                    /* [B][A][F] */
+    float *q_carry;                  /* [B] Q_o(s, a) of the pending (state, action), valid iff carry_valid */
+    float *win_rec;                  /* [win_cap][B][8] step records of the open window */
+    float *trace;                    /* [B][A][F], as of the last flush */
     /* per-option state (device) */
-    float *W, *Wt, *theta, *dW;      /* [K][A][F], [K][F][8], [K][6], [K][A][F] */
+    float *W, *Wt, *theta, *dW;      /* [K][A][F], [F][K][8], [K][6], [K][A][F] */
     int32_t *cnt;                    /* [K] */
     uint32_t *parents;               /* [K] */
     float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */
@@ -147,25 +157,32 @@ typedef struct scg_agent {
     int32_t *stats;
 } scg_agent_t;
 
-/* One lock-step agent step.  After it returns, (x2,y2,vx2,vy2) hold the next state: the caller
- * swaps the two state sets (scg_agent_swap does it on the struct) before the next call. */
-int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag, void *stream);
-void scg_agent_swap(scg_agent_t *ag);
+/* One lock-step agent step.  Updates the struct: swaps (x..vy) with (x2..vy2) so that x..vy is the new
+ * current state, step += 1, window_steps += 1, win_len += 1, carry_valid = 1; flushes the window when
+ * win_len reaches win_cap.  Clear carry_valid whenever state, action, option or weights are changed
+ * from outside (scg_apply changes the weights: callers clear it after every apply). */
+int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
+/* Fold the open window into dW and the traces (no-op when win_len == 0). */
+int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
+/* n_steps steps in one call; when sync_interval > 0 (single rank) also flush + scg_apply every
+ * sync_interval steps.  With sync_interval == 0 the caller flushes, all-reduces dW / cnt and applies. */
+int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n_steps, int sync_interval,
+                  void *stream);
 
 /* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
  * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]
  * host->device, runs the fused step, copies next state, reward, flags, next action and TD error
  * device->host and waits for them.  Traces and weights stay resident on the device. */
-int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag,
+int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag,
                         const float *h_state_soa, const int *h_action, float *h_state2_soa,
                         float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
 
-/* Per-kernel device timing of scg_agent_step with CUDA events on the launch stream.
- * scg_profile_begin arms it (up to max_steps steps are recorded); scg_profile_end waits for the
- * recorded events and returns the summed milliseconds of each stage:
- * ms[0] K1 step, ms[1] K2+K4 control, ms[2] K3 trace sweep, ms[3] dW reduction; *steps = steps seen. */
-int scg_profile_begin(scg_ctx_t *ctx, int max_steps);
-int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [4] */, int *steps);
+/* Per-kernel device timing of the agent pipeline with CUDA events on the launch stream.
+ * scg_profile_begin arms it (up to max_events kernel launches are recorded); scg_profile_end waits for
+ * the recorded events and returns, per kind, the summed milliseconds and the launch count:
+ * kind 0 fused step kernel, 1 window trace sweep, 2 dW reduction, 3 weight apply. */
+int scg_profile_begin(scg_ctx_t *ctx, int max_events);
+int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [4] */, int *count /* HOST [4] */);
 
 /* kernel launch counter (this library's launches since load), for bench.py's gpu_launches */
 uint64_t scg_launch_count(void);

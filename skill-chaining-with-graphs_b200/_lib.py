@@ -10,6 +10,7 @@ N_ACTIONS = 5
 N_PSI = 6
 MAX_OPTIONS = 16
 MAX_ORDER = 5
+WIN_MAX = 32
 GOAL_BIT = 0x80000000
 STREAM_ACTION, STREAM_RESET, STREAM_RESELECT = 0, 1, 2
 
@@ -27,13 +28,14 @@ class AgentStruct(C.Structure):
         ("seed", C.c_uint64),
         ("gamma", C.c_float), ("lam", C.c_float), ("epsilon", C.c_float), ("option_bonus", C.c_float),
         ("option_timeout", C.c_int32), ("max_episode_steps", C.c_int32), ("cull", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("carry_valid", C.c_int32),
+        ("alpha", C.c_float), ("window_steps", C.c_int32), ("win_cap", C.c_int32), ("win_len", C.c_int32),
         ("x", C.c_void_p), ("y", C.c_void_p), ("vx", C.c_void_p), ("vy", C.c_void_p),
         ("x2", C.c_void_p), ("y2", C.c_void_p), ("vx2", C.c_void_p), ("vy2", C.c_void_p),
         ("action", C.c_void_p), ("option", C.c_void_p), ("t_opt", C.c_void_p), ("ep_steps", C.c_void_p),
         ("start_xy", C.c_void_p), ("ep_return", C.c_void_p),
-        ("reward", C.c_void_p), ("flags", C.c_void_p), ("delta", C.c_void_p), ("rec", C.c_void_p),
-        ("trace", C.c_void_p),
+        ("reward", C.c_void_p), ("flags", C.c_void_p), ("delta", C.c_void_p), ("q_carry", C.c_void_p),
+        ("win_rec", C.c_void_p), ("trace", C.c_void_p),
         ("W", C.c_void_p), ("Wt", C.c_void_p), ("theta", C.c_void_p), ("dW", C.c_void_p),
         ("cnt", C.c_void_p), ("parents", C.c_void_p),
         ("ex_xy", C.c_void_p), ("ex_label", C.c_void_p),
@@ -70,10 +72,11 @@ _SIGS = {
     "scg_clf_grad": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "scg_clf_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_float, _P]),
     "scg_agent_step": (C.c_int, [_P, _P, C.POINTER(AgentStruct), _P]),
-    "scg_agent_swap": (None, [C.POINTER(AgentStruct)]),
+    "scg_agent_flush": (C.c_int, [_P, C.POINTER(AgentStruct), _P]),
+    "scg_agent_run": (C.c_int, [_P, _P, C.POINTER(AgentStruct), C.c_int, C.c_int, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
     "scg_profile_begin": (C.c_int, [_P, C.c_int]),
-    "scg_profile_end": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "scg_profile_end": (C.c_int, [_P, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGS)

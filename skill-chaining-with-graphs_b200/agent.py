@@ -1,7 +1,8 @@
-"""Batched skill-chaining agent on B200: the fused lock-step step (K1 -> K2+K4 -> K3), the low-rate
-option-creation controller, and the cross-GPU weight-delta sync.  Same interface and semantics as
-the CPU oracle's SkillChainAgent (oracle/agent.py, which stands in for the reference - the
-reference has no code: /root/reference/README.md:1-2).
+"""Batched skill-chaining agent on B200: the fused lock-step step (one kernel: K1 + K2 + K4), the
+windowed Sarsa(lambda) sweep (K3, once per window), the low-rate option-creation controller, and the
+cross-GPU weight-delta sync.  Same interface and semantics as the CPU oracle's SkillChainAgent
+(oracle/agent.py, which stands in for the reference - the reference has no code:
+/root/reference/README.md:1-2).
 
     agent = SkillChainAgent(AgentConfig(map="easy", batch=65536, max_options=4))
     stats = agent.run_episode(max_steps=2000)
@@ -19,7 +20,7 @@ from . import _lib
 from ._lib import check, ptr, AgentStruct, GOAL_BIT, N_ACTIONS
 from .option import OptionSet
 from .pinball import PinballMap
-from .sync import allreduce_deltas
+from .sync import allreduce_deltas, allreduce_scalar_sum, world_size
 
 
 @dataclass
@@ -44,6 +45,7 @@ class AgentConfig:
     clf_lr: float = 1.0
     graph: bool = False
     cull: bool = True
+    window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
 
 
 class SkillChainAgent:
@@ -61,11 +63,13 @@ class SkillChainAgent:
         self.device = dev
         self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon, cfg.seed,
                                  cfg.env_offset, dev)
-        F = self.options.F
+        self.options._pre_read = self.flush        # dW / trace reads see the open window folded in
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        self.s = torch.zeros((4, B), **f32)
-        self.s2 = torch.zeros((4, B), **f32)
+        self.win_cap = int(cfg.window) if cfg.window else max(1, min(int(cfg.sync_interval), 8))
+        if not 1 <= self.win_cap <= _lib.WIN_MAX:
+            raise ValueError(f"window must be in 1..{_lib.WIN_MAX}")
+        self._sbuf = (torch.zeros((4, B), **f32), torch.zeros((4, B), **f32))
         self.action = torch.zeros(B, **i32)
         self.option = torch.zeros(B, **i32)
         self.t_opt = torch.zeros(B, **i32)
@@ -75,7 +79,8 @@ class SkillChainAgent:
         self.reward = torch.zeros(B, **f32)
         self.flags = torch.zeros(B, **i32)
         self.delta = torch.zeros(B, **f32)
-        self.rec = torch.zeros((B, 12), **f32)
+        self.q_carry = torch.zeros(B, **f32)
+        self.win_rec = torch.zeros((self.win_cap, B, 8), **f32)
         self.parents = torch.zeros(K, dtype=torch.int32, device=dev)
         self.parents_host = np.zeros(K, dtype=np.uint32)
         self.parents_host[0] = GOAL_BIT
@@ -88,57 +93,95 @@ class SkillChainAgent:
         self.stats = torch.zeros(4, **i32)
         self.active_mask = 0
         self.n_active = 0
-        self.t = 0
-        self._swapped = False
         # initial state, option and action (oracle/agent.py __init__)
+        s = self._sbuf[0]
         if initial_states is not None:
             st = torch.as_tensor(np.asarray(initial_states, dtype=np.float32)).to(dev).reshape(B, 4)
-            self.s.copy_(st.t())
+            s.copy_(st.t())
         else:
-            check(self.lib.scg_reset(self.map.handle, B, None, ptr(self.s[0]), ptr(self.s[1]), ptr(self.s[2]),
-                                     ptr(self.s[3]), cfg.seed, 0, cfg.env_offset, _lib.current_stream()))
-        self.start_xy.copy_(self.s[:2].t())
+            check(self.lib.scg_reset(self.map.handle, B, None, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), cfg.seed, 0,
+                                     cfg.env_offset, _lib.current_stream()))
+        self.start_xy.copy_(s[:2].t())
         self.options.pack()
-        self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT,
-                                           soa=self.s))
-        self._struct = AgentStruct()
+        self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT, soa=s))
+        self._struct = self._make_struct()
 
     # -- plumbing --------------------------------------------------------------------------------
     def _push_parents(self):
         self.parents.copy_(self.torch.from_numpy(self.parents_host.view(np.int32)))
+
+    def _make_struct(self):
+        cfg, o, g = self.cfg, self.options, AgentStruct()
+        g.B, g.K, g.order = cfg.batch, o.K, o.order
+        g.env_offset, g.example_capacity, g.seed = cfg.env_offset, cfg.example_capacity, cfg.seed
+        g.gamma, g.lam, g.epsilon, g.option_bonus = cfg.gamma, cfg.lam, cfg.epsilon, cfg.option_bonus
+        g.option_timeout, g.max_episode_steps, g.cull = cfg.option_timeout, cfg.max_episode_steps, int(cfg.cull)
+        g.alpha, g.win_cap = cfg.alpha, self.win_cap
+        g.step = g.window_steps = g.win_len = g.carry_valid = 0
+        s, s2 = self._sbuf
+        g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
+        g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
+        for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
+                     "q_carry", "win_rec", "parents", "ex_xy", "ex_label", "ex_count", "n_success", "n_fail", "stats"):
+            setattr(g, name, getattr(self, name).data_ptr())
+        g.trace, g.W, g.Wt, g.theta = o._trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
+        g.dW, g.cnt = o._dW.data_ptr(), o.cnt.data_ptr()
+        return g
+
+    def _sync_struct(self):
+        """Push the host-side controller state the kernels read."""
+        g = self._struct
+        g.n_active, g.active_mask = self.n_active, self.active_mask
+        return g
+
+    @property
+    def t(self):
+        return int(self._struct.step)
+
+    @property
+    def s(self):
+        """(4, B) SoA tensor holding the current state."""
+        a, b = self._sbuf
+        return a if self._struct.x == a[0].data_ptr() else b
 
     @property
     def state(self):
         """(B, 4) copy of the current state."""
         return self.s.t().contiguous()
 
-    def _fill_struct(self):
-        cfg, o, g = self.cfg, self.options, self._struct
-        g.B, g.K, g.order, g.n_active = cfg.batch, o.K, o.order, self.n_active
-        g.active_mask, g.env_offset = self.active_mask, cfg.env_offset
-        g.step, g.example_capacity, g.seed = self.t & 0xFFFFFFFF, cfg.example_capacity, cfg.seed
-        g.gamma, g.lam, g.epsilon, g.option_bonus = cfg.gamma, cfg.lam, cfg.epsilon, cfg.option_bonus
-        g.option_timeout, g.max_episode_steps, g.cull = cfg.option_timeout, cfg.max_episode_steps, int(cfg.cull)
-        s, s2 = self.s, self.s2
-        g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
-        g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
-        for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
-                     "rec", "parents", "ex_xy", "ex_label", "ex_count", "n_success", "n_fail", "stats"):
-            setattr(g, name, getattr(self, name).data_ptr())
-        g.trace, g.W, g.Wt, g.theta = o.trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
-        g.dW, g.cnt = o.dW.data_ptr(), o.cnt.data_ptr()
-        return g
+    def invalidate(self):
+        """Call after changing state, action, option or weights from outside: the carried Q_o(s, a)
+        is stale and the next step re-evaluates it."""
+        self._struct.carry_valid = 0
 
     # -- the hot path ----------------------------------------------------------------------------
     def step(self):
         """One lock-step agent step for the whole batch (oracle/agent.py SkillChainAgent.step)."""
-        g = self._fill_struct()
-        check(self.lib.scg_agent_step(self.map.handle, self.options.ctx, C.byref(g), _lib.current_stream()))
-        self.s, self.s2 = self.s2, self.s
-        self.options.tick()
-        self.t += 1
-        if self.t % self.cfg.sync_interval == 0:
-            self.sync()
+        self.run(1)
+
+    def run(self, n_steps):
+        """`n_steps` lock-step agent steps, with the weight sync every `sync_interval` steps.  On one
+        rank the whole loop runs inside the library (scg_agent_run); with several ranks it returns to
+        Python at every sync for the NCCL all-reduce."""
+        g = self._sync_struct()
+        st = _lib.current_stream()
+        n, T = int(n_steps), int(self.cfg.sync_interval)
+        if world_size(self.pg) == 1:
+            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), n, T, st))
+            self.options.window_steps = int(g.window_steps)
+            return
+        while n > 0:
+            k = min(n, T - int(g.window_steps))
+            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), k, 0, st))
+            n -= k
+            if int(g.window_steps) >= T:
+                self.sync()
+
+    def flush(self):
+        """Fold the open window's step records into dW and the traces (scg_agent_flush)."""
+        g = self._struct
+        if int(g.win_len) > 0:
+            check(self.lib.scg_agent_flush(self.options.ctx, C.byref(g), _lib.current_stream()))
 
     def step_host(self, state, action):
         """The same step for a caller that keeps state and actions in host memory (as a user of the
@@ -150,42 +193,56 @@ class SkillChainAgent:
         B = self.cfg.batch
         if getattr(self, "_host", None) is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            self._host = dict(s=pin((4, B), torch.float32), a=pin((B,), torch.int32), s2=pin((4, B), torch.float32),
+            mk = lambda: dict(s=pin((4, B), torch.float32), a=pin((B,), torch.int32), s2=pin((4, B), torch.float32),
                               r=pin((B,), torch.float32), f=pin((B,), torch.int32), a2=pin((B,), torch.int32),
                               d=pin((B,), torch.float32))
-            self._host_np = {k: v.numpy() for k, v in self._host.items()}
-        h, hn = self._host, self._host_np
-        hn["s"][...] = state
-        hn["a"][...] = action
-        g = self._fill_struct()
-        check(self.lib.scg_agent_step_host(self.map.handle, self.options.ctx, C.byref(g), ptr(h["s"]), ptr(h["a"]),
-                                           ptr(h["s2"]), ptr(h["r"]), ptr(h["f"]), ptr(h["a2"]), ptr(h["d"]),
+            self._host = [mk(), mk()]                       # ping-pong: results of call i are inputs of call i+1
+            self._host_np = [{k: v.numpy() for k, v in h.items()} for h in self._host]
+            self._host_i = 0
+        prev, prev_np = self._host[self._host_i], self._host_np[self._host_i]
+        cur, cur_np = self._host[1 - self._host_i], self._host_np[1 - self._host_i]
+        if state is prev_np["s2"]:
+            src_s = prev["s2"]                              # previous result fed straight back: already pinned
+        else:
+            cur_np["s"][...] = state
+            src_s = cur["s"]
+        if action is prev_np["a2"]:
+            src_a = prev["a2"]
+        else:
+            cur_np["a"][...] = action
+            src_a = cur["a"]
+        g = self._sync_struct()
+        check(self.lib.scg_agent_step_host(self.map.handle, self.options.ctx, C.byref(g), ptr(src_s), ptr(src_a),
+                                           ptr(cur["s2"]), ptr(cur["r"]), ptr(cur["f"]), ptr(cur["a2"]), ptr(cur["d"]),
                                            _lib.current_stream()))
-        self.s, self.s2 = self.s2, self.s
-        self.options.tick()
-        self.t += 1
-        if self.t % self.cfg.sync_interval == 0:
+        self._host_i = 1 - self._host_i
+        self.options.window_steps = int(g.window_steps)
+        if int(g.window_steps) >= self.cfg.sync_interval:
             self.sync()
-        return hn["s2"], hn["r"], hn["f"], hn["a2"], hn["d"]
+        return cur_np["s2"], cur_np["r"], cur_np["f"], cur_np["a2"], cur_np["d"]
 
     HOST_H2D_BYTES_PER_ENV = 20      # state 16 + action 4
     HOST_D2H_BYTES_PER_ENV = 32      # next state 16 + reward 4 + flags 4 + next action 4 + TD error 4
 
-    def profile_begin(self, max_steps):
-        check(self.lib.scg_profile_begin(self.options.ctx, int(max_steps)))
+    def profile_begin(self, max_events):
+        check(self.lib.scg_profile_begin(self.options.ctx, int(max_events)))
 
     def profile_end(self):
-        """-> (ms per stage [K1 step, K2+K4 control, K3 trace sweep, dW reduction], steps recorded)."""
+        """-> (ms per kind, launches per kind) for [fused step, window sweep, dW reduction, apply]."""
         ms = (C.c_float * 4)()
-        n = C.c_int()
-        check(self.lib.scg_profile_end(self.options.ctx, ms, C.byref(n)))
-        return [float(v) for v in ms], n.value
+        n = (C.c_int * 4)()
+        check(self.lib.scg_profile_end(self.options.ctx, ms, n))
+        return [float(v) for v in ms], [int(v) for v in n]
 
     def sync(self):
-        """All-reduce the window's dW / cnt over ranks (if any) and apply."""
-        o = self.options
-        allreduce_deltas(o.dW, o.cnt, self.pg)
+        """Flush the window, all-reduce its dW / cnt over ranks (if any) and apply."""
+        o, g = self.options, self._struct
+        self.flush()
+        allreduce_deltas(o._dW, o.cnt, self.pg)
+        o.window_steps = int(g.window_steps)
         o.apply()
+        g.window_steps = 0
+        g.carry_valid = 0
 
     # -- low-rate controller ---------------------------------------------------------------------
     def examples(self, k):
@@ -200,21 +257,17 @@ class SkillChainAgent:
         g = self.n_active
         if g >= K - 1:
             return False
-        n_succ = self.n_success[g:g + 1].clone()
-        distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
-            and torch.distributed.get_world_size() > 1
-        if distributed:
-            torch.distributed.all_reduce(n_succ, group=self.pg)
+        n_succ = allreduce_scalar_sum(self.n_success[g:g + 1].clone(), self.pg)
         if int(n_succ) < cfg.gestation_successes:
             return False
         X, y = self.examples(g)
         self.options.theta[g].zero_()
         if X.shape[0] > 0:
             self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
-        if distributed:
-            th = self.options.theta[g].clone()
-            torch.distributed.all_reduce(th, group=self.pg)
-            self.options.theta[g].copy_(th / torch.distributed.get_world_size())
+        ws = world_size(self.pg)
+        if ws > 1:
+            th = allreduce_scalar_sum(self.options.theta[g].clone(), self.pg)
+            self.options.theta[g].copy_(th / ws)
         self.active_mask |= (1 << g)
         self.n_active += 1
         n = self.n_active
@@ -238,12 +291,12 @@ class SkillChainAgent:
         steps = 0
         B = self.cfg.batch
         while steps < max_steps:
-            self.step()
-            steps += 1
-            if steps % manage_every == 0:
-                self.manage()
-                if int(self.stats[0]) - base >= B:
-                    break
+            k = min(manage_every, max_steps - steps)
+            self.run(k)
+            steps += k
+            self.manage()
+            if int(self.stats[0]) - base >= B:
+                break
         c = self.counters()
         return dict(steps=steps, finished=c["episodes"] - base, goals=c["goals"], mean_return=c["mean_return"],
                     n_active=self.n_active, env_steps=steps * B)

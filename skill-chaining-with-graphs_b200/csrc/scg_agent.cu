@@ -1,212 +1,358 @@
-// scg_agent.cu - the fused lock-step agent step: K1 (env step) -> K2+K4 (control) -> K3 (traces).
+// scg_agent.cu - the fused lock-step agent step (K1 + K2 + K4 in ONE kernel) and the windowed pipeline.
 //
 // Mirrors oracle/agent.py SkillChainAgent.step, numbered steps 1-8 of its docstring (the reference
-// has no code: /root/reference/README.md:1-2).  One C call launches, on one stream:
-//   k_step            s2, r_env, flags = env.step(a)                       (scg_step.cu)
-//   k_agent_control   initiation bits of s2 (K4), termination, option reward, Q_o(s, a) and
-//                     Q_o(s2, .) with shared weight loads (K2), eps-greedy a2, TD error, the
-//                     48-byte update record for K3, example-ring append, env reset, option
-//                     re-selection + first action under the new option
-//   k_trace, k_reduce the trace sweep and dW reduction                     (scg_sarsa.cu)
-// Weight application (and the cross-GPU allreduce of dW / cnt) happens outside, every sync interval.
+// has no code: /root/reference/README.md:1-2).  Per env step one kernel, k_agent_step, does
+//   1    s2, r_env, flags = env.step(a)                                   (pinball_step, scg_step.cuh)
+//   2-3  initiation bits of s2 (K4), termination, option reward
+//   4    Q_o(s2, .) (K2), eps-greedy a2, TD error; Q_o(s, a) is carried from the previous step
+//        (q_carry) and only recomputed (PAIR variant, weight loads shared) after the weights changed
+//   5    a 32-byte step record for the window sweep (state, delta, action/option/termination bits)
+//   6-8  example-ring append, env reset, option re-selection + first action under the new option
+// Sarsa(lambda) itself runs once per window of up to win_cap steps (k_window in scg_sarsa.cu: the
+// forward-view form of oracle/option.py OptionSet.flush), so the dense per-env traces cross HBM once
+// per window instead of once per step.  Weight application (and the cross-GPU all-reduce of dW / cnt)
+// happens every sync interval.
+//
+// Kernel design: one thread per env, work handed out per warp (32 envs) and interleaved over the
+// persistent CTAs so that every SM gets the same number of warps even at B = 65,536.  Each CTA stages
+// the map blob and, when it fits, the packed weights [F][K][8] into shared memory with bulk-TMA copies
+// (cp.async.bulk + mbarrier); lanes executing different options then read different banks.
 #include <algorithm>
 
 #include "scg_common.cuh"
+#include "scg_step.cuh"
 
-int scg_launch_step(const scg_map_t *map, int B, const float *x, const float *y, const float *vx, const float *vy,
-                    const int *action, float *x2, float *y2, float *vx2, float *vy2, float *reward, int *flags,
-                    int cull, cudaStream_t st);
-int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float gl, float *dW, cudaStream_t st,
-                     cudaEvent_t *ev2 = nullptr);
+int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace, float gl, float *dW,
+                      cudaStream_t st);
+int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
-struct ControlArgs {
+struct StepArgs {
     scg_agent_t ag;
     const unsigned char *map_blob;
+    int blob_bytes, w_bytes;
+    float4 *rec;  // this step's slab of the window: [B][2]
 };
 
-template <int N1>
-__global__ void __launch_bounds__(32 * N1) k_agent_control(const __grid_constant__ ControlArgs args) {
-    constexpr int F = N1 * N1 * N1 * N1;
-    __shared__ float zsh[2][4][2][32];           // [state][dim][cos, sin][lane]
-    __shared__ float part[N1][2 * SCG_A][32];    // [warp][q value][lane]
+// bulk-TMA staging of up to two global blocks into shared memory behind one mbarrier
+__device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, int bytes0, unsigned char *dst1,
+                                       const void *src1, int bytes1, unsigned long long *bar) {
+    uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes0 + bytes1)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst0)),
+                     "l"(src0), "r"(bytes0), "r"(bar_a)
+                     : "memory");
+        if (bytes1 > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(dst1)),
+                         "l"(src1), "r"(bytes1), "r"(bar_a)
+                         : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_a)
+            : "memory");
+    }
+}
+
+template <int N1, bool SMEMW, bool PAIR>
+__global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ StepArgs args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
     const scg_agent_t &g = args.ag;
-    const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(args.map_blob);
+    unsigned char *w_smem = smem + ((args.blob_bytes + 127) & ~127);
+    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? args.w_bytes : 0, &bar);
+    const StepMap m = make_step_map(smem);
+    const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
+    const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
     const int K = g.K;
     const int gest = min(g.n_active, K - 1);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = blockIdx.x * 32; base < g.B; base += gridDim.x * 32) {
-        const bool valid = base + lane < g.B;
-        const int b = valid ? base + lane : g.B - 1;
-        float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
-        float nx = g.x2[b], ny = g.y2[b], nvx = g.vx2[b], nvy = g.vy2[b];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int n_tiles = (g.B + 31) >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    // warp-granular work, interleaved over CTAs: tile i goes to CTA i % grid, warp i / grid.  The warp stays
+    // converged through the whole tile (lanes past the batch end compute on a clamped index and skip stores).
+    for (int tile = w * gridDim.x + blockIdx.x; tile < n_tiles; tile += gridDim.x * nw) {
+        const bool valid = tile * 32 + lane < g.B;
+        const int b = valid ? tile * 32 + lane : g.B - 1;
+        const float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
+        const int a = g.action[b];
         const int o = g.option[b];
-        // phasors of s and s2: warp w evaluates dimensions w, w + N1, ... and shares them
-        {
-            float sa[4], sb[4];
-            scg_normalise(sx, sy, svx, svy, sa);
-            scg_normalise(nx, ny, nvx, nvy, sb);
+        // 1: env step
+        float nx = sx, ny = sy, nvx = svx, nvy = svy, r_env;
+        int fl;
+        if (g.cull) pinball_step<true>(m, nx, ny, nvx, nvy, a, r_env, fl);
+        else pinball_step<false>(m, nx, ny, nvx, nvy, a, r_env, fl);
+        const bool env_done = (fl & SCG_FLAG_DONE) != 0;
+        // 4a: Q_o(s2, .) (and Q_o(s, .) when the carried value is stale)
+        float2 zb[4];
+        scg_phasors(nx, ny, nvx, nvy, zb);
+        float qb[SCG_A], qsa;
+        const WCur<SMEMW> wc(Wt, K, o);
+        if constexpr (PAIR) {
+            float2 za[4];
+            scg_phasors(sx, sy, svx, svy, za);
+            float qa[SCG_A];
+            scg_q_pair<N1, SMEMW>(za, zb, wc, qa, qb);
+            qsa = 0.f;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                if (d % N1 == w) {
-                    float sn, cs;
-                    sincospif(sa[d], &sn, &cs);
-                    zsh[0][d][0][lane] = cs; zsh[0][d][1][lane] = sn;
-                    sincospif(sb[d], &sn, &cs);
-                    zsh[1][d][0][lane] = cs; zsh[1][d][1][lane] = sn;
-                }
-            }
+            for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
+        } else {
+            scg_q_one<N1, SMEMW>(zb, wc, qb);
+            qsa = g.q_carry[b];
         }
-        __syncthreads();
-        float2 za[4], zb[4];
+        const uint32_t env = g.env_offset + (uint32_t)b;
+        // 2-3: initiation bits of s2, termination, option reward
+        const uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
+        const uint32_t pm = g.parents[o];
+        const bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
+        int t_opt = g.t_opt[b] + 1, ep = g.ep_steps[b] + 1;
+        const bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
+        const bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
+        const bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
+        const float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
+        // 4b: a2, TD error
+        const int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_ACTION));
+        float qs2 = 0.f;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            za[d] = make_float2(zsh[0][d][0][lane], zsh[0][d][1][lane]);
-            zb[d] = make_float2(zsh[1][d][0][lane], zsh[1][d][1][lane]);
+        for (int i = 0; i < SCG_A; ++i) qs2 = (i == a2) ? qb[i] : qs2;
+        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
+        float ret = g.ep_return[b] + r_env;
+        const bool reset = env_done || ep_timeout;
+        {   // cnt[o] += 1, one atomic per (warp, option)
+            const uint32_t peers = __match_any_sync(FULL, valid ? o : -1);
+            if (valid && (__ffs(peers) - 1) == lane) atomicAdd(g.cnt + o, __popc(peers));
         }
-        // 4a: this warp's share of Q_o(s, .) and Q_o(s2, .)
-        {
-            float qa[SCG_A], qb[SCG_A];
-            scg_q_pair_c0<N1>(w, za, zb, g.Wt + (size_t)o * F * SCG_WT_STRIDE, qa, qb);
-#pragma unroll
-            for (int i = 0; i < SCG_A; ++i) {
-                part[w][i][lane] = qa[i];
-                part[w][SCG_A + i][lane] = qb[i];
-            }
-        }
-        __syncthreads();
-        if (w == 0 && valid) {
-            float qa[SCG_A], qb[SCG_A];
-#pragma unroll
-            for (int i = 0; i < SCG_A; ++i) {
-                float s0 = part[0][i][lane], s1 = part[0][SCG_A + i][lane];
-#pragma unroll
-                for (int ww = 1; ww < N1; ++ww) {
-                    s0 += part[ww][i][lane];
-                    s1 += part[ww][SCG_A + i][lane];
-                }
-                qa[i] = s0; qb[i] = s1;
-            }
-            const uint32_t env = g.env_offset + (uint32_t)b;
-            const int a = g.action[b];
-            const float r_env = g.reward[b];
-            const bool env_done = (g.flags[b] & SCG_FLAG_DONE) != 0;
-            // 2-3: initiation bits of s2, termination, option reward
-            uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
-            uint32_t pm = g.parents[o];
-            bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
-            int t_opt = g.t_opt[b] + 1, ep = g.ep_steps[b] + 1;
-            bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
-            bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
-            bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
-            float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
-            // 4b: a2, TD error
-            int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_ACTION));
-            float qsa = 0.f, qs2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < SCG_A; ++i) {
-                qsa = (i == a) ? qa[i] : qsa;
-                qs2 = (i == a2) ? qb[i] : qs2;
-            }
-            float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
+        if (valid) {
+            g.reward[b] = r_env;
+            g.flags[b] = fl;
             g.delta[b] = delta;
-            // 5: hand the update to K3
-            float4 *rec = reinterpret_cast<float4 *>(g.rec) + (size_t)b * 3;
-            uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
-            rec[0] = make_float4(za[0].x, za[0].y, za[1].x, za[1].y);
-            rec[1] = make_float4(za[2].x, za[2].y, za[3].x, za[3].y);
-            rec[2] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
-            {   // cnt[o] += 1, one atomic per (warp, option)
-                uint32_t peers = __match_any_sync(__activemask(), o);
-                if ((__ffs(peers) - 1) == lane) atomicAdd(g.cnt + o, __popc(peers));
-            }
-            float ret = g.ep_return[b] + r_env;
+            // 5: the step record for the window sweep
+            const uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
+            float4 *rec = args.rec + (size_t)b * 2;
+            rec[0] = make_float4(sx, sy, svx, svy);
+            rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
             // 6: example for option o's initiation classifier
             if (term) {
-                int eslot = atomicAdd(g.ex_count + o, 1) % (int)g.example_capacity;
-                size_t ei = (size_t)o * g.example_capacity + eslot;
+                const int eslot = atomicAdd(g.ex_count + o, 1) % (int)g.example_capacity;
+                const size_t ei = (size_t)o * g.example_capacity + eslot;
                 g.ex_xy[2 * ei] = g.start_xy[2 * b];
                 g.ex_xy[2 * ei + 1] = g.start_xy[2 * b + 1];
                 g.ex_label[ei] = hit ? 1 : 0;
                 atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
             }
             // 7: env reset
-            bool reset = env_done || ep_timeout;
             if (reset) {
-                uint4 rr = scg_draw(g.seed, env, g.step, SCG_STREAM_RESET);
-                int ns = mh->n_starts;
-                int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
-                const float2 *starts = reinterpret_cast<const float2 *>(args.map_blob + mh->off_starts);
-                float2 s0 = starts[pick];
+                const uint4 rr = scg_draw(g.seed, env, g.step, SCG_STREAM_RESET);
+                const int ns = mh->n_starts;
+                const int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
+                const float2 s0 = reinterpret_cast<const float2 *>(smem + mh->off_starts)[pick];
                 nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
                 atomicAdd(g.stats + 0, 1);
                 if (env_done) atomicAdd(g.stats + 1, 1);
                 atomicAdd(reinterpret_cast<float *>(g.stats + 2), ret);
                 ret = 0.f;
                 ep = 0;
-                g.x2[b] = nx; g.y2[b] = ny; g.vx2[b] = nvx; g.vy2[b] = nvy;
             }
+            g.x2[b] = nx; g.y2[b] = ny; g.vx2[b] = nvx; g.vy2[b] = nvy;
             g.ep_return[b] = ret;
             g.ep_steps[b] = ep;
-            // 8: option re-selection (rare: this lane walks all F features of the new option alone)
-            int o_next = o, a_next = a2;
-            if (term) {
-                uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
+        }
+        // 8: option re-selection.  Terminations are rare, so the Q evaluation under the new option is
+        // compacted inside the warp: N1 lanes share one terminated env, one leading digit c0 each.
+        int o_next = o, a_next = a2;
+        float q_next = qs2;
+        const bool tv = term && valid;
+        unsigned tmask = __ballot_sync(FULL, tv);
+        if (tmask) {
+            float2 zn[4] = {zb[0], zb[1], zb[2], zb[3]};
+            if (tv) {
+                const uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
                 o_next = bn ? (__ffs(bn) - 1) : gest;
-                float2 zn[4];
                 if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
-                else { zn[0] = zb[0]; zn[1] = zb[1]; zn[2] = zb[2]; zn[3] = zb[3]; }
-                float qn[SCG_A];
-                scg_q_one<N1>(zn, g.Wt + (size_t)o_next * F * SCG_WT_STRIDE, qn);
+            }
+            constexpr int PER = 32 / N1;                         // envs served per pass
+            const int my_slot = __popc(tmask & ((1u << lane) - 1u));   // rank of this lane among the terminated
+            const int slot = lane / N1, c0 = lane - slot * N1;
+            float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int base = 0; base < __popc(tmask); base += PER) {
+                const unsigned src = __fns(tmask, 0, base + slot + 1);   // lane of the (base+slot)-th terminated env
+                const bool have = slot < PER && src < 32u;
+                const int sl = have ? (int)src : 0;
+                float2 zs[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    zs[d].x = __shfl_sync(FULL, zn[d].x, sl);
+                    zs[d].y = __shfl_sync(FULL, zn[d].y, sl);
+                }
+                const int os = __shfl_sync(FULL, o_next, sl);
+                float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, K, os), qp);
+#pragma unroll
+                for (int d = 1; d < N1; ++d) {                   // slot head (c0 == 0) gathers the partial sums
+#pragma unroll
+                    for (int i = 0; i < SCG_A; ++i) {
+                        const float v = __shfl_down_sync(FULL, qp[i], d);
+                        if (c0 == 0) qp[i] += v;
+                    }
+                }
+                const int rel = my_slot - base;
+                const bool mine = tv && rel >= 0 && rel < PER;
+                const int head = mine ? rel * N1 : 0;
+#pragma unroll
+                for (int i = 0; i < SCG_A; ++i) {
+                    const float v = __shfl_sync(FULL, qp[i], head);
+                    if (mine) qn[i] = v;
+                }
+            }
+            if (tv) {
                 a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_RESELECT));
+#pragma unroll
+                for (int i = 0; i < SCG_A; ++i) q_next = (i == a_next) ? qn[i] : q_next;
                 t_opt = 0;
                 g.start_xy[2 * b] = nx;
                 g.start_xy[2 * b + 1] = ny;
+                g.option[b] = o_next;
             }
-            g.t_opt[b] = t_opt;
-            g.option[b] = o_next;
-            g.action[b] = a_next;
         }
-        __syncthreads();
+        if (valid) {
+            g.t_opt[b] = t_opt;
+            g.action[b] = a_next;
+            g.q_carry[b] = q_next;
+        }
     }
 }
 
-extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag, void *stream) {
+// ---- launch plumbing --------------------------------------------------------------------------------
+template <int N1, bool SMEMW, bool PAIR>
+static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
+    auto kern = k_agent_step<N1, SMEMW, PAIR>;
+    static size_t configured = 0;
+    static int per_sm = 0;
+    if (smem > configured || per_sm == 0) {
+        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        configured = smem;
+    }
+    if (per_sm < 1) return SCG_ELIMIT;
+    const int n_tiles = (args.ag.B + 31) / 32;
+    // enough CTAs for one warp per tile if they all fit at once, else every resident slot
+    int grid = (n_tiles + 7) / 8;
+    if (grid > SCG_NUM_SMS) {   // same number of CTAs on every SM: as many rounds of 148 as the tiles need, if resident
+        const int rounds = std::min(per_sm, (grid + SCG_NUM_SMS - 1) / SCG_NUM_SMS);
+        grid = SCG_NUM_SMS * rounds;
+    }
+    grid = std::max(grid, 1);
+    kern<<<grid, 256, smem, st>>>(args);
+    SCG_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N1>
+static int launch_step_n(const StepArgs &args, bool smemw, bool pair, cudaStream_t st) {
+    const size_t blob = (size_t)((args.blob_bytes + 127) & ~127);
+    if (smemw) {
+        const size_t smem = blob + args.w_bytes;
+        return pair ? launch_step_t<N1, true, true>(args, smem, st) : launch_step_t<N1, true, false>(args, smem, st);
+    }
+    return pair ? launch_step_t<N1, false, true>(args, blob, st) : launch_step_t<N1, false, false>(args, blob, st);
+}
+
+static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_agent_t *ag) {
     if (!map || !ctx || !ag) return SCG_EINVAL;
     if (ag->K != ctx->K || ag->order != ctx->order) return SCG_EINVAL;
     if (ag->K < 1 || ag->K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
-    if (ag->B <= 0) return ag->B == 0 ? 0 : SCG_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaEvent_t *ev = nullptr;
-    if (ctx->prof_on && ctx->prof_n < ctx->prof_cap) ev = ctx->prof_ev + (size_t)5 * ctx->prof_n++;
-    if (ev) SCG_CUDA_OK(cudaEventRecord(ev[0], st));
-    int rc = scg_launch_step(map, ag->B, ag->x, ag->y, ag->vx, ag->vy, ag->action, ag->x2, ag->y2, ag->vx2, ag->vy2,
-                             ag->reward, ag->flags, ag->cull, st);
-    if (rc) return rc;
-    if (ev) SCG_CUDA_OK(cudaEventRecord(ev[1], st));
-    ControlArgs args;
-    args.ag = *ag;
-    args.map_blob = map->d_blob;
-    int grid = std::max(1, std::min((ag->B + 31) / 32, SCG_NUM_SMS * 32));
-    DISPATCH_ORDER(ag->order, k_agent_control<N1><<<grid, 32 * N1, 0, st>>>(args));
-    SCG_LAUNCH_CHECK();
-    if (ev) SCG_CUDA_OK(cudaEventRecord(ev[2], st));
-    return scg_launch_trace(ctx, ag->B, ag->rec, ag->trace, ag->gamma * ag->lambda, ag->dW, st, ev ? ev + 3 : nullptr);
+    if (ag->B < 0 || ag->win_cap < 1 || ag->win_cap > SCG_WIN_MAX || ag->win_len < 0 || ag->win_len >= ag->win_cap)
+        return SCG_EINVAL;
+    if (map->hdr.blob_bytes > 160 * 1024) return SCG_ELIMIT;
+    return 0;
 }
 
-extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, const scg_agent_t *ag,
-                                   const float *h_state_soa, const int *h_action, float *h_state2_soa,
-                                   float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream) {
+extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
+    if (!ctx || !ag) return SCG_EINVAL;
+    if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; return 0; }
+    int rc = scg_launch_window(ctx, ag->B, ag->win_len, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
+                               (cudaStream_t)stream);
+    if (rc) return rc;
+    ag->win_len = 0;
+    return 0;
+}
+
+extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
+    int rc = check_agent(map, ctx, ag);
+    if (rc) return rc;
+    if (ag->B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    StepArgs args;
+    args.ag = *ag;
+    args.map_blob = map->d_blob;
+    args.blob_bytes = map->hdr.blob_bytes;
+    args.w_bytes = ag->K * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
+    args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
+    // weights go to shared memory when two CTAs per SM still fit next to the map
+    const bool smemw = (size_t)args.w_bytes + args.blob_bytes + 256 <= 100 * 1024;
+    const bool pair = !ag->carry_valid;
+    if ((rc = scg_prof_push(ctx, 0, st, false))) return rc;
+    DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, smemw, pair, st));
+    if (rc) return rc;
+    if ((rc = scg_prof_push(ctx, 0, st, true))) return rc;
+    std::swap(ag->x, ag->x2); std::swap(ag->y, ag->y2);
+    std::swap(ag->vx, ag->vx2); std::swap(ag->vy, ag->vy2);
+    ag->step += 1;
+    ag->window_steps += 1;
+    ag->win_len += 1;
+    ag->carry_valid = 1;
+    if (ag->win_len >= ag->win_cap) return scg_agent_flush(ctx, ag, stream);
+    return 0;
+}
+
+extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n_steps, int sync_interval,
+                             void *stream) {
+    if (n_steps < 0 || sync_interval < 0) return SCG_EINVAL;
+    for (int i = 0; i < n_steps; ++i) {
+        int rc = scg_agent_step(map, ctx, ag, stream);
+        if (rc) return rc;
+        if (sync_interval > 0 && ag->window_steps >= sync_interval) {
+            if ((rc = scg_agent_flush(ctx, ag, stream))) return rc;
+            if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, false))) return rc;
+            if ((rc = scg_apply(ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream)))
+                return rc;
+            if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, true))) return rc;
+            ag->window_steps = 0;
+            ag->carry_valid = 0;
+        }
+    }
+    return 0;
+}
+
+extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, const float *h_state_soa,
+                                   const int *h_action, float *h_state2_soa, float *h_reward, int *h_flags,
+                                   int *h_action2, float *h_delta, void *stream) {
     if (!map || !ctx || !ag || !h_state_soa || !h_action || !h_state2_soa || !h_reward || !h_flags || !h_action2 ||
         !h_delta)
         return SCG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     size_t n = (size_t)ag->B * sizeof(float);
-    float *in[4] = {ag->x, ag->y, ag->vx, ag->vy}, *out[4] = {ag->x2, ag->y2, ag->vx2, ag->vy2};
+    float *in[4] = {ag->x, ag->y, ag->vx, ag->vy};
     for (int i = 0; i < 4; ++i)
         SCG_CUDA_OK(cudaMemcpyAsync(in[i], h_state_soa + (size_t)i * ag->B, n, cudaMemcpyHostToDevice, st));
     SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
+    ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
     int rc = scg_agent_step(map, ctx, ag, stream);
     if (rc) return rc;
+    float *out[4] = {ag->x, ag->y, ag->vx, ag->vy};   // the step swapped the buffers: x..vy is the new state
     for (int i = 0; i < 4; ++i)
         SCG_CUDA_OK(cudaMemcpyAsync(h_state2_soa + (size_t)i * ag->B, out[i], n, cudaMemcpyDeviceToHost, st));
     SCG_CUDA_OK(cudaMemcpyAsync(h_reward, ag->reward, n, cudaMemcpyDeviceToHost, st));
@@ -217,41 +363,52 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, const s
     return 0;
 }
 
-extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_steps) {
-    if (!ctx || max_steps <= 0) return SCG_EINVAL;
-    if (max_steps > ctx->prof_cap) {
-        for (int i = 0; i < 5 * ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
+// ---- per-kernel timing ---------------------------------------------------------------------------------
+int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end) {
+    if (!ctx->prof_on) return 0;
+    if (!end) {
+        if (ctx->prof_n >= ctx->prof_cap) return 0;
+        ctx->prof_kind[ctx->prof_n] = kind;
+        SCG_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], st));
+        ctx->prof_open = 1;
+    } else if (ctx->prof_open) {
+        SCG_CUDA_OK(cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], st));
+        ctx->prof_n += 1;
+        ctx->prof_open = 0;
+    }
+    return 0;
+}
+
+extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_events) {
+    if (!ctx || max_events <= 0) return SCG_EINVAL;
+    if (max_events > ctx->prof_cap) {
+        for (int i = 0; i < 2 * ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         free(ctx->prof_ev);
+        free(ctx->prof_kind);
         ctx->prof_cap = 0;
-        ctx->prof_ev = (cudaEvent_t *)calloc((size_t)5 * max_steps, sizeof(cudaEvent_t));
-        if (!ctx->prof_ev) return SCG_ENOMEM;
-        for (int i = 0; i < 5 * max_steps; ++i) SCG_CUDA_OK(cudaEventCreate(&ctx->prof_ev[i]));
-        ctx->prof_cap = max_steps;
+        ctx->prof_ev = (cudaEvent_t *)calloc((size_t)2 * max_events, sizeof(cudaEvent_t));
+        ctx->prof_kind = (int *)calloc((size_t)max_events, sizeof(int));
+        if (!ctx->prof_ev || !ctx->prof_kind) return SCG_ENOMEM;
+        for (int i = 0; i < 2 * max_events; ++i) SCG_CUDA_OK(cudaEventCreate(&ctx->prof_ev[i]));
+        ctx->prof_cap = max_events;
     }
     ctx->prof_n = 0;
+    ctx->prof_open = 0;
     ctx->prof_on = 1;
     return 0;
 }
 
-extern "C" int scg_profile_end(scg_ctx_t *ctx, float *ms, int *steps) {
-    if (!ctx || !ms || !steps) return SCG_EINVAL;
+extern "C" int scg_profile_end(scg_ctx_t *ctx, float *ms, int *count) {
+    if (!ctx || !ms || !count) return SCG_EINVAL;
     ctx->prof_on = 0;
-    for (int k = 0; k < 4; ++k) ms[k] = 0.f;
-    *steps = ctx->prof_n;
+    for (int k = 0; k < 4; ++k) { ms[k] = 0.f; count[k] = 0; }
     for (int i = 0; i < ctx->prof_n; ++i) {
-        cudaEvent_t *ev = ctx->prof_ev + (size_t)5 * i;
-        SCG_CUDA_OK(cudaEventSynchronize(ev[4]));
-        for (int k = 0; k < 4; ++k) {
-            float t = 0.f;
-            SCG_CUDA_OK(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
-            ms[k] += t;
-        }
+        float t = 0.f;
+        SCG_CUDA_OK(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+        SCG_CUDA_OK(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        int k = ctx->prof_kind[i] & 3;
+        ms[k] += t;
+        count[k] += 1;
     }
     return 0;
-}
-
-extern "C" void scg_agent_swap(scg_agent_t *ag) {
-    if (!ag) return;
-    std::swap(ag->x, ag->x2); std::swap(ag->y, ag->y2);
-    std::swap(ag->vx, ag->vx2); std::swap(ag->vy, ag->vy2);
 }

@@ -8,11 +8,15 @@
 #define SCG_A SCG_N_ACTIONS
 #define SCG_WT_STRIDE 8  // packed weights: [K][F][8] (5 actions + 3 pad) -> two 16-byte loads per feature
 #define SCG_REC_FLOATS 12
+#define SCG_WREC_FLOATS 8
 #define SCG_NUM_SMS 148
 
-// update record (K2 -> K3), 48 bytes per env:
+// dense-sweep update record (scg_sarsa_update), 48 bytes per env:
 //   [0..7]  cos/sin(pi * s_hat_j), j = 0..3 of the state the update is for
 //   [8]     delta        [9] meta bits        [10],[11] unused
+// window step record (agent pipeline), 32 bytes per env-step:
+//   [0..3]  x, y, vx, vy of the state the update is for     [4] delta     [5] meta bits     [6],[7] unused
+// meta bits: action (bits 0-2), option (bits 8-15), ZERO_AFTER (trace reset after the update), ACTIVE
 #define SCG_META_ACTIVE (1u << 31)
 #define SCG_META_ZERO_AFTER (1u << 16)
 
@@ -77,9 +81,11 @@ struct scg_ctx {
     float *d_partial;    // [n_partials][K][A*F]
     float *d_rec;        // records for the standalone scg_sarsa_update, grown on demand
     int rec_capacity;
-    // optional per-kernel timing of scg_agent_step (scg_profile_begin / scg_profile_end)
-    cudaEvent_t *prof_ev;  // [prof_cap][5]
-    int prof_cap, prof_n, prof_on;
+    int win_grid;        // CTAs of the window kernel (0 = not configured yet)
+    // optional per-kernel timing of the agent pipeline (scg_profile_begin / scg_profile_end)
+    cudaEvent_t *prof_ev;  // [prof_cap][2] start/stop pairs
+    int *prof_kind;        // [prof_cap]
+    int prof_cap, prof_n, prof_on, prof_open;
 };
 
 #ifdef __CUDACC__
@@ -134,29 +140,62 @@ __device__ __forceinline__ void scg_phasors(float x, float y, float vx, float vy
     for (int j = 0; j < 4; ++j) sincospif(s[j], &z[j].y, &z[j].x);
 }
 
+// ---- packed weights ------------------------------------------------------------------------------
+// Wt is [F][K][8] fp32: feature-major, then option, then 5 action weights + 3 pad, so that one feature
+// of one option is two 16-byte loads, and the K options of a feature sit in consecutive 32-byte slots
+// (lanes of a warp that execute different options hit different shared-memory banks).
+// WCur walks the table for one option, from global memory (read-only path) or from a shared-memory copy.
+__device__ __forceinline__ uint32_t scg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool SMEM> struct WCur;
+template <> struct WCur<false> {
+    const float4 *p;
+    int stride;  // float4 units between consecutive features
+    __device__ __forceinline__ WCur(const float *Wt, int K, int o)
+        : p(reinterpret_cast<const float4 *>(Wt) + 2 * o), stride(2 * K) {}
+    __device__ __forceinline__ void load(int f, float4 &a, float4 &b) const {
+        const float4 *q = p + (size_t)f * stride;
+        a = __ldg(q);
+        b = __ldg(q + 1);
+    }
+};
+template <> struct WCur<true> {
+    uint32_t addr, stride;  // bytes
+    __device__ __forceinline__ WCur(const float *Wt_smem, int K, int o)
+        : addr(scg_smem_u32(Wt_smem) + 32u * (uint32_t)o), stride(32u * (uint32_t)K) {}
+    __device__ __forceinline__ void load(int f, float4 &a, float4 &b) const {
+        uint32_t q = addr + (uint32_t)f * stride;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(q));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(q));
+    }
+};
+
 // Q_o(s, .) for one env: nested loops over the multi-index with running phasor products
-// (cos(pi c.s) = Re prod_j z_j^{c_j}); the innermost dimension uses a register table.
-// Wt_o points at the packed weights of the env's option: [F][8].
-template <int N1>
-__device__ __forceinline__ void scg_q_one(const float2 z[4], const float *__restrict__ Wt_o, float q[SCG_A]) {
+// (cos(pi c.s) = Re prod_j z_j^{c_j}); the two innermost dimensions are unrolled and use a register
+// table of z_3 powers.  Each feature is consumed by five FFMAs the moment it is formed.
+template <int N1, bool SMEM>
+__device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
     float2 p3[N1];
     p3[0] = make_float2(1.f, 0.f);
 #pragma unroll
     for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
 #pragma unroll
     for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
-    const float4 *w = reinterpret_cast<const float4 *>(Wt_o);
     float2 z0 = make_float2(1.f, 0.f);
+    int f = 0;
+#pragma unroll 1
     for (int c0 = 0; c0 < N1; ++c0) {
         float2 z01 = z0;
+#pragma unroll 1
         for (int c1 = 0; c1 < N1; ++c1) {
             float2 z012 = z01;
+#pragma unroll
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
                 for (int c3 = 0; c3 < N1; ++c3) {
                     float phi = fmaf(z012.x, p3[c3].x, -z012.y * p3[c3].y);
-                    float4 wa = __ldg(w), wb = __ldg(w + 1);
-                    w += 2;
+                    float4 wa, wb;
+                    w.load(f + c2 * N1 + c3, wa, wb);
                     q[0] = fmaf(wa.x, phi, q[0]);
                     q[1] = fmaf(wa.y, phi, q[1]);
                     q[2] = fmaf(wa.z, phi, q[2]);
@@ -165,15 +204,52 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const float *__rest
                 }
                 z012 = scg_cmul(z012, z[2]);
             }
+            f += N1 * N1;
             z01 = scg_cmul(z01, z[1]);
         }
         z0 = scg_cmul(z0, z[0]);
     }
 }
 
-// Same for two states sharing the weight loads: q1 = Q_o(s1, .), q2 = Q_o(s2, .)
-template <int N1>
-__device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4], const float *__restrict__ Wt_o,
+// The slice of Q_o(s, .) whose features have leading multi-index digit c0 (N1^3 features): N1 lanes
+// that share one env each take one digit and add their partial sums (option re-selection).
+template <int N1, bool SMEM>
+__device__ __forceinline__ void scg_q_c0(int c0, const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
+    float2 p3[N1];
+    p3[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
+#pragma unroll
+    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
+    float2 z01 = make_float2(1.f, 0.f);
+    for (int i = 0; i < c0; ++i) z01 = scg_cmul(z01, z[0]);
+    int f = c0 * N1 * N1 * N1;
+#pragma unroll 1
+    for (int c1 = 0; c1 < N1; ++c1) {
+        float2 z012 = z01;
+#pragma unroll
+        for (int c2 = 0; c2 < N1; ++c2) {
+#pragma unroll
+            for (int c3 = 0; c3 < N1; ++c3) {
+                float phi = fmaf(z012.x, p3[c3].x, -z012.y * p3[c3].y);
+                float4 wa, wb;
+                w.load(f + c2 * N1 + c3, wa, wb);
+                q[0] = fmaf(wa.x, phi, q[0]);
+                q[1] = fmaf(wa.y, phi, q[1]);
+                q[2] = fmaf(wa.z, phi, q[2]);
+                q[3] = fmaf(wa.w, phi, q[3]);
+                q[4] = fmaf(wb.x, phi, q[4]);
+            }
+            z012 = scg_cmul(z012, z[2]);
+        }
+        f += N1 * N1;
+        z01 = scg_cmul(z01, z[1]);
+    }
+}
+
+// Same for two states sharing the weight loads: qa = Q_o(sa, .), qb = Q_o(sb, .)
+template <int N1, bool SMEM>
+__device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4], const WCur<SMEM> &w,
                                            float qa[SCG_A], float qb[SCG_A]) {
     float2 pa[N1], pb[N1];
     pa[0] = pb[0] = make_float2(1.f, 0.f);
@@ -184,19 +260,22 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
     }
 #pragma unroll
     for (int a = 0; a < SCG_A; ++a) qa[a] = qb[a] = 0.f;
-    const float4 *w = reinterpret_cast<const float4 *>(Wt_o);
     float2 a0 = make_float2(1.f, 0.f), b0 = a0;
+    int f = 0;
+#pragma unroll 1
     for (int c0 = 0; c0 < N1; ++c0) {
         float2 a01 = a0, b01 = b0;
+#pragma unroll 1
         for (int c1 = 0; c1 < N1; ++c1) {
             float2 a012 = a01, b012 = b01;
+#pragma unroll 1
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
                 for (int c3 = 0; c3 < N1; ++c3) {
                     float fa = fmaf(a012.x, pa[c3].x, -a012.y * pa[c3].y);
                     float fb = fmaf(b012.x, pb[c3].x, -b012.y * pb[c3].y);
-                    float4 wa = __ldg(w), wb = __ldg(w + 1);
-                    w += 2;
+                    float4 wa, wb;
+                    w.load(f + c3, wa, wb);
                     qa[0] = fmaf(wa.x, fa, qa[0]);
                     qa[1] = fmaf(wa.y, fa, qa[1]);
                     qa[2] = fmaf(wa.z, fa, qa[2]);
@@ -208,6 +287,7 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
                     qb[3] = fmaf(wa.w, fb, qb[3]);
                     qb[4] = fmaf(wb.x, fb, qb[4]);
                 }
+                f += N1;
                 a012 = scg_cmul(a012, za[2]);
                 b012 = scg_cmul(b012, zb[2]);
             }
@@ -237,58 +317,6 @@ __device__ __forceinline__ uint32_t scg_init_bits(const float *__restrict__ thet
         if (zz >= 0.f) bits |= (1u << k);
     }
     return bits;
-}
-
-// ---- one warp per leading multi-index digit ---------------------------------------------------
-// The hot control kernel runs N1 warps over the same 32 envs: warp w sums the features whose
-// multi-index has c0 = w (a quarter of them at order 3), lane l is env l.  Every lane of a warp
-// reads the same packed-weight address (one L1 wavefront when the 32 envs share an option), and
-// N1 times more threads than one-per-env keep the FP32 pipe fed at B = 65,536.  The partial Q
-// vectors meet in shared memory.
-template <int N1>
-__device__ __forceinline__ void scg_q_pair_c0(int c0, const float2 za[4], const float2 zb[4],
-                                              const float *__restrict__ Wt_o, float qa[SCG_A], float qb[SCG_A]) {
-    float2 pa[N1], pb[N1];
-    pa[0] = pb[0] = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int c = 1; c < N1; ++c) {
-        pa[c] = scg_cmul(pa[c - 1], za[3]);
-        pb[c] = scg_cmul(pb[c - 1], zb[3]);
-    }
-#pragma unroll
-    for (int a = 0; a < SCG_A; ++a) qa[a] = qb[a] = 0.f;
-    float2 a01 = make_float2(1.f, 0.f), b01 = a01;
-    for (int i = 0; i < c0; ++i) {          // z0^c0 (c0 is warp-uniform)
-        a01 = scg_cmul(a01, za[0]);
-        b01 = scg_cmul(b01, zb[0]);
-    }
-    const float4 *w = reinterpret_cast<const float4 *>(Wt_o) + 2 * (c0 * N1 * N1 * N1);
-    for (int c1 = 0; c1 < N1; ++c1) {
-        float2 a012 = a01, b012 = b01;
-        for (int c2 = 0; c2 < N1; ++c2) {
-#pragma unroll
-            for (int c3 = 0; c3 < N1; ++c3) {
-                float fa = fmaf(a012.x, pa[c3].x, -a012.y * pa[c3].y);
-                float fb = fmaf(b012.x, pb[c3].x, -b012.y * pb[c3].y);
-                float4 wa = __ldg(w), wb = __ldg(w + 1);
-                w += 2;
-                qa[0] = fmaf(wa.x, fa, qa[0]);
-                qa[1] = fmaf(wa.y, fa, qa[1]);
-                qa[2] = fmaf(wa.z, fa, qa[2]);
-                qa[3] = fmaf(wa.w, fa, qa[3]);
-                qa[4] = fmaf(wb.x, fa, qa[4]);
-                qb[0] = fmaf(wa.x, fb, qb[0]);
-                qb[1] = fmaf(wa.y, fb, qb[1]);
-                qb[2] = fmaf(wa.z, fb, qb[2]);
-                qb[3] = fmaf(wa.w, fb, qb[3]);
-                qb[4] = fmaf(wb.x, fb, qb[4]);
-            }
-            a012 = scg_cmul(a012, za[2]);
-            b012 = scg_cmul(b012, zb[2]);
-        }
-        a01 = scg_cmul(a01, za[1]);
-        b01 = scg_cmul(b01, zb[1]);
-    }
 }
 
 __device__ __forceinline__ float scg_warp_sum(float v) {

@@ -8,7 +8,7 @@
 // K2 design: one thread per env.  phi = cos(pi C s_hat) is never materialised: four sincospi
 // calls give z_j = exp(i pi s_hat_j), the multi-index loops keep running complex products, and
 // each feature is consumed by five FFMAs the moment it is formed (scg_q_one / scg_q_pair in
-// scg_common.cuh).  Weights are read from the packed [K][F][8] copy with two 16-byte loads per
+// scg_common.cuh).  Weights are read from the packed [F][K][8] copy with two 16-byte loads per
 // feature, warp-uniform when the warp's envs execute the same option.  The contraction is
 // (B x F).(F x 5): far too skinny for tcgen05 tiles, so it stays on the FP32 pipe.
 // Roofline: FP32, 18 F flop per (env, option).
@@ -54,7 +54,7 @@ __global__ void k_pack_weights(int F, int K, const float *__restrict__ W, float 
     int n = K * F;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int k = i / F, f = i - k * F;
-        float *o = Wt + (size_t)i * SCG_WT_STRIDE;
+        float *o = Wt + ((size_t)f * K + k) * SCG_WT_STRIDE;
 #pragma unroll
         for (int a = 0; a < SCG_A; ++a) o[a] = W[((size_t)k * SCG_A + a) * F + f];
         o[5] = o[6] = o[7] = 0.f;
@@ -66,13 +66,12 @@ __global__ void __launch_bounds__(128) k_q_eval(int K, int B, const float *__res
                                                 const float *__restrict__ vx, const float *__restrict__ vy,
                                                 const int *__restrict__ option, const float *__restrict__ Wt,
                                                 float *__restrict__ Q) {
-    constexpr int F = N1 * N1 * N1 * N1;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         float2 z[4];
         scg_phasors(x[b], y[b], vx[b], vy[b], z);
         int o = min(max(option[b], 0), K - 1);
         float q[SCG_A];
-        scg_q_one<N1>(z, Wt + (size_t)o * F * SCG_WT_STRIDE, q);
+        scg_q_one<N1, false>(z, WCur<false>(Wt, K, o), q);
 #pragma unroll
         for (int a = 0; a < SCG_A; ++a) Q[(size_t)b * SCG_A + a] = q[a];
     }
@@ -97,14 +96,13 @@ __global__ void __launch_bounds__(128) k_td(int K, int B, const float *__restric
                                             const int *__restrict__ a2, const uint8_t *__restrict__ done,
                                             const int *__restrict__ option, const float *__restrict__ Wt, float gamma,
                                             float *__restrict__ delta) {
-    constexpr int F = N1 * N1 * N1 * N1;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         float2 za[4], zb[4];
         scg_phasors(x[b], y[b], vx[b], vy[b], za);
         scg_phasors(x2[b], y2[b], vx2[b], vy2[b], zb);
         int o = min(max(option[b], 0), K - 1);
         float qa[SCG_A], qb[SCG_A];
-        scg_q_pair<N1>(za, zb, Wt + (size_t)o * F * SCG_WT_STRIDE, qa, qb);
+        scg_q_pair<N1, false>(za, zb, WCur<false>(Wt, K, o), qa, qb);
         int ia = a[b], ib = a2[b];
         float qsa = 0.f, qs2 = 0.f;
 #pragma unroll

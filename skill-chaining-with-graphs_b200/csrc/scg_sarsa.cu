@@ -304,6 +304,181 @@ __global__ void __launch_bounds__(NT + 32) k_trace_tma(int B, int K, int S, int 
     for (int i = threadIdx.x; i < K * NCH; i += NT + 32) out[i] = acc[i];
 }
 
+// ---- windowed (forward-view) sweep: the agent pipeline's K3 --------------------------------------
+// Mirrors oracle/option.py OptionSet.flush.  The fused step kernel left, for each of the T steps of the
+// window, a 32-byte record per env (state, delta, action / option / termination bits).  One CTA sweeps
+// one env at a time; thread t owns the same VEC features of all A rows of every env's trace (registers)
+// and of the CTA's dW accumulator (shared memory, [K][A*F], plain read-modify-write: ownership is
+// exclusive).  Per env:
+//   phase A  threads 0..4T-1 load the records, turn each state component into z = exp(i pi s_hat) and
+//            its powers z^0..z^(N1-1)                                             -> pw[t][j][c]
+//   phase B  pair tables P01[t][c0][c1] = z0^c0 z1^c1 and P23[t][c2][c3] = z2^c2 z3^c3 (one complex
+//            multiply per entry), while one thread runs the backward recursion
+//            G_t = delta_t + (done_t ? 0 : gl G_{t+1}) and the trace coefficients c_t
+//   phase C  e <- scale e (+ carry-in dW[o_0] += gl G_0 e_start);  for every step:
+//            phi_f = Re(P01[f / N1^2] P23[f % N1^2]);  dW[o_t][a_t][f] += G_t phi_f;  e[a_t][f] += c_t phi_f
+// so a feature costs two 8-byte shared loads and two FP32 ops to form, and the dense trace crosses HBM
+// once per window: 8*A*F/T + 32 algorithmic bytes per env-step.
+#define SCG_WIN_TB 8   // steps per table block
+
+template <int N1, int VEC, int NT>
+__global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
+                                               float *__restrict__ partial, float gl) {
+    using V = typename VecT<VEC>::type;
+    constexpr int F = N1 * N1 * N1 * N1;
+    constexpr int AF = SCG_A * F;
+    constexpr int NCHR = F / VEC;          // chunks per action row
+    constexpr int NN = N1 * N1;
+    static_assert(F % VEC == 0 && NT >= NCHR && NT >= 4 * SCG_WIN_TB, "layout");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *acc = reinterpret_cast<float *>(smem_raw);                       // [K][AF]
+    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [TB][2][NN], 16-byte aligned
+    float2 *pw = tab + SCG_WIN_TB * 2 * NN;                                 // [TB][4][N1]
+    float *sG = reinterpret_cast<float *>(pw + SCG_WIN_TB * 4 * N1);        // [SCG_WIN_MAX]
+    float *sC = sG + SCG_WIN_MAX;                                           // [SCG_WIN_MAX]
+    float *sD = sC + SCG_WIN_MAX;                                           // [SCG_WIN_MAX] deltas
+    uint32_t *sM = reinterpret_cast<uint32_t *>(sD + SCG_WIN_MAX);          // [SCG_WIN_MAX] meta
+    float *sS = reinterpret_cast<float *>(sM + SCG_WIN_MAX);                // [0] scale, [1] carry, [2] o0 bits
+
+    const int tid = threadIdx.x;
+    const bool own = tid < NCHR;
+    // per-thread constants: table indices of the VEC owned features (same in every row)
+    int i01[VEC], i23[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        int f = (own ? tid : 0) * VEC + v;
+        i01[v] = f / NN;
+        i23[v] = NN + f % NN;
+    }
+    for (int i = tid; i < K * AF; i += NT) acc[i] = 0.f;
+    __syncthreads();
+
+    // software pipeline: the trace and the first table block's records of env i+1 are loaded while env i
+    // is processed, so no phase waits on a global load it has just issued
+    V e[SCG_A], e_nx[SCG_A];
+    float sv_nx = 0.f;
+    float2 dm_nx = make_float2(0.f, 0.f);
+    auto prefetch = [&](int b) {
+        const V *tp = reinterpret_cast<const V *>(trace + (size_t)b * AF);
+        if (own) {
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) e_nx[r] = tp[r * NCHR + tid];
+        }
+        if (tid < T) dm_nx = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)tid * B + b) * 2 + 1));
+        if (tid < min(T, SCG_WIN_TB) * 4)
+            sv_nx = __ldg(reinterpret_cast<const float *>(rec + ((size_t)(tid >> 2) * B + b) * 2) + (tid & 3));
+    };
+    if ((int)blockIdx.x < B) prefetch(blockIdx.x);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+#pragma unroll
+        for (int r = 0; r < SCG_A; ++r) e[r] = e_nx[r];
+        float sv0 = sv_nx;
+        const float2 dm = dm_nx;
+        if (b + (int)gridDim.x < B) prefetch(b + gridDim.x);
+        V *tp = reinterpret_cast<V *>(trace + (size_t)b * AF);
+        for (int t0 = 0; t0 < T; t0 += SCG_WIN_TB) {
+            const int nb = min(SCG_WIN_TB, T - t0);
+            // ---- phase A: deltas / meta of all T steps (first block only) and phasor powers of this block ----
+            if (t0 == 0 && tid < T) {
+                sD[tid] = dm.x;
+                sM[tid] = __float_as_uint(dm.y);
+            }
+            for (int i = tid; i < nb * 4; i += NT) {
+                const int tt = i >> 2, j = i & 3;
+                float sv;
+                if (t0 == 0 && i == tid) sv = sv0;   // prefetched (NT >= 4 * SCG_WIN_TB)
+                else sv = __ldg(reinterpret_cast<const float *>(rec + ((size_t)(t0 + tt) * B + b) * 2) + j);
+                if (j >= 2) sv = __fmul_rn(__fadd_rn(sv, 2.0f), 0.25f);   // oracle/fourier.py normalise
+                float2 z, p = make_float2(1.f, 0.f);
+                sincospif(sv, &z.y, &z.x);
+                float2 *dst = pw + (tt * 4 + j) * N1;
+#pragma unroll
+                for (int c = 0; c < N1; ++c) {
+                    dst[c] = p;
+                    p = scg_cmul(p, z);
+                }
+            }
+            __syncthreads();
+            // ---- phase B: pair tables; one thread runs the backward recursion (first block only) ----
+            for (int i = tid; i < nb * 2 * NN; i += NT) {
+                const int tt = i / (2 * NN), rem = i - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
+                const float2 *pa = pw + (tt * 4 + 2 * half) * N1;
+                tab[i] = scg_cmul(pa[ij / N1], pa[N1 + ij % N1]);
+            }
+            if (t0 == 0 && tid == NT - 1) {
+                float nxt = 0.f, cc = 1.f;
+                bool dead = false;
+                uint32_t o0 = 0;
+                bool any = false;
+                for (int t = T - 1; t >= 0; --t) {
+                    const uint32_t meta = sM[t];
+                    const bool act = (meta & SCG_META_ACTIVE) != 0;
+                    const bool dn = act && (meta & SCG_META_ZERO_AFTER);
+                    if (act) {
+                        nxt = dn ? sD[t] : fmaf(gl, nxt, sD[t]);
+                        dead = dead || dn;
+                        sC[t] = dead ? 0.f : cc;
+                        cc *= gl;
+                        o0 = (meta >> 8) & 0xFF;
+                        any = true;
+                    } else {
+                        sC[t] = 0.f;
+                    }
+                    sG[t] = act ? nxt : 0.f;
+                }
+                sS[0] = dead ? 0.f : cc;
+                sS[1] = any ? gl * nxt : 0.f;
+                sS[2] = __uint_as_float(o0);
+            }
+            __syncthreads();
+            // ---- phase C ----
+            if (own) {
+                if (t0 == 0) {
+                    const float scale = sS[0], carry = sS[1];
+                    if (carry != 0.f) {
+                        V *ap = reinterpret_cast<V *>(acc + (size_t)__float_as_uint(sS[2]) * AF);
+#pragma unroll
+                        for (int r = 0; r < SCG_A; ++r) ap[r * NCHR + tid] = vfma(carry, e[r], ap[r * NCHR + tid]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < SCG_A; ++r) e[r] = vscale(e[r], scale);
+                }
+                for (int tt = 0; tt < nb; ++tt) {
+                    const float G = sG[t0 + tt], c = sC[t0 + tt];
+                    if (G == 0.f && c == 0.f) continue;
+                    const uint32_t meta = sM[t0 + tt];
+                    const int a = meta & 7, o = (meta >> 8) & 0xFF;
+                    const float2 *tb = tab + tt * 2 * NN;
+                    float phi[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float2 p = tb[i01[v]], q = tb[i23[v]];
+                        phi[v] = fmaf(p.x, q.x, -p.y * q.y);
+                    }
+                    V ph;
+                    if constexpr (VEC == 4) ph = make_float4(phi[0], phi[1], phi[2], phi[3]); else ph = phi[0];
+                    V *ap = reinterpret_cast<V *>(acc + ((size_t)o * SCG_A + a) * F) + tid;
+                    *ap = vfma(G, ph, *ap);
+                    switch (a) {   // warp-uniform
+                        case 0: e[0] = vfma(c, ph, e[0]); break;
+                        case 1: e[1] = vfma(c, ph, e[1]); break;
+                        case 2: e[2] = vfma(c, ph, e[2]); break;
+                        case 3: e[3] = vfma(c, ph, e[3]); break;
+                        default: e[4] = vfma(c, ph, e[4]); break;
+                    }
+                }
+            }
+            __syncthreads();   // tables and scalars are rewritten by the next block / env
+        }
+        if (own) {
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) tp[r * NCHR + tid] = e[r];
+        }
+    }
+    float *out = partial + (size_t)blockIdx.x * K * AF;
+    for (int i = tid; i < K * AF; i += NT) out[i] = acc[i];
+}
+
 // dW[j] += sum over slabs; grid (ceil(n/256), slices); a few atomics per address.
 __global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const float *__restrict__ partial,
                                                 float *__restrict__ dW) {
@@ -352,7 +527,7 @@ __global__ void k_apply(int K, float *__restrict__ W, float *__restrict__ Wt, fl
             w = __fadd_rn(w, __fmul_rn(__fmul_rn(alpha, as), __fmul_rn(dW[i], scale)));
             W[i] = w;
         }
-        Wt[((size_t)k * F + f) * SCG_WT_STRIDE + a] = w;
+        Wt[((size_t)f * K + k) * SCG_WT_STRIDE + a] = w;
         dW[i] = 0.f;
     }
 }
@@ -362,6 +537,7 @@ __global__ void k_zero_int(int n, int *p) {
 }
 
 // ---- launch plumbing ----------------------------------------------------------------------------
+static int ensure_partials(scg_ctx *ctx, int n);
 template <int N1, int VEC, int CPT, int NT, int U>
 static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, float gl, cudaStream_t st) {
     size_t smem = (size_t)ctx->K * SCG_A * ctx->F * sizeof(float);
@@ -374,8 +550,9 @@ static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, 
         configured = smem;
     }
     if (per_sm < 1) return SCG_ELIMIT;
-    int grid = std::min(std::min(B, SCG_NUM_SMS * per_sm), ctx->n_partials);
-    grid = std::max(grid, 1);
+    int grid = std::max(std::min(B, SCG_NUM_SMS * per_sm), 1);
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
     kern<<<grid, NT, smem, st>>>(B, ctx->K, rec, trace, ctx->d_partial, gl);
     SCG_LAUNCH_CHECK();
     return grid;
@@ -407,15 +584,15 @@ static int launch_trace_tma_t(scg_ctx *ctx, int B, const float4 *rec, float *tra
         configured = smem;
     }
     if (per_sm < 1) return 0;
-    int grid = std::max(1, std::min(std::min(B, SCG_NUM_SMS * per_sm), ctx->n_partials));
+    int grid = std::max(1, std::min(B, SCG_NUM_SMS * per_sm));
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
     kern<<<grid, NT + 32, smem, st>>>(B, ctx->K, S, D, rec, trace, ctx->d_partial, gl);
     SCG_LAUNCH_CHECK();
     return grid;
 }
 
-// ev2: optional two events, recorded after the sweep and after the reduction
-int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float gl, float *dW, cudaStream_t st,
-                     cudaEvent_t *ev2 = nullptr) {
+int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float gl, float *dW, cudaStream_t st) {
     int grid = 0;
     const float4 *r4 = reinterpret_cast<const float4 *>(rec);
     static int u3 = -1;
@@ -447,13 +624,74 @@ int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float 
         default: return SCG_ELIMIT;
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
-    if (ev2) SCG_CUDA_OK(cudaEventRecord(ev2[0], st));
     int n = ctx->K * SCG_A * ctx->F;
     dim3 g((n + 255) / 256, std::min(grid, 32));
     k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
     SCG_LAUNCH_CHECK();
-    if (ev2) SCG_CUDA_OK(cudaEventRecord(ev2[1], st));
     return 0;
+}
+
+static int ensure_partials(scg_ctx *ctx, int n) {
+    if (n <= ctx->n_partials && ctx->d_partial) return 0;
+    if (ctx->d_partial) cudaFree(ctx->d_partial);
+    ctx->d_partial = nullptr;
+    ctx->n_partials = 0;
+    size_t slab = (size_t)ctx->K * SCG_A * ctx->F * sizeof(float);
+    SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_partial, slab * n));
+    ctx->n_partials = n;
+    return 0;
+}
+
+template <int N1, int VEC, int NT>
+static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
+    constexpr int NN = N1 * N1;
+    const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) + (size_t)SCG_WIN_TB * 2 * NN * sizeof(float2) +
+                        (size_t)SCG_WIN_TB * 4 * N1 * sizeof(float2) + (size_t)4 * SCG_WIN_MAX * sizeof(float) + 16;
+    auto kern = k_window<N1, VEC, NT>;
+    static size_t configured = 0;
+    static int per_sm = 0;
+    if (smem != configured) {
+        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+        configured = smem;
+    }
+    if (per_sm < 1) return SCG_ELIMIT;
+    static int cap = -1;
+    if (cap < 0) { const char *e = getenv("SCG_WIN_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }
+    int occ = cap > 0 ? std::min(cap, per_sm) : per_sm;
+    int grid = std::max(1, std::min(B, SCG_NUM_SMS * occ));
+    int rc = ensure_partials(ctx, grid);
+    if (rc) return rc;
+    kern<<<grid, NT, smem, st>>>(B, ctx->K, T, rec, trace, ctx->d_partial, gl);
+    SCG_LAUNCH_CHECK();
+    return grid;
+}
+
+int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
+
+// fold the T recorded steps of the window into dW and the traces
+int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace, float gl, float *dW,
+                      cudaStream_t st) {
+    if (T < 1 || T > SCG_WIN_MAX) return SCG_EINVAL;
+    const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+    int grid = 0, rc;
+    if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
+    switch (ctx->order) {
+        case 1: grid = launch_window_t<2, 4, 32>(ctx, B, T, r4, trace, gl, st); break;
+        case 2: grid = launch_window_t<3, 1, 96>(ctx, B, T, r4, trace, gl, st); break;
+        case 3: grid = launch_window_t<4, 4, 64>(ctx, B, T, r4, trace, gl, st); break;
+        case 4: grid = launch_window_t<5, 1, 640>(ctx, B, T, r4, trace, gl, st); break;
+        case 5: grid = launch_window_t<6, 4, 352>(ctx, B, T, r4, trace, gl, st); break;
+        default: return SCG_ELIMIT;
+    }
+    if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
+    if ((rc = scg_prof_push(ctx, 1, st, true))) return rc;
+    if ((rc = scg_prof_push(ctx, 2, st, false))) return rc;
+    int n = ctx->K * SCG_A * ctx->F;
+    dim3 g((n + 255) / 256, std::min(grid, 32));
+    k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
+    SCG_LAUNCH_CHECK();
+    return scg_prof_push(ctx, 2, st, true);
 }
 
 extern "C" int scg_ctx_create(int order, int K, scg_ctx_t **out) {
@@ -467,13 +705,7 @@ extern "C" int scg_ctx_create(int order, int K, scg_ctx_t **out) {
         free(c);
         return SCG_ELIMIT;
     }
-    c->n_partials = SCG_NUM_SMS * 8;
-    cudaError_t e = cudaMalloc((void **)&c->d_partial, slab * c->n_partials);
-    if (e != cudaSuccess) {
-        free(c);
-        return (int)e;
-    }
-    *out = c;
+    *out = c;   // the per-CTA dW slabs are allocated by the first sweep (ensure_partials)
     return 0;
 }
 
@@ -481,8 +713,9 @@ extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
     if (!c) return 0;
     if (c->d_partial) cudaFree(c->d_partial);
     if (c->d_rec) cudaFree(c->d_rec);
-    for (int i = 0; i < 5 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
+    for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
     free(c->prof_ev);
+    free(c->prof_kind);
     free(c);
     return 0;
 }

@@ -85,10 +85,11 @@ class OptionSet:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         z = dict(dtype=torch.float32, device=self.device)
         self.W = torch.zeros((self.K, N_ACTIONS, self.F), **z)
-        self.Wt = torch.zeros((self.K, self.F, 8), **z)
+        self.Wt = torch.zeros((self.F, self.K, 8), **z)
         self.theta = torch.zeros((self.K, N_PSI), **z)
-        self.trace = torch.zeros((self.B, N_ACTIONS, self.F), **z)
-        self.dW = torch.zeros((self.K, N_ACTIONS, self.F), **z)
+        self._trace = torch.zeros((self.B, N_ACTIONS, self.F), **z)
+        self._dW = torch.zeros((self.K, N_ACTIONS, self.F), **z)
+        self._pre_read = None        # set by SkillChainAgent: folds its open window in before a read
         self.cnt = torch.zeros(self.K, dtype=torch.int32, device=self.device)
         self.window_steps = 0
         self._ctx = C.c_void_p()
@@ -105,6 +106,20 @@ class OptionSet:
     @property
     def ctx(self):
         return self._ctx
+
+    @property
+    def trace(self):
+        """Per-env eligibility traces (B, A, F)."""
+        if self._pre_read is not None:
+            self._pre_read()
+        return self._trace
+
+    @property
+    def dW(self):
+        """Weight deltas accumulated since the last apply (K, A, F)."""
+        if self._pre_read is not None:
+            self._pre_read()
+        return self._dW
 
     # -- weights ---------------------------------------------------------------------------------
     def set_weights(self, W):
@@ -162,7 +177,7 @@ class OptionSet:
             delta = torch.where(m.bool(), delta, torch.zeros_like(delta))
         gl = float(np.float32(self.gamma) * np.float32(self.lam))
         check(self.lib.scg_sarsa_update(self._ctx, self.B, ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(a),
-                                        ptr(o), ptr(delta), ptr(d), ptr(m), gl, ptr(self.trace), ptr(self.dW),
+                                        ptr(o), ptr(delta), ptr(d), ptr(m), gl, ptr(self._trace), ptr(self._dW),
                                         ptr(self.cnt), _lib.current_stream()))
         return delta
 
@@ -171,7 +186,9 @@ class OptionSet:
 
     def apply(self):
         """Fold the window's dW into W (call after any cross-rank allreduce of dW / cnt)."""
-        check(self.lib.scg_apply(self.order, self.K, ptr(self.W), ptr(self.Wt), ptr(self.dW), ptr(self.cnt),
+        if self._pre_read is not None:
+            self._pre_read()
+        check(self.lib.scg_apply(self.order, self.K, ptr(self.W), ptr(self.Wt), ptr(self._dW), ptr(self.cnt),
                                  self.alpha, max(self.window_steps, 1), _lib.current_stream()))
         self.window_steps = 0
 

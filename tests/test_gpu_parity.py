@@ -393,3 +393,162 @@ def test_agent_run_and_manage_promotes_option(scg, torch):
         ag.step()
     torch.cuda.synchronize()
     assert int((ag.option == 1).sum()) > 0                 # the new gestating option is being executed
+
+
+# ---- windowed pipeline -------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,K,window,name", [(3, 4, 8, "easy"), (2, 3, 5, "easy"), (5, 8, 8, "hard"), (1, 2, 3, "easy"),
+                                                 (4, 2, 4, "hard"), (3, 4, 20, "easy")])
+def test_windowed_sweep_equals_oracle_dense_traces(scg, torch, order, K, window, name):
+    """One window of fused steps with frozen weights: the GPU's forward-view sweep must reproduce the
+    oracle's DENSE per-step traces and dW (the parity target is the dense form's numbers)."""
+    B = 700 if order >= 4 else 2500
+    kw = dict(sync_interval=1000, option_timeout=5, epsilon=0.5, alpha=0.0, max_episode_steps=11)
+    oag, gag = _paired_agents(scg, torch, B, order, K, name, 7, **kw)
+    gag2 = None
+    theta = np.zeros((K, 6), dtype=np.float32)
+    theta[0] = [-1.0, 2.0, 0.0, 0.0, 0.0, 0.0]
+    oag.options.theta[:] = theta
+    oag.active[0] = True
+    oag.n_active = 1
+    oag.parents[1] = 1
+    gag.options.theta.copy_(torch.as_tensor(theta))
+    gag.active_mask, gag.n_active = 1, 1
+    gag.parents_host[1] = 1
+    gag._push_parents()
+    gag.win_cap = window
+    # rebuild the window buffer for the requested window length
+    gag.win_rec = torch.zeros((window, B, 8), dtype=torch.float32, device="cuda")
+    gag._struct.win_rec = gag.win_rec.data_ptr()
+    gag._struct.win_cap = window
+    n_steps = min(window, 12)
+    for t in range(n_steps):
+        out = oag.step()
+        gag.step()
+        # with eps = 0.5 most actions are exploratory (identical draws); follow the oracle's choices exactly
+        # so that the recorded transitions are the same on both sides
+        gag.action.copy_(torch.as_tensor(out["action"]))
+        gag.option.copy_(torch.as_tensor(out["option"]))
+        gag.invalidate()
+        assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
+        assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+    assert out is not None and int(gag._struct.win_len) == (n_steps % window)
+    assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL      # property flushes the window
+    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
+    assert int(gag._struct.win_len) == 0
+    assert oag.n_fail.sum() + oag.n_success.sum() > B // 4                          # terminations inside the window
+
+
+def test_carried_q_equals_recomputed_q(scg, torch):
+    """Q_o(s, a) carried from the previous step == the value recomputed from scratch every step."""
+    B = 4096
+    ags = []
+    for _ in range(2):
+        _, gag = _paired_agents(scg, torch, B, 3, 4, "easy", 3, sync_interval=4, epsilon=0.1, option_timeout=6)
+        ags.append(gag)
+    a, b = ags
+    for t in range(10):
+        a.step()
+        b.invalidate()
+        b.step()
+        assert torch.equal(a.s, b.s) and torch.equal(a.action, b.action) and torch.equal(a.option, b.option)
+        assert float((a.delta - b.delta).abs().max()) <= 1e-5 * max(1.0, float(b.delta.abs().max()))
+    assert float((a.options.W - b.options.W).abs().max()) <= 1e-6 * max(1.0, float(b.options.W.abs().max()))
+
+
+def test_run_equals_step_loop_and_host_step(scg, torch):
+    B = 2048
+    (_, a), (_, b), (_, c) = (_paired_agents(scg, torch, B, 3, 3, "easy", 5, sync_interval=3, epsilon=0.05)
+                              for _ in range(3))
+    a.run(10)
+    for _ in range(10):
+        b.step()
+    hs, ha = c.s.cpu().numpy().copy(), c.action.cpu().numpy().copy()
+    for _ in range(10):
+        hs, r, f, ha, d = c.step_host(hs, ha)
+    torch.cuda.synchronize()
+    assert a.t == b.t == c.t == 10
+    # (the dW slab reduction adds with atomics, so weights agree to rounding, not bit for bit)
+    assert torch.equal(a.s, b.s) and torch.equal(a.action, b.action)
+    assert float((a.options.W - b.options.W).abs().max()) <= 1e-6 * max(1.0, float(a.options.W.abs().max()))
+    assert np.array_equal(hs, a.s.cpu().numpy()) and np.array_equal(ha, a.action.cpu().numpy())
+    assert float((c.options.W - a.options.W).abs().max()) <= 1e-6 * max(1.0, float(a.options.W.abs().max()))
+    assert np.array_equal(d, c.delta.cpu().numpy())
+
+
+# ---- golden fixtures (tests/golden, made by tools/make_golden.py from the oracle) ----------------------
+import os  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["easy", "hard"])
+def test_golden_step(scg, torch, name):
+    g = np.load(os.path.join(GOLD, f"step_{name}.npz"))
+    gmap = scg.PinballMap.from_name(name)
+    env = scg.PinballEnv(gmap, len(g["state"]))
+    env.reset(states=g["state"])
+    ns, r, done, hit = env.step(torch.as_tensor(g["action"]).cuda())
+    assert np.array_equal(ns.cpu().numpy().view(np.uint32), g["next_state"].view(np.uint32))
+    assert np.array_equal(env.flags.cpu().numpy(), g["flags"]) and np.array_equal(r.cpu().numpy(), g["reward"])
+
+
+@pytest.mark.parametrize("order", [3, 5])
+def test_golden_features_q(scg, torch, order):
+    g = np.load(os.path.join(GOLD, f"features_q_o{order}.npz"))
+    assert np.abs(scg.FourierBasis(order).features(g["state"]).cpu().numpy() - g["phi"]).max() < 2e-5
+    s = scg.OptionSet(g["W"].shape[0], order, len(g["state"]))
+    s.set_weights(g["W"])
+    assert rel_err(s.q(g["state"], g["option"]).cpu().numpy(), g["Q"]) < RTOL
+
+
+def test_golden_sarsa_and_classifier(scg, torch):
+    g = np.load(os.path.join(GOLD, "sarsa_o3.npz"))
+    gamma, lam, alpha = (float(v) for v in g["hp"])
+    s = scg.OptionSet(g["W0"].shape[0], 3, g["S"].shape[1], gamma=gamma, lam=lam, alpha=alpha, seed=1)
+    s.set_weights(g["W0"])
+    for it in range(6):
+        d = s.update(g["S"][it], g["A"][it], g["r"][it], g["S2"][it], g["A2"][it], g["done"][it], g["option"][it])
+        s.tick()
+        assert rel_err(d.cpu().numpy(), g["delta"][it]) < RTOL
+        if it == 2:
+            assert rel_err(s.dW.cpu().numpy(), g["dW3"]) < RTOL and np.array_equal(s.cnt.cpu().numpy(), g["cnt3"])
+            assert rel_err(s.trace.double().sum(dim=2).cpu().numpy(), g["trace3_sum"]) < RTOL
+            s.apply()
+            assert rel_err(s.W.cpu().numpy(), g["W3"]) < RTOL
+    assert rel_err(s.dW.cpu().numpy(), g["dW_end"]) < RTOL
+    assert rel_err(s.trace.double().sum(dim=2).cpu().numpy(), g["trace_end_sum"]) < RTOL
+    c = np.load(os.path.join(GOLD, "classifier.npz"))
+    k = scg.OptionSet(2, 1, 1)
+    k.theta[0].copy_(torch.as_tensor(c["theta0"]))
+    assert rel_err(k.clf_grad(0, c["X"], c["y"]).cpu().numpy(), c["grad0"]) < RTOL
+    assert rel_err(k.fit_initiation(1, c["X"], c["y"], steps=100, lr=2.0).cpu().numpy(), c["theta1_fit"]) < RTOL
+    S4 = np.concatenate([c["X"], np.zeros_like(c["X"])], axis=1)
+    assert rel_err(k.initiation_prob(S4).cpu().numpy(), c["prob"]) < RTOL
+
+
+def test_golden_agent_step(scg, torch):
+    g = np.load(os.path.join(GOLD, "agent_step.npz"))
+    B, K = len(g["state"]), g["theta"].shape[0]
+    gmap = scg.PinballMap.from_name("easy")
+    cfg = scg.AgentConfig(map="easy", batch=B, order=3, max_options=K, seed=2, sync_interval=3, option_timeout=3,
+                          epsilon=0.2)
+    ag = scg.SkillChainAgent(cfg, gmap, initial_states=g["state"])
+    ag.options.set_weights(g["W"])
+    ag.options.theta.copy_(torch.as_tensor(g["theta"]))
+    ag.active_mask, ag.n_active = 3, 2
+    ag.parents_host[1], ag.parents_host[2] = 1, 2
+    ag._push_parents()
+    ag.option.copy_(torch.as_tensor(g["option"]))
+    ag.t_opt.copy_(torch.as_tensor(g["t_opt"]))
+    ag.action.copy_(torch.as_tensor(g["action"]))
+    ag.step()
+    torch.cuda.synchronize()
+    assert np.array_equal(ag.state.cpu().numpy().view(np.uint32), g["next_state"].view(np.uint32))
+    assert rel_err(ag.delta.cpu().numpy(), g["delta"]) < RTOL
+    assert np.array_equal(ag.option.cpu().numpy(), g["next_option"])
+    assert np.array_equal(ag.t_opt.cpu().numpy(), g["t_opt_after"])
+    assert np.array_equal(ag.n_success.cpu().numpy(), g["n_success"]) and np.array_equal(ag.n_fail.cpu().numpy(), g["n_fail"])
+    assert np.array_equal(ag.options.cnt.cpu().numpy(), g["cnt"])
+    assert rel_err(ag.options.dW.cpu().numpy(), g["dW"]) < RTOL
+    assert rel_err(ag.options.trace.double().sum(dim=2).cpu().numpy(), g["trace_sum"]) < RTOL
