@@ -309,17 +309,23 @@ __global__ void __launch_bounds__(NT + 32) k_trace_tma(int B, int K, int S, int 
 // window, a 32-byte record per env (state, delta, action / option / termination bits).  One CTA sweeps
 // one env at a time; thread t owns the same VEC features of all A rows of every env's trace (registers)
 // and of the CTA's dW accumulator (shared memory, [K][A*F], plain read-modify-write: ownership is
-// exclusive).  Per env:
-//   phase A  threads 0..4T-1 load the records, turn each state component into z = exp(i pi s_hat) and
-//            its powers z^0..z^(N1-1)                                             -> pw[t][j][c]
-//   phase B  pair tables P01[t][c0][c1] = z0^c0 z1^c1 and P23[t][c2][c3] = z2^c2 z3^c3 (one complex
-//            multiply per entry), while one thread runs the backward recursion
-//            G_t = delta_t + (done_t ? 0 : gl G_{t+1}) and the trace coefficients c_t
-//   phase C  e <- scale e (+ carry-in dW[o_0] += gl G_0 e_start);  for every step:
-//            phi_f = Re(P01[f / N1^2] P23[f % N1^2]);  dW[o_t][a_t][f] += G_t phi_f;  e[a_t][f] += c_t phi_f
-// so a feature costs two 8-byte shared loads and two FP32 ops to form, and the dense trace crosses HBM
-// once per window: 8*A*F/T + 32 algorithmic bytes per env-step.
+// exclusive).  Work items are (env, block of 8 steps); per item:
+//   build  every thread forms a few entries of the pair tables P01[t][c0][c1] = exp(i pi (c0 s0 + c1 s1))
+//          and P23[t][c2][c3] = exp(i pi (c2 s2 + c3 s3)) with one sincospi each; for the env's first
+//          block one thread also runs the backward recursion G_t = delta_t + (done_t ? 0 : gl G_{t+1})
+//          and the trace coefficients c_t
+//   main   phi_f = Re(P01[f / N1^2] P23[f % N1^2]);  d[a_t][f] += G_t phi_f;  e[a_t][f] += c_t phi_f
+//          with d (the env's dW contribution, seeded with the carry-in gl G_0 e_start) and e in registers;
+//          d is added to the shared accumulator once per env (or when the option changes)
+// The tables are double-buffered and the records / traces of the following items are prefetched into
+// registers, so there is one barrier per item and no phase waits on a load it has just issued.  A feature
+// costs two 8-byte shared loads and two FP32 ops to form, and the dense trace crosses HBM once per
+// window: 8*A*F/T + 32 algorithmic bytes per env-step.
 #define SCG_WIN_TB 8   // steps per table block
+
+struct WinItem {   // a work item of the sweep: block `blk` of 8 steps of env `b`
+    int b, blk;
+};
 
 template <int N1, int VEC, int NT>
 __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
@@ -329,151 +335,209 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
     constexpr int AF = SCG_A * F;
     constexpr int NCHR = F / VEC;          // chunks per action row
     constexpr int NN = N1 * N1;
-    static_assert(F % VEC == 0 && NT >= NCHR && NT >= 4 * SCG_WIN_TB, "layout");
+    constexpr int TABN = SCG_WIN_TB * 2 * NN;             // entries of one table buffer
+    constexpr int EPT = (TABN + NT - 1) / NT;             // table entries built per thread
+    static_assert(F % VEC == 0 && NT >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
+    static_assert(VEC == 1 || NN % VEC == 0, "a chunk shares its (c0, c1) digits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *acc = reinterpret_cast<float *>(smem_raw);                       // [K][AF]
-    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [TB][2][NN], 16-byte aligned
-    float2 *pw = tab + SCG_WIN_TB * 2 * NN;                                 // [TB][4][N1]
-    float *sG = reinterpret_cast<float *>(pw + SCG_WIN_TB * 4 * N1);        // [SCG_WIN_MAX]
-    float *sC = sG + SCG_WIN_MAX;                                           // [SCG_WIN_MAX]
-    float *sD = sC + SCG_WIN_MAX;                                           // [SCG_WIN_MAX] deltas
-    uint32_t *sM = reinterpret_cast<uint32_t *>(sD + SCG_WIN_MAX);          // [SCG_WIN_MAX] meta
-    float *sS = reinterpret_cast<float *>(sM + SCG_WIN_MAX);                // [0] scale, [1] carry, [2] o0 bits
+    float *acc = reinterpret_cast<float *>(smem_raw);                                      // [K][AF]
+    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [2][TABN]
+    float4 *sStep = reinterpret_cast<float4 *>(tab + 2 * TABN);                            // [2][SCG_WIN_MAX]: G, c, meta
+    float4 *sHead = sStep + 2 * SCG_WIN_MAX;                                               // [2]: scale, carry, o0
+    float *glpow = reinterpret_cast<float *>(sHead + 2);                                   // [36]: gl^n
 
     const int tid = threadIdx.x;
     const bool own = tid < NCHR;
-    // per-thread constants: table indices of the VEC owned features (same in every row)
-    int i01[VEC], i23[VEC];
+    const int NBLK = (T + SCG_WIN_TB - 1) / SCG_WIN_TB;
+    // per-thread constants: table offsets (bytes) of the owned features' (c0, c1) and (c2, c3) entries ...
+    const int f0 = (own ? tid : 0) * VEC;
+    const int off01 = (f0 / NN) * (int)sizeof(float2);
+    const int off23 = (NN + f0 % NN) * (int)sizeof(float2);
+    // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits
+    int e_tt[EPT], e_half[EPT];
+    float e_ca[EPT], e_cb[EPT];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        int f = (own ? tid : 0) * VEC + v;
-        i01[v] = f / NN;
-        i23[v] = NN + f % NN;
+    for (int k = 0; k < EPT; ++k) {
+        int idx = tid + k * NT;
+        if (idx >= TABN) idx = TABN - 1;                 // duplicate work on the last entry, never out of range
+        const int tt = idx / (2 * NN), rem = idx - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
+        e_tt[k] = tt; e_half[k] = half;
+        e_ca[k] = (float)(ij / N1); e_cb[k] = (float)(ij % N1);
     }
     for (int i = tid; i < K * AF; i += NT) acc[i] = 0.f;
-    __syncthreads();
+    if (tid == 0) {
+        float p = 1.f;
+        for (int n = 0; n < 36; ++n) { glpow[n] = p; p *= gl; }
+    }
 
-    // software pipeline: the trace and the first table block's records of env i+1 are loaded while env i
-    // is processed, so no phase waits on a global load it has just issued
-    V e[SCG_A], e_nx[SCG_A];
-    float sv_nx = 0.f;
-    float2 dm_nx = make_float2(0.f, 0.f);
-    auto prefetch = [&](int b) {
+    const int stride = gridDim.x;
+    auto advance = [&](WinItem it) {
+        if (++it.blk == NBLK) { it.blk = 0; it.b += stride; }
+        return it;
+    };
+
+    // prefetch registers
+    float2 r_sv[EPT];                                    // state pair of the steps this thread builds entries for
+    float2 r_dm = make_float2(0.f, 0.f);                 // (delta, meta) of step tid (first block of an env only)
+    V e[SCG_A], e_nx[SCG_A], d[SCG_A];
+    int o_cur = 0;
+#pragma unroll
+    for (int r = 0; r < SCG_A; ++r) {
+        if constexpr (VEC == 4) { e[r] = vzero4(); e_nx[r] = vzero4(); d[r] = vzero4(); }
+        else { e[r] = 0.f; e_nx[r] = 0.f; d[r] = 0.f; }
+    }
+
+    auto load_rec = [&](WinItem it) {                    // records of a work item -> registers
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int t = min(it.blk * SCG_WIN_TB + e_tt[k], T - 1);
+            r_sv[k] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + e_half[k]);
+        }
+        if (it.blk == 0 && tid < T)
+            r_dm = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)tid * B + it.b) * 2 + 1));
+    };
+    auto load_trace = [&](int b) {
         const V *tp = reinterpret_cast<const V *>(trace + (size_t)b * AF);
         if (own) {
 #pragma unroll
             for (int r = 0; r < SCG_A; ++r) e_nx[r] = tp[r * NCHR + tid];
         }
-        if (tid < T) dm_nx = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)tid * B + b) * 2 + 1));
-        if (tid < min(T, SCG_WIN_TB) * 4)
-            sv_nx = __ldg(reinterpret_cast<const float *>(rec + ((size_t)(tid >> 2) * B + b) * 2) + (tid & 3));
     };
-    if ((int)blockIdx.x < B) prefetch(blockIdx.x);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    // registers -> pair tables (buffer `par`) and, for an env's first block, its step scalars (buffer `epar`)
+    auto build = [&](WinItem it, int par, int epar) {
+        float2 *tb = tab + par * TABN;
 #pragma unroll
-        for (int r = 0; r < SCG_A; ++r) e[r] = e_nx[r];
-        float sv0 = sv_nx;
-        const float2 dm = dm_nx;
-        if (b + (int)gridDim.x < B) prefetch(b + gridDim.x);
-        V *tp = reinterpret_cast<V *>(trace + (size_t)b * AF);
-        for (int t0 = 0; t0 < T; t0 += SCG_WIN_TB) {
-            const int nb = min(SCG_WIN_TB, T - t0);
-            // ---- phase A: deltas / meta of all T steps (first block only) and phasor powers of this block ----
-            if (t0 == 0 && tid < T) {
-                sD[tid] = dm.x;
-                sM[tid] = __float_as_uint(dm.y);
+        for (int k = 0; k < EPT; ++k) {
+            float s0 = r_sv[k].x, s1 = r_sv[k].y;
+            if (e_half[k]) {                             // velocities: oracle/fourier.py normalise
+                s0 = __fmul_rn(__fadd_rn(s0, 2.0f), 0.25f);
+                s1 = __fmul_rn(__fadd_rn(s1, 2.0f), 0.25f);
             }
-            for (int i = tid; i < nb * 4; i += NT) {
-                const int tt = i >> 2, j = i & 3;
-                float sv;
-                if (t0 == 0 && i == tid) sv = sv0;   // prefetched (NT >= 4 * SCG_WIN_TB)
-                else sv = __ldg(reinterpret_cast<const float *>(rec + ((size_t)(t0 + tt) * B + b) * 2) + j);
-                if (j >= 2) sv = __fmul_rn(__fadd_rn(sv, 2.0f), 0.25f);   // oracle/fourier.py normalise
-                float2 z, p = make_float2(1.f, 0.f);
-                sincospif(sv, &z.y, &z.x);
-                float2 *dst = pw + (tt * 4 + j) * N1;
-#pragma unroll
-                for (int c = 0; c < N1; ++c) {
-                    dst[c] = p;
-                    p = scg_cmul(p, z);
-                }
-            }
-            __syncthreads();
-            // ---- phase B: pair tables; one thread runs the backward recursion (first block only) ----
-            for (int i = tid; i < nb * 2 * NN; i += NT) {
-                const int tt = i / (2 * NN), rem = i - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
-                const float2 *pa = pw + (tt * 4 + 2 * half) * N1;
-                tab[i] = scg_cmul(pa[ij / N1], pa[N1 + ij % N1]);
-            }
-            if (t0 == 0 && tid == NT - 1) {
-                float nxt = 0.f, cc = 1.f;
-                bool dead = false;
-                uint32_t o0 = 0;
-                bool any = false;
-                for (int t = T - 1; t >= 0; --t) {
-                    const uint32_t meta = sM[t];
-                    const bool act = (meta & SCG_META_ACTIVE) != 0;
-                    const bool dn = act && (meta & SCG_META_ZERO_AFTER);
-                    if (act) {
-                        nxt = dn ? sD[t] : fmaf(gl, nxt, sD[t]);
-                        dead = dead || dn;
-                        sC[t] = dead ? 0.f : cc;
-                        cc *= gl;
-                        o0 = (meta >> 8) & 0xFF;
-                        any = true;
-                    } else {
-                        sC[t] = 0.f;
-                    }
-                    sG[t] = act ? nxt : 0.f;
-                }
-                sS[0] = dead ? 0.f : cc;
-                sS[1] = any ? gl * nxt : 0.f;
-                sS[2] = __uint_as_float(o0);
-            }
-            __syncthreads();
-            // ---- phase C ----
-            if (own) {
-                if (t0 == 0) {
-                    const float scale = sS[0], carry = sS[1];
-                    if (carry != 0.f) {
-                        V *ap = reinterpret_cast<V *>(acc + (size_t)__float_as_uint(sS[2]) * AF);
-#pragma unroll
-                        for (int r = 0; r < SCG_A; ++r) ap[r * NCHR + tid] = vfma(carry, e[r], ap[r * NCHR + tid]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < SCG_A; ++r) e[r] = vscale(e[r], scale);
-                }
-                for (int tt = 0; tt < nb; ++tt) {
-                    const float G = sG[t0 + tt], c = sC[t0 + tt];
-                    if (G == 0.f && c == 0.f) continue;
-                    const uint32_t meta = sM[t0 + tt];
-                    const int a = meta & 7, o = (meta >> 8) & 0xFF;
-                    const float2 *tb = tab + tt * 2 * NN;
-                    float phi[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float2 p = tb[i01[v]], q = tb[i23[v]];
-                        phi[v] = fmaf(p.x, q.x, -p.y * q.y);
-                    }
-                    V ph;
-                    if constexpr (VEC == 4) ph = make_float4(phi[0], phi[1], phi[2], phi[3]); else ph = phi[0];
-                    V *ap = reinterpret_cast<V *>(acc + ((size_t)o * SCG_A + a) * F) + tid;
-                    *ap = vfma(G, ph, *ap);
-                    switch (a) {   // warp-uniform
-                        case 0: e[0] = vfma(c, ph, e[0]); break;
-                        case 1: e[1] = vfma(c, ph, e[1]); break;
-                        case 2: e[2] = vfma(c, ph, e[2]); break;
-                        case 3: e[3] = vfma(c, ph, e[3]); break;
-                        default: e[4] = vfma(c, ph, e[4]); break;
-                    }
-                }
-            }
-            __syncthreads();   // tables and scalars are rewritten by the next block / env
+            // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
+            const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
+            const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
+            const int idx = tid + k * NT;
+            if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
         }
+        if (it.blk == 0 && tid < 32) {
+            // warp 0: backward recursion G_t = delta_t + m_t G_{t+1} as a suffix scan over (m, delta) pairs,
+            // m_t = 0 after a termination, gl otherwise (1 for a step the env sat out)
+            const int t = tid;
+            const uint32_t meta = (t < T) ? __float_as_uint(r_dm.y) : 0u;
+            const bool act = (meta & SCG_META_ACTIVE) != 0;
+            const bool dn = act && (meta & SCG_META_ZERO_AFTER);
+            float D = act ? r_dm.x : 0.f, M = !act ? 1.f : (dn ? 0.f : gl);
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float D2 = __shfl_down_sync(0xffffffffu, D, off), M2 = __shfl_down_sync(0xffffffffu, M, off);
+                if (t + off < 32) { D = fmaf(M, D2, D); M *= M2; }
+            }
+            const unsigned am = __ballot_sync(0xffffffffu, act), dm = __ballot_sync(0xffffffffu, dn);
+            const bool dead = (dm >> t) != 0;                     // a termination at this step or later in the window
+            const float cf = (act && !dead) ? glpow[__popc((am >> t) >> 1)] : 0.f;
+            if (t < T) sStep[epar * SCG_WIN_MAX + t] = make_float4(act ? D : 0.f, cf, __uint_as_float(meta), 0.f);
+            const int t0 = am ? __ffs(am) - 1 : 0;
+            const uint32_t o0 = (__shfl_sync(0xffffffffu, meta, t0) >> 8) & 0xFF;
+            if (t == 0) sHead[epar] = make_float4(dm ? 0.f : glpow[__popc(am)], am ? gl * D : 0.f, __uint_as_float(o0), 0.f);
+        }
+    };
+    auto flush_d = [&]() {
         if (own) {
+            V *ap = reinterpret_cast<V *>(acc + (size_t)o_cur * AF);
 #pragma unroll
-            for (int r = 0; r < SCG_A; ++r) tp[r * NCHR + tid] = e[r];
+            for (int r = 0; r < SCG_A; ++r) {
+                V cur = ap[r * NCHR + tid];
+                if constexpr (VEC == 4) cur = make_float4(cur.x + d[r].x, cur.y + d[r].y, cur.z + d[r].z, cur.w + d[r].w);
+                else cur = cur + d[r];
+                ap[r * NCHR + tid] = cur;
+            }
         }
+    };
+
+    WinItem cur = {(int)blockIdx.x, 0};
+    if (cur.b < B) {
+        load_rec(cur);
+        load_trace(cur.b);
+    }
+    __syncthreads();                                     // accumulator zeroed, glpow ready
+    WinItem nxt = advance(cur);
+    if (cur.b < B) build(cur, 0, 0);
+    if (nxt.b < B) load_rec(nxt);
+    __syncthreads();
+
+    int par = 0, epar = 0;
+    while (cur.b < B) {
+        const WinItem nx2 = advance(nxt);
+        if (cur.blk == 0) {
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) e[r] = e_nx[r];
+        }
+        // next item's tables (into the other buffer), then the loads for the items after it
+        if (nxt.b < B) build(nxt, par ^ 1, nxt.blk == 0 ? epar ^ 1 : epar);
+        if (nx2.b < B) load_rec(nx2);
+        if (nxt.blk == 0 && nxt.b < B) load_trace(nxt.b);
+        // ---- main ----
+        const float4 *st = sStep + epar * SCG_WIN_MAX + cur.blk * SCG_WIN_TB;
+        const char *tb0 = reinterpret_cast<const char *>(tab + par * TABN);
+        if (cur.blk == 0) {
+            const float4 hd = sHead[epar];
+            o_cur = (int)__float_as_uint(hd.z);
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) {
+                d[r] = vscale(e[r], hd.y);               // carry-in: gl G_0 e_start
+                e[r] = vscale(e[r], hd.x);
+            }
+        }
+        const int nb = min(SCG_WIN_TB, T - cur.blk * SCG_WIN_TB);
+#pragma unroll
+        for (int tt = 0; tt < SCG_WIN_TB; ++tt) {
+            if (tt >= nb) break;
+            const float4 sv = st[tt];
+            const float G = sv.x, c = sv.y;
+            if (G == 0.f && c == 0.f) continue;
+            const uint32_t meta = __float_as_uint(sv.z);
+            const int a = meta & 7, o = (meta >> 8) & 0xFF;
+            if (o != o_cur) {                            // the env changed option inside the window (after a termination)
+                flush_d();
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) {
+                    if constexpr (VEC == 4) d[r] = vzero4(); else d[r] = 0.f;
+                }
+                o_cur = o;
+            }
+            const char *tb = tb0 + tt * 2 * NN * (int)sizeof(float2);
+            const float2 p = *reinterpret_cast<const float2 *>(tb + off01);
+            V ph;
+            if constexpr (VEC == 4) {
+                const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23);
+                const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23 + 16);
+                ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
+                                 fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
+            } else {
+                const float2 q = *reinterpret_cast<const float2 *>(tb + off23);
+                ph = fmaf(p.x, q.x, -p.y * q.y);
+            }
+            switch (a) {   // CTA-uniform
+                case 0: d[0] = vfma(G, ph, d[0]); e[0] = vfma(c, ph, e[0]); break;
+                case 1: d[1] = vfma(G, ph, d[1]); e[1] = vfma(c, ph, e[1]); break;
+                case 2: d[2] = vfma(G, ph, d[2]); e[2] = vfma(c, ph, e[2]); break;
+                case 3: d[3] = vfma(G, ph, d[3]); e[3] = vfma(c, ph, e[3]); break;
+                default: d[4] = vfma(G, ph, d[4]); e[4] = vfma(c, ph, e[4]); break;
+            }
+        }
+        if (cur.blk == NBLK - 1) {
+            flush_d();
+            if (own) {
+                V *tp = reinterpret_cast<V *>(trace + (size_t)cur.b * AF);
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) tp[r * NCHR + tid] = e[r];
+            }
+        }
+        __syncthreads();   // the tables just built become readable, the ones just read become writable
+        if (nxt.blk == 0) epar ^= 1;
+        par ^= 1;
+        cur = nxt;
+        nxt = nx2;
     }
     float *out = partial + (size_t)blockIdx.x * K * AF;
     for (int i = tid; i < K * AF; i += NT) out[i] = acc[i];
@@ -645,8 +709,8 @@ static int ensure_partials(scg_ctx *ctx, int n) {
 template <int N1, int VEC, int NT>
 static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
     constexpr int NN = N1 * N1;
-    const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) + (size_t)SCG_WIN_TB * 2 * NN * sizeof(float2) +
-                        (size_t)SCG_WIN_TB * 4 * N1 * sizeof(float2) + (size_t)4 * SCG_WIN_MAX * sizeof(float) + 16;
+    const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
+                        (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + (size_t)(2 * SCG_WIN_MAX + 2) * sizeof(float4) + 36 * sizeof(float);
     auto kern = k_window<N1, VEC, NT>;
     static size_t configured = 0;
     static int per_sm = 0;
