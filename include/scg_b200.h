@@ -153,8 +153,8 @@ typedef struct scg_agent {
     uint32_t *parents;               /* [K] */
     float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */
     int32_t *ex_count, *n_success, *n_fail; /* [K] */
-    /* global statistics (device): [0] episodes, [1] goals, [2] sum of finished returns (float bits) */
-    int32_t *stats;
+    /* global statistics (device), 4 x 64 bit: [0] episodes, [1] goals (uint64), [2] sum of finished returns (double) */
+    int64_t *stats;
 } scg_agent_t;
 
 /* One lock-step agent step.  Updates the struct: swaps (x..vy) with (x2..vy2) so that x..vy is the new

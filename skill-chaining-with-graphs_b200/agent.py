@@ -90,7 +90,7 @@ class SkillChainAgent:
         self.ex_count = torch.zeros(K, **i32)
         self.n_success = torch.zeros(K, **i32)
         self.n_fail = torch.zeros(K, **i32)
-        self.stats = torch.zeros(4, **i32)
+        self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
         self.active_mask = 0
         self.n_active = 0
         # initial state, option and action (oracle/agent.py __init__)
@@ -246,7 +246,7 @@ class SkillChainAgent:
 
     # -- low-rate controller ---------------------------------------------------------------------
     def examples(self, k):
-        n = int(min(int(self.ex_count[k]), self.cfg.example_capacity))
+        n = int(min(int(self.ex_count[k]) & 0xFFFFFFFF, self.cfg.example_capacity))
         return self.ex_xy[k, :n].clone(), self.ex_label[k, :n].clone()
 
     def manage(self):
@@ -257,7 +257,8 @@ class SkillChainAgent:
         g = self.n_active
         if g >= K - 1:
             return False
-        n_succ = allreduce_scalar_sum(self.n_success[g:g + 1].clone(), self.pg)
+        # the device counter is 32 bits and wraps: read it as unsigned, sum over ranks in 64 bits
+        n_succ = allreduce_scalar_sum(self.n_success[g:g + 1].to(torch.int64) & 0xFFFFFFFF, self.pg)
         if int(n_succ) < cfg.gestation_successes:
             return False
         X, y = self.examples(g)
@@ -279,9 +280,10 @@ class SkillChainAgent:
         """Host copy of the global statistics: episodes, goals, mean finished return, per-option counts."""
         st = self.stats.cpu().numpy()
         ep = int(st[0])
-        ret = float(st[2:3].view(np.float32)[0])
+        ret = float(st[2:3].view(np.float64)[0])
         return dict(episodes=ep, goals=int(st[1]), mean_return=(ret / ep) if ep else float("nan"),
-                    n_success=self.n_success.cpu().numpy().copy(), n_fail=self.n_fail.cpu().numpy().copy(),
+                    n_success=self.n_success.cpu().numpy().view(np.uint32).astype(np.int64),
+                    n_fail=self.n_fail.cpu().numpy().view(np.uint32).astype(np.int64),
                     n_active=self.n_active)
 
     def run_episode(self, max_steps=2000, manage_every=64):

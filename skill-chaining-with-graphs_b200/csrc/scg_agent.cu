@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ Step
             rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
             // 6: example for option o's initiation classifier
             if (term) {
-                const int eslot = atomicAdd(g.ex_count + o, 1) % (int)g.example_capacity;
+                const uint32_t eslot = (uint32_t)atomicAdd(g.ex_count + o, 1) % g.example_capacity;   // unsigned: safe past 2^31 appends
                 const size_t ei = (size_t)o * g.example_capacity + eslot;
                 g.ex_xy[2 * ei] = g.start_xy[2 * b];
                 g.ex_xy[2 * ei + 1] = g.start_xy[2 * b + 1];
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ Step
                 const int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
                 const float2 s0 = reinterpret_cast<const float2 *>(smem + mh->off_starts)[pick];
                 nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
-                atomicAdd(g.stats + 0, 1);
-                if (env_done) atomicAdd(g.stats + 1, 1);
-                atomicAdd(reinterpret_cast<float *>(g.stats + 2), ret);
+                atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 0, 1ull);
+                if (env_done) atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 1, 1ull);
+                atomicAdd(reinterpret_cast<double *>(g.stats) + 2, (double)ret);
                 ret = 0.f;
                 ep = 0;
             }
