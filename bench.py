@@ -51,7 +51,8 @@ def config_json(args, n_gpus):
                     f"sync every {args.sync_interval} steps",
         "envs_per_gpu": args.batch, "global_envs": args.batch * n_gpus, "order": args.order,
         "options": args.options, "sync_interval": args.sync_interval, "map": args.map,
-        "parallelism": f"env-sharded x{n_gpus}, allreduce(dW, cnt) every sync interval",
+        "parallelism": f"env-sharded x{n_gpus}, sum of (dW, cnt) over ranks every sync interval "
+                       f"({'one NVLink peer-memory exchange+apply kernel' if getattr(args, 'sync_backend', 'p2p') == 'p2p' else 'NCCL all-reduce'})",
         "l2": f"traces {args.batch * 5 * F * 4 / 2**20:.0f} MiB per GPU > 126 MiB L2, swept once per window between 8 "
               "step kernels (inputs larger than L2; no explicit flush)",
     }
@@ -198,7 +199,7 @@ def run_ours(args):
     gmap = scg.PinballMap.from_name(args.map)
     rng = np.random.default_rng(1234 + rank)
     S = gmap.sample_free_states(rng, B)
-    cfg = scg.AgentConfig(**wl, env_offset=rank * B)
+    cfg = scg.AgentConfig(**wl, env_offset=rank * B, sync_backend=args.sync_backend)
     ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
     wrng = np.random.default_rng(7)                     # same weights on every rank
     ag.options.set_weights((wrng.standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32))
@@ -319,6 +320,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

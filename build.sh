@@ -8,6 +8,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --shared \
     -o "$OUT" "$PKG"/csrc/scg_api.cu "$PKG"/csrc/scg_step.cu "$PKG"/csrc/scg_q.cu \
-    "$PKG"/csrc/scg_sarsa.cu "$PKG"/csrc/scg_agent.cu 2> build.log || { cat build.log; exit 1; }
+    "$PKG"/csrc/scg_sarsa.cu "$PKG"/csrc/scg_agent.cu "$PKG"/csrc/scg_xchg.cu 2> build.log || { cat build.log; exit 1; }
 grep -E "error|warning" build.log | grep -v "Wall" | head -20 || true
 echo "built $OUT"

@@ -50,6 +50,7 @@ extern "C" {
 
 typedef struct scg_map scg_map_t; /* opaque: edge table + broad-phase grid, host and device copies */
 typedef struct scg_ctx scg_ctx_t; /* opaque: device scratch for the Sarsa(lambda) reduction */
+typedef struct scg_xchg scg_xchg_t; /* opaque: peer-memory exchange buffers of the cross-GPU sync */
 
 const char *scg_error_string(int code);
 int scg_version(void);
@@ -164,10 +165,31 @@ typedef struct scg_agent {
 int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
 /* Fold the open window into dW and the traces (no-op when win_len == 0). */
 int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
-/* n_steps steps in one call; when sync_interval > 0 (single rank) also flush + scg_apply every
- * sync_interval steps.  With sync_interval == 0 the caller flushes, all-reduces dW / cnt and applies. */
+/* n_steps steps in one call; when sync_interval > 0 also flush + apply every sync_interval steps:
+ * scg_apply for a single rank (xchg == NULL), scg_xchg_sync across ranks otherwise.  With
+ * sync_interval == 0 the caller flushes, sums dW / cnt over ranks and applies. */
 int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n_steps, int sync_interval,
-                  void *stream);
+                  scg_xchg_t *xchg, void *stream);
+
+/* ---- S5: cross-GPU weight-delta exchange over NVLink peer memory ---------------------------------
+ * mirrors the multi-rank half of oracle/option.py OptionSet.apply (sum dW and cnt over ranks, then the
+ * same apply on every rank).  One kernel per sync publishes this rank's dW / cnt, signals and waits on
+ * per-slice flags in peer memory, sums every rank's slice in rank order and applies - replicas stay
+ * bit-identical.  One process per GPU: exchange scg_xchg_handle() blobs (scg_xchg_handle_bytes() each,
+ * CUDA IPC) and call scg_xchg_connect with all of them; one process driving several devices:
+ * scg_xchg_connect_ptrs with every rank's scg_xchg_local_ptr (peer access enabled by the caller). */
+int scg_xchg_create(scg_ctx_t *ctx, int rank, int world, scg_xchg_t **out);
+int scg_xchg_destroy(scg_xchg_t *x);
+int scg_xchg_handle_bytes(void);
+int scg_xchg_handle(scg_xchg_t *x, void *handle_out /* HOST */);
+int scg_xchg_connect(scg_xchg_t *x, const void *all_handles /* HOST [world][handle_bytes] */);
+int scg_xchg_local_ptr(scg_xchg_t *x, void **ptr_out);
+int scg_xchg_connect_ptrs(scg_xchg_t *x, void *const *peer_ptrs /* HOST [world] device pointers */);
+int scg_xchg_status(scg_xchg_t *x, int *timed_out);
+/* dW (reduced over this rank's envs) and cnt -> summed over ranks -> W, Wt updated; dW and cnt zeroed.
+ * Every rank must call it the same number of times. */
+int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
+                  int window_steps, void *stream);
 
 /* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
  * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]

@@ -73,7 +73,16 @@ _SIGS = {
     "scg_clf_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_float, _P]),
     "scg_agent_step": (C.c_int, [_P, _P, C.POINTER(AgentStruct), _P]),
     "scg_agent_flush": (C.c_int, [_P, C.POINTER(AgentStruct), _P]),
-    "scg_agent_run": (C.c_int, [_P, _P, C.POINTER(AgentStruct), C.c_int, C.c_int, _P]),
+    "scg_agent_run": (C.c_int, [_P, _P, C.POINTER(AgentStruct), C.c_int, C.c_int, _P, _P]),
+    "scg_xchg_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "scg_xchg_destroy": (C.c_int, [_P]),
+    "scg_xchg_handle_bytes": (C.c_int, []),
+    "scg_xchg_handle": (C.c_int, [_P, _P]),
+    "scg_xchg_connect": (C.c_int, [_P, _P]),
+    "scg_xchg_local_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "scg_xchg_connect_ptrs": (C.c_int, [_P, _P]),
+    "scg_xchg_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
     "scg_profile_begin": (C.c_int, [_P, C.c_int]),
     "scg_profile_end": (C.c_int, [_P, _P, _P]),

@@ -46,6 +46,7 @@ class AgentConfig:
     graph: bool = False
     cull: bool = True
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
+    sync_backend: str = "p2p"   # multi-rank weight-delta exchange: "p2p" (one kernel over NVLink peer memory) or "nccl"
 
 
 class SkillChainAgent:
@@ -105,6 +106,34 @@ class SkillChainAgent:
         self.options.pack()
         self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT, soa=s))
         self._struct = self._make_struct()
+        self._xchg = None
+        if world_size(self.pg) > 1 and cfg.sync_backend == "p2p":
+            self._xchg = self._connect_peers()
+
+    def _connect_peers(self):
+        """Create this rank's exchange buffer and map every peer's through CUDA IPC (handles travel over
+        torch.distributed once)."""
+        dist = self.torch.distributed
+        rank, world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+        x = C.c_void_p()
+        check(self.lib.scg_xchg_create(self.options.ctx, rank, world, C.byref(x)))
+        nb = self.lib.scg_xchg_handle_bytes()
+        buf = (C.c_ubyte * nb)()
+        check(self.lib.scg_xchg_handle(x, buf))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf), group=self.pg)
+        blob = b"".join(handles)
+        check(self.lib.scg_xchg_connect(x, C.c_char_p(blob)))
+        dist.barrier(group=self.pg)
+        return x
+
+    def __del__(self):
+        try:
+            if getattr(self, "_xchg", None):
+                self.lib.scg_xchg_destroy(self._xchg)
+                self._xchg = None
+        except Exception:
+            pass
 
     # -- plumbing --------------------------------------------------------------------------------
     def _push_parents(self):
@@ -160,19 +189,20 @@ class SkillChainAgent:
         self.run(1)
 
     def run(self, n_steps):
-        """`n_steps` lock-step agent steps, with the weight sync every `sync_interval` steps.  On one
-        rank the whole loop runs inside the library (scg_agent_run); with several ranks it returns to
-        Python at every sync for the NCCL all-reduce."""
+        """`n_steps` lock-step agent steps, with the weight sync every `sync_interval` steps.  The whole loop
+        runs inside the library (scg_agent_run): on one rank the sync is the apply kernel, across ranks the
+        peer-memory exchange kernel.  With sync_backend="nccl" it returns to Python at every sync for the
+        NCCL all-reduce."""
         g = self._sync_struct()
         st = _lib.current_stream()
         n, T = int(n_steps), int(self.cfg.sync_interval)
-        if world_size(self.pg) == 1:
-            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), n, T, st))
+        if world_size(self.pg) == 1 or self._xchg is not None:
+            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), n, T, self._xchg, st))
             self.options.window_steps = int(g.window_steps)
             return
         while n > 0:
             k = min(n, T - int(g.window_steps))
-            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), k, 0, st))
+            check(self.lib.scg_agent_run(self.map.handle, self.options.ctx, C.byref(g), k, 0, None, st))
             n -= k
             if int(g.window_steps) >= T:
                 self.sync()
@@ -235,14 +265,27 @@ class SkillChainAgent:
         return [float(v) for v in ms], [int(v) for v in n]
 
     def sync(self):
-        """Flush the window, all-reduce its dW / cnt over ranks (if any) and apply."""
+        """Flush the window, sum its dW / cnt over ranks (if any) and apply."""
         o, g = self.options, self._struct
         self.flush()
-        allreduce_deltas(o._dW, o.cnt, self.pg)
-        o.window_steps = int(g.window_steps)
-        o.apply()
+        if self._xchg is not None:
+            check(self.lib.scg_xchg_sync(self._xchg, o.order, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt),
+                                         self.cfg.alpha, max(int(g.window_steps), 1), _lib.current_stream()))
+            o.window_steps = 0
+        else:
+            allreduce_deltas(o._dW, o.cnt, self.pg)
+            o.window_steps = int(g.window_steps)
+            o.apply()
         g.window_steps = 0
         g.carry_valid = 0
+
+    def peer_sync_timed_out(self):
+        """True if a peer failed to show up at some sync (the exchange kernel gives up after ~2 s)."""
+        if self._xchg is None:
+            return False
+        v = C.c_int()
+        check(self.lib.scg_xchg_status(self._xchg, C.byref(v)))
+        return bool(v.value)
 
     # -- low-rate controller ---------------------------------------------------------------------
     def examples(self, k):

@@ -319,7 +319,7 @@ extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t 
 }
 
 extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n_steps, int sync_interval,
-                             void *stream) {
+                             scg_xchg_t *xchg, void *stream) {
     if (n_steps < 0 || sync_interval < 0) return SCG_EINVAL;
     for (int i = 0; i < n_steps; ++i) {
         int rc = scg_agent_step(map, ctx, ag, stream);
@@ -327,8 +327,9 @@ extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *
         if (sync_interval > 0 && ag->window_steps >= sync_interval) {
             if ((rc = scg_agent_flush(ctx, ag, stream))) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, false))) return rc;
-            if ((rc = scg_apply(ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream)))
-                return rc;
+            if (xchg) rc = scg_xchg_sync(xchg, ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream);
+            else rc = scg_apply(ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream);
+            if (rc) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, true))) return rc;
             ag->window_steps = 0;
             ag->carry_valid = 0;

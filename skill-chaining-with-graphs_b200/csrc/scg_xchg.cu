@@ -1,0 +1,241 @@
+// scg_xchg.cu - S5, the cross-GPU weight-delta exchange, as ONE kernel over NVLink peer memory (sm_100a).
+//
+// Mirrors the multi-rank step of oracle/option.py OptionSet.apply ("dW and cnt are summed over ranks before
+// apply()"; the reference has no code: /root/reference/README.md:1-2).  Every rank owns an env slice and a full
+// replica of the option weights.  At a sync, k_sync on every GPU
+//   1. publishes its slice of the window's dW (and its update counts) in its own exchange buffer,
+//   2. raises a per-slice sequence flag in every peer's flag array (st.release.sys over NVLink),
+//   3. waits for the same slice's flag from every peer (ld.acquire.sys on local memory),
+//   4. reads that slice from every peer (NVLink P2P loads), sums in rank order - identical on every GPU, so the
+//      replicas stay bit-identical - and applies  W += alpha * alpha_scale_f * dW_sum * (steps / cnt_sum),
+//      refreshes the packed copy Wt and zeroes dW.
+// One launch replaces two NCCL all-reduces and the apply kernel; the payload is 20 KiB .. 203 KiB, so the cost is
+// a couple of NVLink round trips.  CTA c only ever waits for CTA c of the peers, which signals before it waits,
+// so no grid-wide barrier (and no co-residency assumption beyond one CTA) is needed.  The exchange buffer is
+// double-buffered by sequence parity: a rank can only be one sync ahead of the slowest reader.
+// Peer buffers are mapped with CUDA IPC (one process per GPU) or passed as plain pointers (one process, several
+// devices with peer access enabled - used by the two-device test).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "scg_common.cuh"
+
+#define XCHG_SLICE 256                 // elements per CTA
+#define XCHG_HDR 16                    // per-slice header: update counts of the K options (int bits)
+#define XCHG_ROW (XCHG_SLICE + XCHG_HDR)
+#define XCHG_MAX_WORLD 16
+
+struct scg_xchg {
+    int rank, world, n, K, slices;
+    uint32_t seq;
+    size_t bytes, flag_bytes;
+    unsigned char *d_local;                      // [flags: world*slices u32 | status u32 x 16 | xbuf: 2*slices*XCHG_ROW f32]
+    unsigned char *d_peer[XCHG_MAX_WORLD];       // mapped bases of every rank's block (own entry = d_local)
+    bool ipc_opened[XCHG_MAX_WORLD];
+    unsigned int *d_ticket;                      // last-CTA-done counter
+};
+
+struct SyncArgs {
+    int n, K, slices, rank, world;
+    uint32_t seq;
+    float alpha, steps;
+    float *W, *Wt, *dW;
+    int *cnt;
+    unsigned int *ticket;
+    size_t flag_bytes;
+    unsigned char *peer[XCHG_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys_f32(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int N1>
+__global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ SyncArgs a) {
+    constexpr int F = N1 * N1 * N1 * N1;
+    __shared__ int s_cnt[SCG_MAX_OPTIONS];
+    const int c = blockIdx.x, i = threadIdx.x, j = c * XCHG_SLICE + i;
+    const int buf = a.seq & 1;
+    unsigned char *mine = a.peer[a.rank];
+    float *xrow = reinterpret_cast<float *>(mine + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+    // 1. publish
+    const float my = (j < a.n) ? a.dW[j] : 0.f;
+    xrow[i] = my;
+    if (i < a.K) xrow[XCHG_SLICE + i] = __int_as_float(a.cnt[i]);
+    __syncthreads();
+    // the last CTA to have read cnt zeroes it for the next window
+    if (i == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            for (int k = 0; k < a.K; ++k) a.cnt[k] = 0;
+            *a.ticket = 0u;
+        }
+    }
+    // 2. signal every peer, 3. wait for every peer (one thread per peer)
+    if (i < a.world && i != a.rank) {
+        __threadfence_system();
+        uint32_t *pf = reinterpret_cast<uint32_t *>(a.peer[i]) + (size_t)a.rank * a.slices + c;
+        st_release_sys(pf, a.seq);
+        const uint32_t *lf = reinterpret_cast<const uint32_t *>(mine) + (size_t)i * a.slices + c;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(lf) - a.seq) < 0) {
+            if (clock64() - t0 > 4000000000ll) {      // ~2 s: a peer died; record it instead of hanging the GPU
+                reinterpret_cast<uint32_t *>(mine)[(size_t)a.world * a.slices] = 1u;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    // 4. sum in rank order, apply
+    float v = 0.f;
+    for (int r = 0; r < a.world; ++r) {
+        if (r == a.rank) { v += my; continue; }
+        const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+        v += ld_sys_f32(prow + i);
+    }
+    if (i < a.K) {
+        int tot = 0;
+        for (int r = 0; r < a.world; ++r) {
+            const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+            tot += __float_as_int(r == a.rank ? xrow[XCHG_SLICE + i] : ld_sys_f32(prow + XCHG_SLICE + i));
+        }
+        s_cnt[i] = tot;
+    }
+    __syncthreads();
+    if (j < a.n) {   // same arithmetic as k_apply (scg_sarsa.cu)
+        const int f = j % F, ka = j / F, act = ka % SCG_A, k = ka / SCG_A;
+        const int cn = s_cnt[k];
+        float w = a.W[j];
+        if (cn > 0) {
+            int d = f, ss = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { int dg = d % N1; ss += dg * dg; d /= N1; }
+            const float as = (ss == 0) ? 1.0f : (float)(1.0 / sqrt((double)ss));
+            const float scale = __fdiv_rn(a.steps, (float)cn);
+            w = __fadd_rn(w, __fmul_rn(__fmul_rn(a.alpha, as), __fmul_rn(v, scale)));
+            a.W[j] = w;
+        }
+        a.Wt[((size_t)f * a.K + k) * SCG_WT_STRIDE + act] = w;
+        a.dW[j] = 0.f;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+extern "C" int scg_xchg_create(scg_ctx_t *ctx, int rank, int world, scg_xchg_t **out) {
+    if (!ctx || !out || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return SCG_EINVAL;
+    if (ctx->K > XCHG_HDR) return SCG_ELIMIT;
+    scg_xchg *x = (scg_xchg *)calloc(1, sizeof(scg_xchg));
+    if (!x) return SCG_ENOMEM;
+    x->rank = rank; x->world = world; x->K = ctx->K;
+    x->n = ctx->K * SCG_A * ctx->F;
+    x->slices = (x->n + XCHG_SLICE - 1) / XCHG_SLICE;
+    x->flag_bytes = (((size_t)world * x->slices + 16) * sizeof(uint32_t) + 255) & ~(size_t)255;
+    x->bytes = x->flag_bytes + (size_t)2 * x->slices * XCHG_ROW * sizeof(float);
+    cudaError_t e = cudaMalloc((void **)&x->d_local, x->bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->d_local, 0, x->bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&x->d_ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(x->d_ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (x->d_local) cudaFree(x->d_local);
+        if (x->d_ticket) cudaFree(x->d_ticket);
+        free(x);
+        return (int)e;
+    }
+    x->d_peer[rank] = x->d_local;
+    *out = x;
+    return 0;
+}
+
+extern "C" int scg_xchg_destroy(scg_xchg_t *x) {
+    if (!x) return 0;
+    for (int r = 0; r < x->world; ++r)
+        if (x->ipc_opened[r]) cudaIpcCloseMemHandle(x->d_peer[r]);
+    if (x->d_local) cudaFree(x->d_local);
+    if (x->d_ticket) cudaFree(x->d_ticket);
+    free(x);
+    return 0;
+}
+
+extern "C" int scg_xchg_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int scg_xchg_local_ptr(scg_xchg_t *x, void **ptr_out) {
+    if (!x || !ptr_out) return SCG_EINVAL;
+    *ptr_out = x->d_local;
+    return 0;
+}
+
+extern "C" int scg_xchg_handle(scg_xchg_t *x, void *handle_out) {
+    if (!x || !handle_out) return SCG_EINVAL;
+    cudaIpcMemHandle_t h;
+    SCG_CUDA_OK(cudaIpcGetMemHandle(&h, x->d_local));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int scg_xchg_connect(scg_xchg_t *x, const void *all_handles) {
+    if (!x || !all_handles) return SCG_EINVAL;
+    const unsigned char *hs = (const unsigned char *)all_handles;
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        SCG_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->d_peer[r] = (unsigned char *)p;
+        x->ipc_opened[r] = true;
+    }
+    return 0;
+}
+
+extern "C" int scg_xchg_connect_ptrs(scg_xchg_t *x, void *const *peer_ptrs) {
+    if (!x || !peer_ptrs) return SCG_EINVAL;
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        if (!peer_ptrs[r]) return SCG_EINVAL;
+        x->d_peer[r] = (unsigned char *)peer_ptrs[r];
+    }
+    return 0;
+}
+
+extern "C" int scg_xchg_status(scg_xchg_t *x, int *timed_out) {
+    if (!x || !timed_out) return SCG_EINVAL;
+    uint32_t v = 0;
+    SCG_CUDA_OK(cudaMemcpy(&v, x->d_local + ((size_t)x->world * x->slices) * sizeof(uint32_t), sizeof(v),
+                           cudaMemcpyDeviceToHost));
+    *timed_out = (int)v;
+    return 0;
+}
+
+// dW (already reduced over this rank's slabs) and cnt -> summed over ranks -> applied; dW and cnt zeroed
+extern "C" int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
+                             int window_steps, void *stream) {
+    if (!x || !W || !Wt || !dW || !cnt) return SCG_EINVAL;
+    if (K != x->K || K * SCG_A * scg_pow4(order + 1) != x->n) return SCG_EINVAL;
+    for (int r = 0; r < x->world; ++r)
+        if (!x->d_peer[r]) return SCG_EINVAL;   // not connected
+    SyncArgs a;
+    a.n = x->n; a.K = K; a.slices = x->slices; a.rank = x->rank; a.world = x->world;
+    a.seq = ++x->seq;
+    a.alpha = alpha; a.steps = (float)std::max(window_steps, 1);
+    a.W = W; a.Wt = Wt; a.dW = dW; a.cnt = cnt; a.ticket = x->d_ticket;
+    a.flag_bytes = x->flag_bytes;
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) a.peer[r] = r < x->world ? x->d_peer[r] : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_ORDER(order, k_sync<N1><<<x->slices, XCHG_SLICE, 0, st>>>(a));
+    SCG_LAUNCH_CHECK();
+    return 0;
+}

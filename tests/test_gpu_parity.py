@@ -552,3 +552,94 @@ def test_golden_agent_step(scg, torch):
     assert np.array_equal(ag.options.cnt.cpu().numpy(), g["cnt"])
     assert rel_err(ag.options.dW.cpu().numpy(), g["dW"]) < RTOL
     assert rel_err(ag.options.trace.double().sum(dim=2).cpu().numpy(), g["trace_sum"]) < RTOL
+
+
+# ---- cross-GPU exchange kernel --------------------------------------------------------------------------
+def test_xchg_single_rank_equals_apply(scg, torch):
+    """world = 1: the exchange kernel degenerates to the apply kernel (same arithmetic, dW and cnt zeroed)."""
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check, ptr, current_stream
+    rng = np.random.default_rng(3)
+    K, order = 3, 3
+    a, b = scg.OptionSet(K, order, 4, alpha=0.07), scg.OptionSet(K, order, 4, alpha=0.07)
+    W = (rng.standard_normal(tuple(a.W.shape)) * 0.1).astype(np.float32)
+    dW = rng.standard_normal(tuple(a.W.shape)).astype(np.float32)
+    cnt = np.array([5, 0, 17], dtype=np.int32)
+    for o in (a, b):
+        o.set_weights(W)
+        o._dW.copy_(torch.as_tensor(dW))
+        o.cnt.copy_(torch.as_tensor(cnt))
+        o.window_steps = 4
+    a.apply()
+    lib = scg.load_library()
+    x = C.c_void_p()
+    check(lib.scg_xchg_create(b.ctx, 0, 1, C.byref(x)))
+    check(lib.scg_xchg_sync(x, order, K, ptr(b.W), ptr(b.Wt), ptr(b._dW), ptr(b.cnt), 0.07, 4, current_stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a.W, b.W) and torch.equal(a.Wt, b.Wt)
+    assert float(b._dW.abs().max()) == 0.0 and int(b.cnt.sum()) == 0
+    t = C.c_int(7)
+    check(lib.scg_xchg_status(x, C.byref(t)))
+    assert t.value == 0
+    lib.scg_xchg_destroy(x)
+
+
+def test_xchg_two_devices_sum_and_identical_replicas(scg, torch):
+    """Two ranks on two devices of one process (peer access, plain pointers): both apply the same summed delta."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check, ptr
+    lib = scg.load_library()
+    rng = np.random.default_rng(4)
+    K, order = 4, 3
+    W = (rng.standard_normal((K, 5, 256)) * 0.1).astype(np.float32)
+    dWs = [rng.standard_normal((K, 5, 256)).astype(np.float32) for _ in range(2)]
+    cnts = [np.array([3, 0, 9, 1], dtype=np.int32), np.array([4, 0, 2, 0], dtype=np.int32)]
+    sets, xs = [], []
+    for r in range(2):
+        with torch.cuda.device(r):
+            o = scg.OptionSet(K, order, 4, alpha=0.05)
+            o.set_weights(W)
+            o._dW.copy_(torch.as_tensor(dWs[r]))
+            o.cnt.copy_(torch.as_tensor(cnts[r]))
+            x = C.c_void_p()
+            check(lib.scg_xchg_create(o.ctx, r, 2, C.byref(x)))
+            sets.append(o); xs.append(x)
+    for r in range(2):                       # peer access both ways
+        with torch.cuda.device(r):
+            torch.zeros(1, device=f"cuda:{1 - r}").to(f"cuda:{r}")      # makes torch enable peer access
+    ptrs = (C.c_void_p * 2)()
+    for r in range(2):
+        p = C.c_void_p()
+        check(lib.scg_xchg_local_ptr(xs[r], C.byref(p)))
+        ptrs[r] = p
+    for r in range(2):
+        check(lib.scg_xchg_connect_ptrs(xs[r], ptrs))
+    for it in range(3):                      # three syncs: exercises the double buffering and the sequence flags
+        for r in range(2):
+            with torch.cuda.device(r):
+                o = sets[r]
+                check(lib.scg_xchg_sync(xs[r], order, K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt), 0.05, 8,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for r in range(2):
+            torch.cuda.synchronize(r)
+        ref = scg.OptionSet if False else None
+        w0, w1 = sets[0].W.cpu(), sets[1].W.cpu()
+        assert torch.equal(w0, w1)                                           # replicas bit-identical
+        if it == 0:
+            ora = oracle.OptionSet(K, order, 4, alpha=0.05)
+            ora.W[:] = W
+            ora.window_steps = 8
+            ora.apply((dWs[0].astype(np.float64) + dWs[1]), cnts[0] + cnts[1])
+            assert rel_err(w0.numpy(), ora.W) < 1e-6
+        for r in range(2):                   # next round: new deltas
+            with torch.cuda.device(r):
+                assert float(sets[r]._dW.abs().max()) == 0.0 and int(sets[r].cnt.sum()) == 0
+                sets[r]._dW.copy_(torch.as_tensor(dWs[r] * (it + 2)))
+                sets[r].cnt.copy_(torch.as_tensor(cnts[r]))
+    for r in range(2):
+        t = C.c_int()
+        check(lib.scg_xchg_status(xs[r], C.byref(t)))
+        assert t.value == 0
+        lib.scg_xchg_destroy(xs[r])
