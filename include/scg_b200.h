@@ -200,10 +200,11 @@ int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag,
                         float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
 
 /* Per-kernel device timing of the agent pipeline with CUDA events on the launch stream.
- * scg_profile_begin arms it (up to max_events kernel launches are recorded); scg_profile_end waits for
- * the recorded events and returns, per kind, the summed milliseconds and the launch count:
- * kind 0 fused step kernel, 1 window trace sweep, 2 dW reduction, 3 weight apply. */
-int scg_profile_begin(scg_ctx_t *ctx, int max_events);
+ * scg_profile_begin arms it (up to max_events kernel launches of the kinds in kind_mask are recorded);
+ * scg_profile_end waits for the recorded events and returns, per kind, the summed milliseconds and the
+ * launch count: kind 0 fused step kernel, 1 window trace sweep, 2 dW reduction, 3 weight apply / exchange.
+ * (Events around the step kernels - bit 0 - keep consecutive step kernels from overlapping their prologues.) */
+int scg_profile_begin(scg_ctx_t *ctx, int max_events, int kind_mask);
 int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [4] */, int *count /* HOST [4] */);
 
 /* kernel launch counter (this library's launches since load), for bench.py's gpu_launches */

@@ -71,15 +71,15 @@ class SkillChainAgent:
         if not 1 <= self.win_cap <= _lib.WIN_MAX:
             raise ValueError(f"window must be in 1..{_lib.WIN_MAX}")
         self._sbuf = (torch.zeros((4, B), **f32), torch.zeros((4, B), **f32))
-        self.action = torch.zeros(B, **i32)
+        # reward, flags, action, delta back to back: the host-buffer step returns them with one copy
+        self._out = torch.zeros((4, B), **f32)
+        self.reward, self.delta = self._out[0], self._out[3]
+        self.flags, self.action = self._out[1].view(torch.int32), self._out[2].view(torch.int32)
         self.option = torch.zeros(B, **i32)
         self.t_opt = torch.zeros(B, **i32)
         self.ep_steps = torch.zeros(B, **i32)
         self.start_xy = torch.zeros((B, 2), **f32)
         self.ep_return = torch.zeros(B, **f32)
-        self.reward = torch.zeros(B, **f32)
-        self.flags = torch.zeros(B, **i32)
-        self.delta = torch.zeros(B, **f32)
         self.q_carry = torch.zeros(B, **f32)
         self.win_rec = torch.zeros((self.win_cap, B, 8), **f32)
         self.parents = torch.zeros(K, dtype=torch.int32, device=dev)
@@ -223,9 +223,10 @@ class SkillChainAgent:
         B = self.cfg.batch
         if getattr(self, "_host", None) is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            mk = lambda: dict(s=pin((4, B), torch.float32), a=pin((B,), torch.int32), s2=pin((4, B), torch.float32),
-                              r=pin((B,), torch.float32), f=pin((B,), torch.int32), a2=pin((B,), torch.int32),
-                              d=pin((B,), torch.float32))
+            def mk():
+                out = pin((4, B), torch.float32)      # reward, flags, next action, TD error rows, back to back
+                return dict(s=pin((4, B), torch.float32), a=pin((B,), torch.int32), s2=pin((4, B), torch.float32),
+                            r=out[0], f=out[1].view(torch.int32), a2=out[2].view(torch.int32), d=out[3])
             self._host = [mk(), mk()]                       # ping-pong: results of call i are inputs of call i+1
             self._host_np = [{k: v.numpy() for k, v in h.items()} for h in self._host]
             self._host_i = 0
@@ -254,8 +255,9 @@ class SkillChainAgent:
     HOST_H2D_BYTES_PER_ENV = 20      # state 16 + action 4
     HOST_D2H_BYTES_PER_ENV = 32      # next state 16 + reward 4 + flags 4 + next action 4 + TD error 4
 
-    def profile_begin(self, max_events):
-        check(self.lib.scg_profile_begin(self.options.ctx, int(max_events)))
+    def profile_begin(self, max_events, kinds=(0, 1, 2, 3)):
+        """Record CUDA events around the launches of the given kinds (0 step, 1 window sweep, 2 reduce, 3 apply)."""
+        check(self.lib.scg_profile_begin(self.options.ctx, int(max_events), sum(1 << k for k in kinds)))
 
     def profile_end(self):
         """-> (ms per kind, launches per kind) for [fused step, window sweep, dW reduction, apply]."""

@@ -30,6 +30,7 @@ struct StepArgs {
     scg_agent_t ag;
     const unsigned char *map_blob;
     int blob_bytes, w_bytes;
+    int wait_first;   // 1: the previous launch may have written the weights - wait for it before staging them
     float4 *rec;  // this step's slab of the window: [B][2]
 };
 
@@ -73,7 +74,19 @@ __global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ Step
     __shared__ __align__(8) unsigned long long bar;
     const scg_agent_t &g = args.ag;
     unsigned char *w_smem = smem + ((args.blob_bytes + 127) & ~127);
-    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? args.w_bytes : 0, &bar);
+    // Programmatic dependent launch: let the next step kernel start its prologue (map + weight staging) under
+    // this kernel's tail, and do our own staging before waiting for the previous kernel - unless that kernel
+    // may have rewritten the weights.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // bulk copies move multiples of 16 bytes: the (at most 8-byte) tail of the weight table is copied by hand
+    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? (args.w_bytes & ~15) : 0, &bar);
+    if (SMEMW && (args.w_bytes & 15)) {
+        const int done = (args.w_bytes & ~15) / 4, tail = (args.w_bytes & 15) / 4;
+        if ((int)threadIdx.x < tail) reinterpret_cast<float *>(w_smem)[done + threadIdx.x] = g.Wt[done + threadIdx.x];
+        __syncthreads();
+    }
+    if (!args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
     const StepMap m = make_step_map(smem);
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
     const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
@@ -255,8 +268,18 @@ static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
         grid = SCG_NUM_SMS * rounds;
     }
     grid = std::max(grid, 1);
-    kern<<<grid, 256, smem, st>>>(args);
-    SCG_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SCG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args));
+    ++g_scg_launches;
     return 0;
 }
 
@@ -304,6 +327,8 @@ extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t 
     // weights go to shared memory when two CTAs per SM still fit next to the map
     const bool smemw = (size_t)args.w_bytes + args.blob_bytes + 256 <= 100 * 1024;
     const bool pair = !ag->carry_valid;
+    // a step kernel directly behind another step kernel of the same window may stage the weights early
+    args.wait_first = !(ag->carry_valid && ag->win_len > 0 && !(ctx->prof_on && (ctx->prof_mask & 1)));
     if ((rc = scg_prof_push(ctx, 0, st, false))) return rc;
     DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, smemw, pair, st));
     if (rc) return rc;
@@ -338,6 +363,19 @@ extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *
     return 0;
 }
 
+// copy `rows` arrays of n bytes each; one cudaMemcpyAsync when they are contiguous on both sides
+static int copy_rows(void *const *dst, const void *const *src, int rows, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+    bool contig = true;
+    for (int i = 1; i < rows; ++i)
+        contig = contig && (const char *)dst[i] == (const char *)dst[0] + i * n && (const char *)src[i] == (const char *)src[0] + i * n;
+    if (contig) {
+        SCG_CUDA_OK(cudaMemcpyAsync(dst[0], src[0], n * rows, kind, st));
+        return 0;
+    }
+    for (int i = 0; i < rows; ++i) SCG_CUDA_OK(cudaMemcpyAsync(dst[i], src[i], n, kind, st));
+    return 0;
+}
+
 extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, const float *h_state_soa,
                                    const int *h_action, float *h_state2_soa, float *h_reward, int *h_flags,
                                    int *h_action2, float *h_delta, void *stream) {
@@ -345,28 +383,33 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_age
         !h_delta)
         return SCG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t n = (size_t)ag->B * sizeof(float);
-    float *in[4] = {ag->x, ag->y, ag->vx, ag->vy};
-    for (int i = 0; i < 4; ++i)
-        SCG_CUDA_OK(cudaMemcpyAsync(in[i], h_state_soa + (size_t)i * ag->B, n, cudaMemcpyHostToDevice, st));
+    const size_t n = (size_t)ag->B * sizeof(float);
+    int rc;
+    {
+        void *dst[4] = {ag->x, ag->y, ag->vx, ag->vy};
+        const void *src[4] = {h_state_soa, h_state_soa + ag->B, h_state_soa + 2 * (size_t)ag->B, h_state_soa + 3 * (size_t)ag->B};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyHostToDevice, st))) return rc;
+    }
     SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
     ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
-    int rc = scg_agent_step(map, ctx, ag, stream);
-    if (rc) return rc;
-    float *out[4] = {ag->x, ag->y, ag->vx, ag->vy};   // the step swapped the buffers: x..vy is the new state
-    for (int i = 0; i < 4; ++i)
-        SCG_CUDA_OK(cudaMemcpyAsync(h_state2_soa + (size_t)i * ag->B, out[i], n, cudaMemcpyDeviceToHost, st));
-    SCG_CUDA_OK(cudaMemcpyAsync(h_reward, ag->reward, n, cudaMemcpyDeviceToHost, st));
-    SCG_CUDA_OK(cudaMemcpyAsync(h_flags, ag->flags, n, cudaMemcpyDeviceToHost, st));
-    SCG_CUDA_OK(cudaMemcpyAsync(h_action2, ag->action, n, cudaMemcpyDeviceToHost, st));
-    SCG_CUDA_OK(cudaMemcpyAsync(h_delta, ag->delta, n, cudaMemcpyDeviceToHost, st));
+    if ((rc = scg_agent_step(map, ctx, ag, stream))) return rc;
+    {   // the step swapped the buffers: x..vy is the new state
+        void *dst[4] = {h_state2_soa, h_state2_soa + ag->B, h_state2_soa + 2 * (size_t)ag->B, h_state2_soa + 3 * (size_t)ag->B};
+        const void *src[4] = {ag->x, ag->y, ag->vx, ag->vy};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+    }
+    {   // reward, flags, next action, TD error: one copy when both sides keep them back to back
+        void *dst[4] = {h_reward, h_flags, h_action2, h_delta};
+        const void *src[4] = {ag->reward, ag->flags, ag->action, ag->delta};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+    }
     SCG_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 
 // ---- per-kernel timing ---------------------------------------------------------------------------------
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end) {
-    if (!ctx->prof_on) return 0;
+    if (!ctx->prof_on || !((ctx->prof_mask >> kind) & 1)) return 0;
     if (!end) {
         if (ctx->prof_n >= ctx->prof_cap) return 0;
         ctx->prof_kind[ctx->prof_n] = kind;
@@ -380,8 +423,9 @@ int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end) {
     return 0;
 }
 
-extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_events) {
+extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_events, int kind_mask) {
     if (!ctx || max_events <= 0) return SCG_EINVAL;
+    ctx->prof_mask = kind_mask & 15;
     if (max_events > ctx->prof_cap) {
         for (int i = 0; i < 2 * ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         free(ctx->prof_ev);

@@ -85,7 +85,7 @@ struct scg_ctx {
     // optional per-kernel timing of the agent pipeline (scg_profile_begin / scg_profile_end)
     cudaEvent_t *prof_ev;  // [prof_cap][2] start/stop pairs
     int *prof_kind;        // [prof_cap]
-    int prof_cap, prof_n, prof_on, prof_open;
+    int prof_cap, prof_n, prof_on, prof_open, prof_mask;
 };
 
 #ifdef __CUDACC__
@@ -143,7 +143,9 @@ __device__ __forceinline__ void scg_phasors(float x, float y, float vx, float vy
 // ---- packed weights ------------------------------------------------------------------------------
 // Wt is [F][K][8] fp32: feature-major, then option, then 5 action weights + 3 pad, so that one feature
 // of one option is two 16-byte loads, and the K options of a feature sit in consecutive 32-byte slots
-// (lanes of a warp that execute different options hit different shared-memory banks).
+// (lanes of a warp that execute different options hit different shared-memory banks).  Measured on B200: a
+// 16-byte shared load with 2-3 distinct addresses costs ~3.7 wavefronts, the [F][K][6] / three 8-byte loads
+// alternative ~2.2 each - the same LSU time with more instructions, so the 16-byte form stays.
 // WCur walks the table for one option, from global memory (read-only path) or from a shared-memory copy.
 __device__ __forceinline__ uint32_t scg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
