@@ -327,7 +327,16 @@ struct WinItem {   // a work item of the sweep: block `blk` of 8 steps of env `b
     int b, blk;
 };
 
-template <int N1, int VEC, int NT>
+// per-env control block written by the scan warp, read by every thread in the main phase (double-buffered)
+struct WinCtl {
+    float2 gc[SCG_WIN_MAX];            // (G_t, c_t) per step
+    uint32_t mask[SCG_WIN_MAX][8];     // [segment][action]: steps of that segment taken with that action (5 used)
+    uint32_t seg_o[SCG_WIN_MAX];       // option of each segment (an env changes option only after a termination)
+    float scale, carry;                // e <- scale * e_start;  d <- carry * e_start
+    int nseg, pad;
+};
+
+template <int N1, int VEC, int NT, int CH, bool MULTI>
 __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl) {
     using V = typename VecT<VEC>::type;
@@ -337,31 +346,40 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
     constexpr int NN = N1 * N1;
     constexpr int TABN = SCG_WIN_TB * 2 * NN;             // entries of one table buffer
     constexpr int EPT = (TABN + NT - 1) / NT;             // table entries built per thread
-    static_assert(F % VEC == 0 && NT >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
+    constexpr int TSTRIDE = 2 * NN * (int)sizeof(float2); // bytes between the tables of consecutive steps
+    static_assert(F % VEC == 0 && NT * CH >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
     static_assert(VEC == 1 || NN % VEC == 0, "a chunk shares its (c0, c1) digits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);                                      // [K][AF]
     float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [2][TABN]
-    float4 *sStep = reinterpret_cast<float4 *>(tab + 2 * TABN);                            // [2][SCG_WIN_MAX]: G, c, meta
-    float4 *sHead = sStep + 2 * SCG_WIN_MAX;                                               // [2]: scale, carry, o0
-    float *glpow = reinterpret_cast<float *>(sHead + 2);                                   // [36]: gl^n
+    WinCtl *ctl = reinterpret_cast<WinCtl *>(tab + 2 * TABN);                              // [2]
+    float *glpow = reinterpret_cast<float *>(ctl + 2);                                     // [36]: gl^n
 
     const int tid = threadIdx.x;
-    const bool own = tid < NCHR;
-    const int NBLK = (T + SCG_WIN_TB - 1) / SCG_WIN_TB;
+    // thread t owns chunks t, t + NT, ... of every action row (each a coalesced access across the CTA)
+    bool own[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) own[j] = tid + j * NT < NCHR;
+    const int NBLK = MULTI ? (T + SCG_WIN_TB - 1) / SCG_WIN_TB : 1;
     // per-thread constants: table offsets (bytes) of the owned features' (c0, c1) and (c2, c3) entries ...
-    const int f0 = (own ? tid : 0) * VEC;
-    const int off01 = (f0 / NN) * (int)sizeof(float2);
-    const int off23 = (NN + f0 % NN) * (int)sizeof(float2);
-    // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits
+    int off01[CH], off23[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const int f0 = (own[j] ? tid + j * NT : 0) * VEC;
+        off01[j] = (f0 / NN) * (int)sizeof(float2);
+        off23[j] = (NN + f0 % NN) * (int)sizeof(float2);
+    }
+    // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits,
+    // and the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4)
     int e_tt[EPT], e_half[EPT];
-    float e_ca[EPT], e_cb[EPT];
+    float e_ca[EPT], e_cb[EPT], e_mul[EPT], e_add[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
         int idx = tid + k * NT;
         if (idx >= TABN) idx = TABN - 1;                 // duplicate work on the last entry, never out of range
         const int tt = idx / (2 * NN), rem = idx - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
         e_tt[k] = tt; e_half[k] = half;
+        e_mul[k] = half ? 0.25f : 1.f; e_add[k] = half ? 0.5f : 0.f;
         e_ca[k] = (float)(ij / N1); e_cb[k] = (float)(ij % N1);
     }
     for (int i = tid; i < K * AF; i += NT) acc[i] = 0.f;
@@ -372,19 +390,26 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
 
     const int stride = gridDim.x;
     auto advance = [&](WinItem it) {
-        if (++it.blk == NBLK) { it.blk = 0; it.b += stride; }
+        if constexpr (MULTI) {
+            if (++it.blk == NBLK) { it.blk = 0; it.b += stride; }
+        } else {
+            it.b += stride;
+        }
         return it;
     };
 
     // prefetch registers
     float2 r_sv[EPT];                                    // state pair of the steps this thread builds entries for
     float2 r_dm = make_float2(0.f, 0.f);                 // (delta, meta) of step tid (first block of an env only)
-    V e[SCG_A], e_nx[SCG_A], d[SCG_A];
-    int o_cur = 0;
+    V e[CH][SCG_A], e_nx[CH][SCG_A], d[CH][SCG_A];
+    uint32_t o_cur = 0;
 #pragma unroll
-    for (int r = 0; r < SCG_A; ++r) {
-        if constexpr (VEC == 4) { e[r] = vzero4(); e_nx[r] = vzero4(); d[r] = vzero4(); }
-        else { e[r] = 0.f; e_nx[r] = 0.f; d[r] = 0.f; }
+    for (int j = 0; j < CH; ++j) {
+#pragma unroll
+        for (int r = 0; r < SCG_A; ++r) {
+            if constexpr (VEC == 4) { e[j][r] = vzero4(); e_nx[j][r] = vzero4(); d[j][r] = vzero4(); }
+            else { e[j][r] = 0.f; e_nx[j][r] = 0.f; d[j][r] = 0.f; }
+        }
     }
 
     auto load_rec = [&](WinItem it) {                    // records of a work item -> registers
@@ -398,21 +423,20 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
     };
     auto load_trace = [&](int b) {
         const V *tp = reinterpret_cast<const V *>(trace + (size_t)b * AF);
-        if (own) {
 #pragma unroll
-            for (int r = 0; r < SCG_A; ++r) e_nx[r] = tp[r * NCHR + tid];
+        for (int j = 0; j < CH; ++j) {
+            if (own[j]) {
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) e_nx[j][r] = tp[r * NCHR + tid + j * NT];
+            }
         }
     };
-    // registers -> pair tables (buffer `par`) and, for an env's first block, its step scalars (buffer `epar`)
+    // registers -> pair tables (buffer `par`) and, for an env's first block, its control block (buffer `epar`)
     auto build = [&](WinItem it, int par, int epar) {
         float2 *tb = tab + par * TABN;
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
-            float s0 = r_sv[k].x, s1 = r_sv[k].y;
-            if (e_half[k]) {                             // velocities: oracle/fourier.py normalise
-                s0 = __fmul_rn(__fadd_rn(s0, 2.0f), 0.25f);
-                s1 = __fmul_rn(__fadd_rn(s1, 2.0f), 0.25f);
-            }
+            const float s0 = fmaf(r_sv[k].x, e_mul[k], e_add[k]), s1 = fmaf(r_sv[k].y, e_mul[k], e_add[k]);
             // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
             const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
             const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
@@ -420,36 +444,66 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
             if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
         }
         if (it.blk == 0 && tid < 32) {
-            // warp 0: backward recursion G_t = delta_t + m_t G_{t+1} as a suffix scan over (m, delta) pairs,
-            // m_t = 0 after a termination, gl otherwise (1 for a step the env sat out)
+            // warp 0, lane = step: backward recursion G_t = delta_t + m_t G_{t+1} as a suffix scan over (m, delta)
+            // pairs, m_t = 0 after a termination, gl otherwise (1 for a step the env sat out)
+            WinCtl &cb = ctl[epar];
+            const unsigned FULL = 0xffffffffu;
             const int t = tid;
             const uint32_t meta = (t < T) ? __float_as_uint(r_dm.y) : 0u;
             const bool act = (meta & SCG_META_ACTIVE) != 0;
             const bool dn = act && (meta & SCG_META_ZERO_AFTER);
+            const uint32_t a = meta & 7u, o = (meta >> 8) & 0xFFu;
             float D = act ? r_dm.x : 0.f, M = !act ? 1.f : (dn ? 0.f : gl);
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const float D2 = __shfl_down_sync(0xffffffffu, D, off), M2 = __shfl_down_sync(0xffffffffu, M, off);
+                const float D2 = __shfl_down_sync(FULL, D, off), M2 = __shfl_down_sync(FULL, M, off);
                 if (t + off < 32) { D = fmaf(M, D2, D); M *= M2; }
             }
-            const unsigned am = __ballot_sync(0xffffffffu, act), dm = __ballot_sync(0xffffffffu, dn);
+            const unsigned am = __ballot_sync(FULL, act), dm = __ballot_sync(FULL, dn);
             const bool dead = (dm >> t) != 0;                     // a termination at this step or later in the window
             const float cf = (act && !dead) ? glpow[__popc((am >> t) >> 1)] : 0.f;
-            if (t < T) sStep[epar * SCG_WIN_MAX + t] = make_float4(act ? D : 0.f, cf, __uint_as_float(meta), 0.f);
-            const int t0 = am ? __ffs(am) - 1 : 0;
-            const uint32_t o0 = (__shfl_sync(0xffffffffu, meta, t0) >> 8) & 0xFF;
-            if (t == 0) sHead[epar] = make_float4(dm ? 0.f : glpow[__popc(am)], am ? gl * D : 0.f, __uint_as_float(o0), 0.f);
+            const float G = act ? D : 0.f;
+            if (t < T) cb.gc[t] = make_float2(G, cf);
+            // segments: maximal runs of steps under the same option
+            const unsigned before = am & ((1u << t) - 1u);
+            const int prev = before ? 31 - __clz(before) : t;
+            const uint32_t o_prev = __shfl_sync(FULL, o, prev);
+            const unsigned chg = __ballot_sync(FULL, act && before && o != o_prev);
+            const int seg = __popc(chg & ((2u << t) - 1u));
+            const int nseg = am ? __popc(chg) + 1 : 0;
+            const bool nz = act && (G != 0.f || cf != 0.f);
+            for (int sgm = 0; sgm < nseg; ++sgm) {
+                const unsigned in_seg = __ballot_sync(FULL, act && seg == sgm);
+                const uint32_t os = __shfl_sync(FULL, o, __ffs(in_seg) - 1);
+                unsigned mine = 0;
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) {
+                    const unsigned mr = __ballot_sync(FULL, nz && seg == sgm && a == (uint32_t)r);
+                    if (t == r) mine = mr;
+                }
+                if (t < SCG_A) cb.mask[sgm][t] = mine;
+                if (t == 0) cb.seg_o[sgm] = os;
+            }
+            if (t == 0) {
+                cb.scale = dm ? 0.f : glpow[__popc(am)];
+                cb.carry = am ? gl * D : 0.f;
+                cb.nseg = nseg;
+            }
         }
     };
     auto flush_d = [&]() {
-        if (own) {
-            V *ap = reinterpret_cast<V *>(acc + (size_t)o_cur * AF);
+        V *ap = reinterpret_cast<V *>(acc + (size_t)o_cur * AF);
 #pragma unroll
-            for (int r = 0; r < SCG_A; ++r) {
-                V cur = ap[r * NCHR + tid];
-                if constexpr (VEC == 4) cur = make_float4(cur.x + d[r].x, cur.y + d[r].y, cur.z + d[r].z, cur.w + d[r].w);
-                else cur = cur + d[r];
-                ap[r * NCHR + tid] = cur;
+        for (int j = 0; j < CH; ++j) {
+            if (own[j]) {
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) {
+                    V cur = ap[r * NCHR + tid + j * NT];
+                    if constexpr (VEC == 4)
+                        cur = make_float4(cur.x + d[j][r].x, cur.y + d[j][r].y, cur.z + d[j][r].z, cur.w + d[j][r].w);
+                    else cur = cur + d[j][r];
+                    ap[r * NCHR + tid + j * NT] = cur;
+                }
             }
         }
     };
@@ -470,67 +524,94 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
         const WinItem nx2 = advance(nxt);
         if (cur.blk == 0) {
 #pragma unroll
-            for (int r = 0; r < SCG_A; ++r) e[r] = e_nx[r];
+            for (int j = 0; j < CH; ++j) {
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) e[j][r] = e_nx[j][r];
+            }
         }
         // next item's tables (into the other buffer), then the loads for the items after it
         if (nxt.b < B) build(nxt, par ^ 1, nxt.blk == 0 ? epar ^ 1 : epar);
         if (nx2.b < B) load_rec(nx2);
         if (nxt.blk == 0 && nxt.b < B) load_trace(nxt.b);
         // ---- main ----
-        const float4 *st = sStep + epar * SCG_WIN_MAX + cur.blk * SCG_WIN_TB;
+        const WinCtl &cb = ctl[epar];
         const char *tb0 = reinterpret_cast<const char *>(tab + par * TABN);
+        const float2 *gc = cb.gc + cur.blk * SCG_WIN_TB;
         if (cur.blk == 0) {
-            const float4 hd = sHead[epar];
-            o_cur = (int)__float_as_uint(hd.z);
+            const float carry = cb.carry, scale = cb.scale;
+            o_cur = cb.seg_o[0];
 #pragma unroll
-            for (int r = 0; r < SCG_A; ++r) {
-                d[r] = vscale(e[r], hd.y);               // carry-in: gl G_0 e_start
-                e[r] = vscale(e[r], hd.x);
-            }
-        }
-        const int nb = min(SCG_WIN_TB, T - cur.blk * SCG_WIN_TB);
-#pragma unroll
-        for (int tt = 0; tt < SCG_WIN_TB; ++tt) {
-            if (tt >= nb) break;
-            const float4 sv = st[tt];
-            const float G = sv.x, c = sv.y;
-            if (G == 0.f && c == 0.f) continue;
-            const uint32_t meta = __float_as_uint(sv.z);
-            const int a = meta & 7, o = (meta >> 8) & 0xFF;
-            if (o != o_cur) {                            // the env changed option inside the window (after a termination)
-                flush_d();
+            for (int j = 0; j < CH; ++j) {
 #pragma unroll
                 for (int r = 0; r < SCG_A; ++r) {
-                    if constexpr (VEC == 4) d[r] = vzero4(); else d[r] = 0.f;
+                    d[j][r] = vscale(e[j][r], carry);    // carry-in: gl G_0 e_start
+                    e[j][r] = vscale(e[j][r], scale);
                 }
-                o_cur = o;
             }
-            const char *tb = tb0 + tt * 2 * NN * (int)sizeof(float2);
-            const float2 p = *reinterpret_cast<const float2 *>(tb + off01);
-            V ph;
-            if constexpr (VEC == 4) {
-                const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23);
-                const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23 + 16);
-                ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
-                                 fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
-            } else {
-                const float2 q = *reinterpret_cast<const float2 *>(tb + off23);
-                ph = fmaf(p.x, q.x, -p.y * q.y);
+        }
+        const int nseg = cb.nseg;
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+            // this segment's steps inside this block, one bit mask per action
+            uint32_t mk[SCG_A];
+            {
+                const uint4 m4 = *reinterpret_cast<const uint4 *>(cb.mask[sgm]);
+                mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; mk[4] = cb.mask[sgm][4];
             }
-            switch (a) {   // CTA-uniform
-                case 0: d[0] = vfma(G, ph, d[0]); e[0] = vfma(c, ph, e[0]); break;
-                case 1: d[1] = vfma(G, ph, d[1]); e[1] = vfma(c, ph, e[1]); break;
-                case 2: d[2] = vfma(G, ph, d[2]); e[2] = vfma(c, ph, e[2]); break;
-                case 3: d[3] = vfma(G, ph, d[3]); e[3] = vfma(c, ph, e[3]); break;
-                default: d[4] = vfma(G, ph, d[4]); e[4] = vfma(c, ph, e[4]); break;
+            uint32_t any = 0;
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) {
+                if constexpr (MULTI) mk[r] = (mk[r] >> (cur.blk * SCG_WIN_TB)) & ((1u << SCG_WIN_TB) - 1u);
+                any |= mk[r];
+            }
+            if (!any) continue;
+            const uint32_t so = cb.seg_o[sgm];
+            if (so != o_cur) {                           // the env changed option inside the window (after a termination)
+                flush_d();
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+#pragma unroll
+                    for (int r = 0; r < SCG_A; ++r) {
+                        if constexpr (VEC == 4) d[j][r] = vzero4(); else d[j][r] = 0.f;
+                    }
+                }
+                o_cur = so;
+            }
+#pragma unroll
+            for (int r = 0; r < SCG_A; ++r) {            // static register rows: no dynamic indexing, no switch
+                uint32_t mm = mk[r];
+                while (mm) {
+                    const int tt = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const float2 g2 = gc[tt];
+                    const char *tb = tb0 + tt * TSTRIDE;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {       // independent chunks: their loads and FMAs interleave
+                        const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
+                        V ph;
+                        if constexpr (VEC == 4) {
+                            const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
+                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + 16);
+                            ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
+                                             fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
+                        } else {
+                            const float2 q = *reinterpret_cast<const float2 *>(tb + off23[j]);
+                            ph = fmaf(p.x, q.x, -p.y * q.y);
+                        }
+                        d[j][r] = vfma(g2.x, ph, d[j][r]);
+                        e[j][r] = vfma(g2.y, ph, e[j][r]);
+                    }
+                }
             }
         }
         if (cur.blk == NBLK - 1) {
             flush_d();
-            if (own) {
-                V *tp = reinterpret_cast<V *>(trace + (size_t)cur.b * AF);
+            V *tp = reinterpret_cast<V *>(trace + (size_t)cur.b * AF);
 #pragma unroll
-                for (int r = 0; r < SCG_A; ++r) tp[r * NCHR + tid] = e[r];
+            for (int j = 0; j < CH; ++j) {
+                if (own[j]) {
+#pragma unroll
+                    for (int r = 0; r < SCG_A; ++r) tp[r * NCHR + tid + j * NT] = e[j][r];
+                }
             }
         }
         __syncthreads();   // the tables just built become readable, the ones just read become writable
@@ -706,12 +787,12 @@ static int ensure_partials(scg_ctx *ctx, int n) {
     return 0;
 }
 
-template <int N1, int VEC, int NT>
-static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
+template <int N1, int VEC, int NT, int CH, bool MULTI>
+static int launch_window_tm(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
     constexpr int NN = N1 * N1;
     const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
-                        (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + (size_t)(2 * SCG_WIN_MAX + 2) * sizeof(float4) + 36 * sizeof(float);
-    auto kern = k_window<N1, VEC, NT>;
+                        (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + 2 * sizeof(WinCtl) + 36 * sizeof(float);
+    auto kern = k_window<N1, VEC, NT, CH, MULTI>;
     static size_t configured = 0;
     static int per_sm = 0;
     if (smem != configured) {
@@ -731,6 +812,12 @@ static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float 
     return grid;
 }
 
+template <int N1, int VEC, int NT, int CH>
+static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false>(ctx, B, T, rec, trace, gl, st);
+    return launch_window_tm<N1, VEC, NT, CH, true>(ctx, B, T, rec, trace, gl, st);
+}
+
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
 // fold the T recorded steps of the window into dW and the traces
@@ -739,13 +826,25 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace
     if (T < 1 || T > SCG_WIN_MAX) return SCG_EINVAL;
     const float4 *r4 = reinterpret_cast<const float4 *>(rec);
     int grid = 0, rc;
+    static int win_ch3 = -1, win_ch5 = -1;   // tuning knobs: chunks per thread at orders 3 and 5
+    if (win_ch3 < 0) { const char *e = getenv("SCG_WIN_CH3"); win_ch3 = e ? atoi(e) : 1; }
+    if (win_ch5 < 0) { const char *e = getenv("SCG_WIN_CH5"); win_ch5 = e ? atoi(e) : 1; }
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
     switch (ctx->order) {
-        case 1: grid = launch_window_t<2, 4, 32>(ctx, B, T, r4, trace, gl, st); break;
-        case 2: grid = launch_window_t<3, 1, 96>(ctx, B, T, r4, trace, gl, st); break;
-        case 3: grid = launch_window_t<4, 4, 64>(ctx, B, T, r4, trace, gl, st); break;
-        case 4: grid = launch_window_t<5, 1, 640>(ctx, B, T, r4, trace, gl, st); break;
-        case 5: grid = launch_window_t<6, 4, 352>(ctx, B, T, r4, trace, gl, st); break;
+        // <N1, floats per chunk, threads, chunks per thread>.  Measured on B200 (order 3, B = 65,536): two warps per
+        // env with one chunk per thread 0.155 ms; one warp per env with two chunks per thread (SCG_WIN_CH3=2) has 18 %
+        // fewer instructions but only 8 warps/SM to hide the shared-memory latency: 0.159 ms.  Order 5: 2.27 vs 2.38 ms.
+        case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, r4, trace, gl, st); break;
+        case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, r4, trace, gl, st); break;
+        case 3:
+            if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, r4, trace, gl, st);
+            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, r4, trace, gl, st);
+            break;
+        case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, r4, trace, gl, st); break;
+        case 5:
+            if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, r4, trace, gl, st);
+            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, r4, trace, gl, st);
+            break;
         default: return SCG_ELIMIT;
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;

@@ -643,3 +643,123 @@ def test_xchg_two_devices_sum_and_identical_replicas(scg, torch):
         check(lib.scg_xchg_status(xs[r], C.byref(t)))
         assert t.value == 0
         lib.scg_xchg_destroy(xs[r])
+
+
+# ---- BASELINE.json full sizes: size-independent properties ----------------------------------------------
+FULL_B = 65536          # configs[1]: 65,536 envs on one B200
+
+
+def _full_agent(scg, torch, B, lo, seed=11, window=0, order=3, K=4, name="easy", **kw):
+    gmap = scg.PinballMap.from_name(name)
+    rng = np.random.default_rng(99)
+    S = gmap.sample_free_states(rng, FULL_B)[lo:lo + B]
+    cfg = scg.AgentConfig(map=name, batch=B, order=order, max_options=K, seed=seed, env_offset=lo, sync_interval=1000,
+                          epsilon=0.1, option_timeout=6, alpha=1e-3, window=window, **kw)
+    ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
+    W = (np.random.default_rng(5).standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32)
+    ag.options.set_weights(W)
+    theta = np.zeros((K, 6), dtype=np.float32)
+    theta[0, :3] = [-6.0, 10.0, 0.0]
+    theta[1, :3] = [4.5, 0.0, -10.0]
+    ag.options.theta.copy_(torch.as_tensor(theta))
+    ag.active_mask, ag.n_active = 3, 2
+    ag.parents_host[1], ag.parents_host[2] = 1, 2
+    ag._push_parents()
+    return ag
+
+
+def test_full_size_sharding_invariance(scg, torch):
+    """65,536 envs as one batch == the same envs as 4 shards of 16,384 (global env ids key the RNG): states and
+    actions bit-identical, summed dW / cnt equal to the unsharded ones."""
+    n = 8
+    whole = _full_agent(scg, torch, FULL_B, 0)
+    whole.run(n)
+    dW, cnt = whole.options.dW.double().cpu(), whole.options.cnt.cpu()
+    sdW, scnt, states, actions = torch.zeros_like(dW), torch.zeros_like(cnt), [], []
+    for i in range(4):
+        sh = _full_agent(scg, torch, FULL_B // 4, i * FULL_B // 4)
+        sh.run(n)
+        sdW += sh.options.dW.double().cpu()
+        scnt += sh.options.cnt.cpu()
+        states.append(sh.s.cpu()); actions.append(sh.action.cpu())
+        del sh
+    assert torch.equal(torch.cat(states, dim=1), whole.s.cpu())
+    assert torch.equal(torch.cat(actions), whole.action.cpu())
+    assert torch.equal(scnt, cnt) and int(cnt.sum()) == n * FULL_B
+    assert float((sdW - dW).abs().max()) <= 1e-4 * max(1.0, float(dW.abs().max()))
+
+
+def test_full_size_window_length_invariance(scg, torch):
+    """The same 12 steps swept with windows of 1 (the dense per-step form), 4 and 8 steps give the same traces and
+    dW: the forward-view sweep is exact for any window length (weights frozen)."""
+    ref = None
+    for window in (1, 4, 8):
+        ag = _full_agent(scg, torch, FULL_B, 0, window=window)
+        ag.run(12)
+        tr, dW = ag.options.trace.clone(), ag.options.dW.clone()
+        st = ag.s.clone()
+        del ag
+        if ref is None:
+            ref = (tr, dW, st)
+            continue
+        assert torch.equal(st, ref[2])
+        assert float((tr - ref[0]).abs().max()) <= 1e-4 * max(1.0, float(ref[0].abs().max()))
+        assert float((dW - ref[1]).abs().max()) <= 1e-4 * max(1.0, float(ref[1].abs().max()))
+
+
+def test_full_size_step_properties(scg, torch):
+    """One step of 65,536 envs on the hard map: rewards are in the reward set, flags decode to valid (obstacle, edge)
+    pairs of the map, positions stay in the unit square, speed never grows except by the thrust impulse."""
+    gmap = scg.PinballMap.from_name("hard")
+    rng = np.random.default_rng(1)
+    S = gmap.sample_free_states(rng, FULL_B)
+    A = rng.integers(0, 5, FULL_B).astype(np.int32)
+    env = scg.PinballEnv(gmap, FULL_B)
+    env.reset(states=S)
+    ns, r, done, hit = env.step(torch.as_tensor(A).cuda())
+    ns, r, done, hit = ns.cpu().numpy(), r.cpu().numpy(), done.cpu().numpy(), hit.cpu().numpy()
+    assert set(np.unique(r).tolist()) <= {-1.0, -5.0, 10000.0}
+    assert np.array_equal(r == 10000.0, done)
+    assert ns[:, :2].min() >= 0.0 and ns[:, :2].max() <= 1.0
+    edges, obst, local = gmap.edge_table()
+    n_local = np.bincount(obst)
+    k = hit[:, 0] != 0
+    assert k.mean() > 0.02 and hit[~k, 1].max() == -1
+    assert hit[k, 1].min() >= 0 and hit[k, 1].max() < len(n_local)
+    assert np.all(hit[k, 2] < n_local[hit[k, 1]])
+    sp0 = np.hypot(S[:, 2], S[:, 3]) + 0.2 + 1e-6
+    assert np.all(np.hypot(ns[:, 2], ns[:, 3]) <= sp0)
+    # a sample of it against the oracle, bit for bit
+    idx = rng.choice(FULL_B, 4000, replace=False)
+    ons, orr, ofl = step_batched(oracle.PinballMap.from_name("hard"), S[idx], A[idx])
+    assert np.array_equal(ns[idx].view(np.uint32), ons.view(np.uint32)) and np.array_equal(r[idx], orr)
+
+
+def test_graph_mode_parents_match_oracle(scg, torch):
+    """Option-graph variant: an option whose parents are several initiation sets and the goal terminates on any of
+    them (oracle/agent.py, graph=True); one fused step against the oracle."""
+    B, K = 4000, 4
+    oag, gag = _paired_agents(scg, torch, B, 3, K, "hard", 12, sync_interval=5, option_timeout=50, epsilon=0.2, graph=True)
+    theta = np.zeros((K, 6), dtype=np.float32)
+    theta[0] = [-1.2, 2.0, 0.0, 0.0, 0.0, 0.0]
+    theta[1] = [-0.8, 0.0, 2.0, 0.0, 0.0, 0.0]
+    oag.options.theta[:] = theta
+    oag.active[:2] = True
+    oag.n_active = 2
+    oag.parents[1] = np.uint32(1) | np.uint32(1 << 31)
+    oag.parents[2] = np.uint32(3) | np.uint32(1 << 31)
+    gag.options.theta.copy_(torch.as_tensor(theta))
+    gag.active_mask, gag.n_active = 3, 2
+    gag.parents_host[1], gag.parents_host[2] = 1 | (1 << 31), 3 | (1 << 31)
+    gag._push_parents()
+    opt = np.full(B, 2, dtype=np.int32)
+    oag.option = opt.copy()
+    gag.option.copy_(torch.as_tensor(opt))
+    out = oag.step()
+    gag.step()
+    torch.cuda.synchronize()
+    assert out["hit"].sum() > 20
+    assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
+    assert np.array_equal(gag.option.cpu().numpy(), out["option"])
+    assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+    assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success) and np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
