@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one lock-step agent step over the whole env batch: ONE fused kernel does env step (K1) ->
-initiation classifiers + Q evaluation + eps-greedy + TD error (K2+K4) -> 32-byte step record; every
-`sync_interval` steps the window's records are folded into the traces and weight deltas by one
-Sarsa(lambda) sweep (K3, forward-view form), followed by the cross-GPU allreduce and the weight apply.
+A "step" is one lock-step agent step over the whole env batch: a fused kernel does env step (K1) ->
+initiation classifiers + Q evaluation + eps-greedy + TD error (K2+K4) -> 32-byte step record, for the
+`sync_interval` consecutive steps of a window in one launch (nothing couples the envs while the weights are
+frozen); then the window's records are folded into the traces and weight deltas by one Sarsa(lambda) sweep
+(K3, forward-view form), followed by the cross-GPU exchange and the weight apply.
 Workload at every N: BASELINE.json configs[1] per GPU - Pinball 'easy', 65,536 envs, order-3 Fourier
 basis, 4 option slots with 2 active logistic initiation classifiers (weak scaling: each rank owns
 its own 65,536-env slice).  Synthetic data: random free-space start states, random-init weights.
@@ -222,7 +223,7 @@ def run_ours(args):
         sampler.start()
     # ---- timed region: exactly K steps, device-resident ----
     launches0 = lib.scg_launch_count()
-    ag.profile_begin(4 * args.steps + 16, kinds=(1, 2, 3))      # the per-window kernels, live in the timed region
+    ag.profile_begin(4 * args.steps + 16)                       # CUDA events around every launch, live in the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -232,14 +233,6 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     kind_ms, kind_n = ag.profile_end()
     launches = lib.scg_launch_count() - launches0
-    # the step kernel is timed in a separate, untimed pass: events between consecutive step kernels would stop
-    # them from overlapping their prologues (programmatic dependent launch) inside the timed region
-    n_side = min(args.steps, 64)
-    ag.profile_begin(n_side + 8, kinds=(0,))
-    ag.run(n_side)
-    torch.cuda.synchronize()
-    side_ms, side_n = ag.profile_end()
-    kind_ms[0], kind_n[0] = side_ms[0] * args.steps / max(side_n[0], 1), args.steps
     # ---- e2e: same K steps through the host-buffer API ----
     hs = ag.s.cpu().numpy().copy()
     ha = ag.action.cpu().numpy().copy()
@@ -294,9 +287,8 @@ def run_ours(args):
                          "share_of_step": (kind_ms[1] / tot_ms) if tot_ms else None},
             "stages_ms_per_step": {"fused_step_k1_k2_k4": kind_ms[0] / args.steps, "k3_window_sweep": kind_ms[1] / args.steps,
                                    "dw_reduce": kind_ms[2] / args.steps, "apply": kind_ms[3] / args.steps,
-                                   "fused_step_avg_launch_ms": avg(0),
-                                   "note": "window/reduce/apply timed live in the timed region; the step kernel in a "
-                                           "separate pass with events between launches (no prologue overlap)"},
+                                   "fused_step_avg_launch_ms": avg(0), "fused_step_launches": kind_n[0],
+                                   "steps_per_fused_launch": args.steps / max(kind_n[0], 1)},
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": B * ag.HOST_H2D_BYTES_PER_ENV,
                     "d2h_bytes_per_step": B * ag.HOST_D2H_BYTES_PER_ENV,

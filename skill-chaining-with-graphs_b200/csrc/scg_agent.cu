@@ -17,6 +17,8 @@
 // persistent CTAs so that every SM gets the same number of warps even at B = 65,536.  Each CTA stages
 // the map blob and, when it fits, the packed weights [F][K][8] into shared memory with bulk-TMA copies
 // (cp.async.bulk + mbarrier); lanes executing different options then read different banks.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "scg_common.cuh"
@@ -31,6 +33,7 @@ struct StepArgs {
     const unsigned char *map_blob;
     int blob_bytes, w_bytes;
     int wait_first;   // 1: the previous launch may have written the weights - wait for it before staging them
+    int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
     float4 *rec;  // this step's slab of the window: [B][2]
 };
 
@@ -69,7 +72,7 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
 }
 
 template <int N1, bool SMEMW, bool PAIR>
-__global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ StepArgs args) {
+__global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ StepArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
     const scg_agent_t &g = args.ag;
@@ -79,13 +82,7 @@ __global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ Step
     // may have rewritten the weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
-    // bulk copies move multiples of 16 bytes: the (at most 8-byte) tail of the weight table is copied by hand
-    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? (args.w_bytes & ~15) : 0, &bar);
-    if (SMEMW && (args.w_bytes & 15)) {
-        const int done = (args.w_bytes & ~15) / 4, tail = (args.w_bytes & 15) / 4;
-        if ((int)threadIdx.x < tail) reinterpret_cast<float *>(w_smem)[done + threadIdx.x] = g.Wt[done + threadIdx.x];
-        __syncthreads();
-    }
+    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? args.w_bytes : 0, &bar);
     if (!args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
     const StepMap m = make_step_map(smem);
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
@@ -97,153 +94,167 @@ __global__ void __launch_bounds__(256) k_agent_step(const __grid_constant__ Step
     constexpr unsigned FULL = 0xffffffffu;
     // warp-granular work, interleaved over CTAs: tile i goes to CTA i % grid, warp i / grid.  The warp stays
     // converged through the whole tile (lanes past the batch end compute on a clamped index and skip stores).
+    // Inside a window nothing couples the envs (the weights are frozen), so a launch runs n_steps consecutive
+    // steps of every env with the env's state in registers: one load and one store of the per-env state, one
+    // staging of the map and the weights and one launch per window instead of per step.
     for (int tile = w * gridDim.x + blockIdx.x; tile < n_tiles; tile += gridDim.x * nw) {
         const bool valid = tile * 32 + lane < g.B;
         const int b = valid ? tile * 32 + lane : g.B - 1;
-        const float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
-        const int a = g.action[b];
-        const int o = g.option[b];
-        // 1: env step
-        float nx = sx, ny = sy, nvx = svx, nvy = svy, r_env;
-        int fl;
-        if (g.cull) pinball_step<true>(m, nx, ny, nvx, nvy, a, r_env, fl);
-        else pinball_step<false>(m, nx, ny, nvx, nvy, a, r_env, fl);
-        const bool env_done = (fl & SCG_FLAG_DONE) != 0;
-        // 4a: Q_o(s2, .) (and Q_o(s, .) when the carried value is stale)
-        float2 zb[4];
-        scg_phasors(nx, ny, nvx, nvy, zb);
-        float qb[SCG_A], qsa;
-        const WCur<SMEMW> wc(Wt, K, o);
-        if constexpr (PAIR) {
-            float2 za[4];
-            scg_phasors(sx, sy, svx, svy, za);
-            float qa[SCG_A];
-            scg_q_pair<N1, SMEMW>(za, zb, wc, qa, qb);
-            qsa = 0.f;
-#pragma unroll
-            for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
-        } else {
-            scg_q_one<N1, SMEMW>(zb, wc, qb);
-            qsa = g.q_carry[b];
-        }
         const uint32_t env = g.env_offset + (uint32_t)b;
-        // 2-3: initiation bits of s2, termination, option reward
-        const uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
-        const uint32_t pm = g.parents[o];
-        const bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
-        int t_opt = g.t_opt[b] + 1, ep = g.ep_steps[b] + 1;
-        const bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
-        const bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
-        const bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
-        const float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
-        // 4b: a2, TD error
-        const int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_ACTION));
-        float qs2 = 0.f;
+        float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
+        int a = g.action[b], o = g.option[b];
+        int t_opt = g.t_opt[b], ep = g.ep_steps[b];
+        float ret = g.ep_return[b], qc = PAIR ? 0.f : g.q_carry[b];
+        float stx = g.start_xy[2 * b], sty = g.start_xy[2 * b + 1];
+        float r_env = 0.f, delta = 0.f;
+        int fl = 0;
+        for (int s = 0; s < args.n_steps; ++s) {
+            const uint32_t step = g.step + (uint32_t)s;
+            // 1: env step
+            float nx = sx, ny = sy, nvx = svx, nvy = svy;
+            if (g.cull) pinball_step<true>(m, nx, ny, nvx, nvy, a, r_env, fl);
+            else pinball_step<false>(m, nx, ny, nvx, nvy, a, r_env, fl);
+            const bool env_done = (fl & SCG_FLAG_DONE) != 0;
+            // 4a: Q_o(s2, .) (and Q_o(s, .) when the carried value is stale: first step after a weight change)
+            float2 zb[4];
+            scg_phasors(nx, ny, nvx, nvy, zb);
+            float qb[SCG_A], qsa = qc;
+            const WCur<SMEMW> wc(Wt, K, o);
+            if (PAIR && s == 0) {
+                float2 za[4];
+                scg_phasors(sx, sy, svx, svy, za);
+                float qa[SCG_A];
+                scg_q_pair<N1, SMEMW>(za, zb, wc, qa, qb);
+                qsa = 0.f;
 #pragma unroll
-        for (int i = 0; i < SCG_A; ++i) qs2 = (i == a2) ? qb[i] : qs2;
-        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
-        float ret = g.ep_return[b] + r_env;
-        const bool reset = env_done || ep_timeout;
-        {   // cnt[o] += 1, one atomic per (warp, option)
-            const uint32_t peers = __match_any_sync(FULL, valid ? o : -1);
-            if (valid && (__ffs(peers) - 1) == lane) atomicAdd(g.cnt + o, __popc(peers));
+                for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
+            } else {
+                scg_q_one<N1, SMEMW>(zb, wc, qb);
+            }
+            // 2-3: initiation bits of s2, termination, option reward
+            const uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
+            const uint32_t pm = g.parents[o];
+            const bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
+            t_opt += 1;
+            ep += 1;
+            const bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
+            const bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
+            const bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
+            const float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
+            // 4b: a2, TD error
+            const int a2 = scg_eps_greedy(qb, g.epsilon, scg_draw(g.seed, env, step, SCG_STREAM_ACTION));
+            float qs2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < SCG_A; ++i) qs2 = (i == a2) ? qb[i] : qs2;
+            delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
+            ret += r_env;
+            const bool reset = env_done || ep_timeout;
+            {   // cnt[o] += 1, one atomic per (warp, option)
+                const uint32_t peers = __match_any_sync(FULL, valid ? o : -1);
+                if (valid && (__ffs(peers) - 1) == lane) atomicAdd(g.cnt + o, __popc(peers));
+            }
+            if (valid) {
+                // 5: the step record for the window sweep
+                const uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
+                float4 *rec = args.rec + ((size_t)s * g.B + b) * 2;
+                rec[0] = make_float4(sx, sy, svx, svy);
+                rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
+                // 6: example for option o's initiation classifier
+                if (term) {
+                    const uint32_t eslot = (uint32_t)atomicAdd(g.ex_count + o, 1) % g.example_capacity;   // unsigned: safe past 2^31 appends
+                    const size_t ei = (size_t)o * g.example_capacity + eslot;
+                    g.ex_xy[2 * ei] = stx;
+                    g.ex_xy[2 * ei + 1] = sty;
+                    g.ex_label[ei] = hit ? 1 : 0;
+                    atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
+                }
+                // 7: env reset
+                if (reset) {
+                    const uint4 rr = scg_draw(g.seed, env, step, SCG_STREAM_RESET);
+                    const int ns = mh->n_starts;
+                    const int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
+                    const float2 s0 = reinterpret_cast<const float2 *>(smem + mh->off_starts)[pick];
+                    nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
+                    atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 0, 1ull);
+                    if (env_done) atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 1, 1ull);
+                    atomicAdd(reinterpret_cast<double *>(g.stats) + 2, (double)ret);
+                    ret = 0.f;
+                    ep = 0;
+                }
+            }
+            // 8: option re-selection.  Terminations are rare, so the Q evaluation under the new option is
+            // compacted inside the warp: N1 lanes share one terminated env, one leading digit c0 each.
+            int o_next = o, a_next = a2;
+            float q_next = qs2;
+            const bool tv = term && valid;
+            const unsigned tmask = __ballot_sync(FULL, tv);
+            if (tmask) {
+                float2 zn[4] = {zb[0], zb[1], zb[2], zb[3]};
+                if (tv) {
+                    const uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
+                    o_next = bn ? (__ffs(bn) - 1) : gest;
+                    if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
+                }
+                constexpr int PER = 32 / N1;                         // envs served per pass
+                const int my_slot = __popc(tmask & ((1u << lane) - 1u));   // rank of this lane among the terminated
+                const int slot = lane / N1, c0 = lane - slot * N1;
+                float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int base = 0; base < __popc(tmask); base += PER) {
+                    const unsigned src = __fns(tmask, 0, base + slot + 1);   // lane of the (base+slot)-th terminated env
+                    const bool have = slot < PER && src < 32u;
+                    const int sl = have ? (int)src : 0;
+                    float2 zs[4];
+#pragma unroll
+                    for (int dd = 0; dd < 4; ++dd) {
+                        zs[dd].x = __shfl_sync(FULL, zn[dd].x, sl);
+                        zs[dd].y = __shfl_sync(FULL, zn[dd].y, sl);
+                    }
+                    const int os = __shfl_sync(FULL, o_next, sl);
+                    float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, K, os), qp);
+#pragma unroll
+                    for (int dd = 1; dd < N1; ++dd) {                // slot head (c0 == 0) gathers the partial sums
+#pragma unroll
+                        for (int i = 0; i < SCG_A; ++i) {
+                            const float v = __shfl_down_sync(FULL, qp[i], dd);
+                            if (c0 == 0) qp[i] += v;
+                        }
+                    }
+                    const int rel = my_slot - base;
+                    const bool mine = tv && rel >= 0 && rel < PER;
+                    const int head = mine ? rel * N1 : 0;
+#pragma unroll
+                    for (int i = 0; i < SCG_A; ++i) {
+                        const float v = __shfl_sync(FULL, qp[i], head);
+                        if (mine) qn[i] = v;
+                    }
+                }
+                if (tv) {
+                    a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, step, SCG_STREAM_RESELECT));
+#pragma unroll
+                    for (int i = 0; i < SCG_A; ++i) q_next = (i == a_next) ? qn[i] : q_next;
+                    t_opt = 0;
+                    stx = nx;
+                    sty = ny;
+                }
+            }
+            // the next step starts from here
+            sx = nx; sy = ny; svx = nvx; svy = nvy;
+            a = a_next; o = o_next; qc = q_next;
         }
         if (valid) {
+            g.x2[b] = sx; g.y2[b] = sy; g.vx2[b] = svx; g.vy2[b] = svy;
+            g.action[b] = a;
+            g.option[b] = o;
+            g.t_opt[b] = t_opt;
+            g.ep_steps[b] = ep;
+            g.ep_return[b] = ret;
+            g.q_carry[b] = qc;
+            g.start_xy[2 * b] = stx;
+            g.start_xy[2 * b + 1] = sty;
             g.reward[b] = r_env;
             g.flags[b] = fl;
             g.delta[b] = delta;
-            // 5: the step record for the window sweep
-            const uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
-            float4 *rec = args.rec + (size_t)b * 2;
-            rec[0] = make_float4(sx, sy, svx, svy);
-            rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
-            // 6: example for option o's initiation classifier
-            if (term) {
-                const uint32_t eslot = (uint32_t)atomicAdd(g.ex_count + o, 1) % g.example_capacity;   // unsigned: safe past 2^31 appends
-                const size_t ei = (size_t)o * g.example_capacity + eslot;
-                g.ex_xy[2 * ei] = g.start_xy[2 * b];
-                g.ex_xy[2 * ei + 1] = g.start_xy[2 * b + 1];
-                g.ex_label[ei] = hit ? 1 : 0;
-                atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
-            }
-            // 7: env reset
-            if (reset) {
-                const uint4 rr = scg_draw(g.seed, env, g.step, SCG_STREAM_RESET);
-                const int ns = mh->n_starts;
-                const int pick = min((int)__fmul_rn(scg_u01(rr.x), (float)ns), ns - 1);
-                const float2 s0 = reinterpret_cast<const float2 *>(smem + mh->off_starts)[pick];
-                nx = s0.x; ny = s0.y; nvx = 0.f; nvy = 0.f;
-                atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 0, 1ull);
-                if (env_done) atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 1, 1ull);
-                atomicAdd(reinterpret_cast<double *>(g.stats) + 2, (double)ret);
-                ret = 0.f;
-                ep = 0;
-            }
-            g.x2[b] = nx; g.y2[b] = ny; g.vx2[b] = nvx; g.vy2[b] = nvy;
-            g.ep_return[b] = ret;
-            g.ep_steps[b] = ep;
-        }
-        // 8: option re-selection.  Terminations are rare, so the Q evaluation under the new option is
-        // compacted inside the warp: N1 lanes share one terminated env, one leading digit c0 each.
-        int o_next = o, a_next = a2;
-        float q_next = qs2;
-        const bool tv = term && valid;
-        unsigned tmask = __ballot_sync(FULL, tv);
-        if (tmask) {
-            float2 zn[4] = {zb[0], zb[1], zb[2], zb[3]};
-            if (tv) {
-                const uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
-                o_next = bn ? (__ffs(bn) - 1) : gest;
-                if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
-            }
-            constexpr int PER = 32 / N1;                         // envs served per pass
-            const int my_slot = __popc(tmask & ((1u << lane) - 1u));   // rank of this lane among the terminated
-            const int slot = lane / N1, c0 = lane - slot * N1;
-            float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int base = 0; base < __popc(tmask); base += PER) {
-                const unsigned src = __fns(tmask, 0, base + slot + 1);   // lane of the (base+slot)-th terminated env
-                const bool have = slot < PER && src < 32u;
-                const int sl = have ? (int)src : 0;
-                float2 zs[4];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    zs[d].x = __shfl_sync(FULL, zn[d].x, sl);
-                    zs[d].y = __shfl_sync(FULL, zn[d].y, sl);
-                }
-                const int os = __shfl_sync(FULL, o_next, sl);
-                float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, K, os), qp);
-#pragma unroll
-                for (int d = 1; d < N1; ++d) {                   // slot head (c0 == 0) gathers the partial sums
-#pragma unroll
-                    for (int i = 0; i < SCG_A; ++i) {
-                        const float v = __shfl_down_sync(FULL, qp[i], d);
-                        if (c0 == 0) qp[i] += v;
-                    }
-                }
-                const int rel = my_slot - base;
-                const bool mine = tv && rel >= 0 && rel < PER;
-                const int head = mine ? rel * N1 : 0;
-#pragma unroll
-                for (int i = 0; i < SCG_A; ++i) {
-                    const float v = __shfl_sync(FULL, qp[i], head);
-                    if (mine) qn[i] = v;
-                }
-            }
-            if (tv) {
-                a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, g.step, SCG_STREAM_RESELECT));
-#pragma unroll
-                for (int i = 0; i < SCG_A; ++i) q_next = (i == a_next) ? qn[i] : q_next;
-                t_opt = 0;
-                g.start_xy[2 * b] = nx;
-                g.start_xy[2 * b + 1] = ny;
-                g.option[b] = o_next;
-            }
-        }
-        if (valid) {
-            g.t_opt[b] = t_opt;
-            g.action[b] = a_next;
-            g.q_carry[b] = q_next;
         }
     }
 }
@@ -313,10 +324,8 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     return 0;
 }
 
-extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
-    int rc = check_agent(map, ctx, ag);
-    if (rc) return rc;
-    if (ag->B == 0) return 0;
+// n consecutive steps (1 <= n <= win_cap - win_len) in one launch
+static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     StepArgs args;
     args.ag = *ag;
@@ -324,31 +333,49 @@ extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t 
     args.blob_bytes = map->hdr.blob_bytes;
     args.w_bytes = ag->K * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
+    args.n_steps = n;
     // weights go to shared memory when two CTAs per SM still fit next to the map
     const bool smemw = (size_t)args.w_bytes + args.blob_bytes + 256 <= 100 * 1024;
     const bool pair = !ag->carry_valid;
     // a step kernel directly behind another step kernel of the same window may stage the weights early
     args.wait_first = !(ag->carry_valid && ag->win_len > 0 && !(ctx->prof_on && (ctx->prof_mask & 1)));
+    int rc;
     if ((rc = scg_prof_push(ctx, 0, st, false))) return rc;
     DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, smemw, pair, st));
     if (rc) return rc;
     if ((rc = scg_prof_push(ctx, 0, st, true))) return rc;
     std::swap(ag->x, ag->x2); std::swap(ag->y, ag->y2);
     std::swap(ag->vx, ag->vx2); std::swap(ag->vy, ag->vy2);
-    ag->step += 1;
-    ag->window_steps += 1;
-    ag->win_len += 1;
+    ag->step += n;
+    ag->window_steps += n;
+    ag->win_len += n;
     ag->carry_valid = 1;
     if (ag->win_len >= ag->win_cap) return scg_agent_flush(ctx, ag, stream);
     return 0;
 }
 
+extern "C" int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
+    int rc = check_agent(map, ctx, ag);
+    if (rc) return rc;
+    if (ag->B == 0) return 0;
+    return agent_steps(map, ctx, ag, 1, stream);
+}
+
 extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n_steps, int sync_interval,
                              scg_xchg_t *xchg, void *stream) {
     if (n_steps < 0 || sync_interval < 0) return SCG_EINVAL;
-    for (int i = 0; i < n_steps; ++i) {
-        int rc = scg_agent_step(map, ctx, ag, stream);
-        if (rc) return rc;
+    int rc = check_agent(map, ctx, ag);
+    if (rc) return rc;
+    if (ag->B == 0) return 0;
+    static int fuse = -1;   // SCG_STEPS_PER_LAUNCH=1 falls back to one launch per step (tuning / debugging)
+    if (fuse < 0) { const char *e = getenv("SCG_STEPS_PER_LAUNCH"); fuse = e ? atoi(e) : SCG_WIN_MAX; if (fuse < 1) fuse = 1; }
+    for (int done = 0; done < n_steps;) {
+        // as many steps as fit before the window is full, the sync is due, or the request ends
+        int n = std::min(n_steps - done, ag->win_cap - ag->win_len);
+        if (sync_interval > 0) n = std::min(n, std::max(1, sync_interval - ag->window_steps));
+        n = std::min(n, fuse);
+        if ((rc = agent_steps(map, ctx, ag, n, stream))) return rc;
+        done += n;
         if (sync_interval > 0 && ag->window_steps >= sync_interval) {
             if ((rc = scg_agent_flush(ctx, ag, stream))) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, false))) return rc;
