@@ -624,14 +624,23 @@ __global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4
     for (int i = tid; i < K * AF; i += NT) out[i] = acc[i];
 }
 
-// dW[j] += sum over slabs; grid (ceil(n/256), slices); a few atomics per address.
+// dW[j] += sum over slabs; grid (ceil(n/256), slices); one atomic per address per slice.  Each thread keeps four
+// independent loads in flight (the slabs were just written and mostly sit in L2).
 __global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const float *__restrict__ partial,
                                                 float *__restrict__ dW) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    float s = 0.f;
-    for (int p = blockIdx.y; p < n_partials; p += gridDim.y) s += partial[(size_t)p * n + j];
-    atomicAdd(dW + j, s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int gy = gridDim.y;
+    int p = blockIdx.y;
+    for (; p + 3 * gy < n_partials; p += 4 * gy) {
+        s0 += partial[(size_t)p * n + j];
+        s1 += partial[(size_t)(p + gy) * n + j];
+        s2 += partial[(size_t)(p + 2 * gy) * n + j];
+        s3 += partial[(size_t)(p + 3 * gy) * n + j];
+    }
+    for (; p < n_partials; p += gy) s0 += partial[(size_t)p * n + j];
+    atomicAdd(dW + j, (s0 + s1) + (s2 + s3));
 }
 
 __global__ void k_make_rec(int B, const float *__restrict__ x, const float *__restrict__ y,
@@ -851,7 +860,7 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace
     if ((rc = scg_prof_push(ctx, 1, st, true))) return rc;
     if ((rc = scg_prof_push(ctx, 2, st, false))) return rc;
     int n = ctx->K * SCG_A * ctx->F;
-    dim3 g((n + 255) / 256, std::min(grid, 32));
+    dim3 g((n + 255) / 256, std::min(grid, 96));
     k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
     SCG_LAUNCH_CHECK();
     return scg_prof_push(ctx, 2, st, true);
