@@ -263,13 +263,10 @@ __global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ S
 template <int N1, bool SMEMW, bool PAIR>
 static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
     auto kern = k_agent_step<N1, SMEMW, PAIR>;
-    static size_t configured = 0;
-    static int per_sm = 0;
-    if (smem > configured || per_sm == 0) {
-        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-        configured = smem;
-    }
+    static ScgKernelCfg cfgc = {};
+    int per_sm = 0;
+    int rcc = scg_configure(cfgc, kern, 256, smem, &per_sm);
+    if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
     const int n_tiles = (args.ag.B + 31) / 32;
     // enough CTAs for one warp per tile if they all fit at once, else every resident slot

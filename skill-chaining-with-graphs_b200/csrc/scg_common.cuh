@@ -48,6 +48,27 @@ extern uint64_t g_scg_launches;  // host-side launch counter (scg_api.cu)
 
 static inline int scg_pow4(int n1) { return n1 * n1 * n1 * n1; }
 
+// Per-device cache of a kernel's dynamic shared-memory opt-in and occupancy (cudaFuncSetAttribute is per device,
+// and one process may drive several devices).
+#define SCG_MAX_DEVICES 32
+struct ScgKernelCfg {
+    size_t configured[SCG_MAX_DEVICES];
+    int per_sm[SCG_MAX_DEVICES];
+};
+template <typename Kern>
+static inline int scg_configure(ScgKernelCfg &c, Kern kern, int threads, size_t smem, int *per_sm_out) {
+    int dev = 0;
+    SCG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= SCG_MAX_DEVICES) return SCG_ELIMIT;
+    if (smem != c.configured[dev] || c.per_sm[dev] == 0) {
+        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm[dev], kern, threads, smem));
+        c.configured[dev] = smem;
+    }
+    *per_sm_out = c.per_sm[dev];
+    return 0;
+}
+
 // ---- map blob ------------------------------------------------------------------------------
 // One contiguous, 16-byte aligned block in global memory, bulk-copied into shared memory by the
 // step kernel.  Sections (byte offsets in the header):

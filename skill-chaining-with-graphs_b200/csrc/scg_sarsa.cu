@@ -696,13 +696,10 @@ template <int N1, int VEC, int CPT, int NT, int U>
 static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, float gl, cudaStream_t st) {
     size_t smem = (size_t)ctx->K * SCG_A * ctx->F * sizeof(float);
     auto kern = k_trace<N1, VEC, CPT, NT, U>;
-    static size_t configured = 0;
-    static int per_sm = 0;
-    if (smem > configured) {
-        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-        configured = smem;
-    }
+    static ScgKernelCfg cfgc = {};
+    int per_sm = 0;
+    int rcc = scg_configure(cfgc, kern, NT, smem, &per_sm);
+    if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
     int grid = std::max(std::min(B, SCG_NUM_SMS * per_sm), 1);
     int rc = ensure_partials(ctx, grid);
@@ -730,13 +727,10 @@ static int launch_trace_tma_t(scg_ctx *ctx, int B, const float4 *rec, float *tra
     if (d_env >= 1 && d_env < S && d_env <= 6) D = d_env;
     size_t smem = acc + (size_t)S * block;
     auto kern = k_trace_tma<N1, CPT, NT>;
-    static size_t configured = 0;
-    static int per_sm = 0;
-    if (smem != configured) {
-        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT + 32, smem));
-        configured = smem;
-    }
+    static ScgKernelCfg cfgc = {};
+    int per_sm = 0;
+    int rcc = scg_configure(cfgc, kern, NT + 32, smem, &per_sm);
+    if (rcc) return rcc;
     if (per_sm < 1) return 0;
     int grid = std::max(1, std::min(B, SCG_NUM_SMS * per_sm));
     int rc = ensure_partials(ctx, grid);
@@ -802,13 +796,10 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, const float4 *rec, float
     const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
                         (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + 2 * sizeof(WinCtl) + 36 * sizeof(float);
     auto kern = k_window<N1, VEC, NT, CH, MULTI>;
-    static size_t configured = 0;
-    static int per_sm = 0;
-    if (smem != configured) {
-        SCG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-        configured = smem;
-    }
+    static ScgKernelCfg cfgc = {};
+    int per_sm = 0;
+    int rcc = scg_configure(cfgc, kern, NT, smem, &per_sm);
+    if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
     static int cap = -1;
     if (cap < 0) { const char *e = getenv("SCG_WIN_CTAS_PER_SM"); cap = e ? atoi(e) : 0; }

@@ -268,12 +268,10 @@ int scg_launch_step(const scg_map_t *map, int B, const float *x, const float *y,
     if (B == 0) return 0;
     const int threads = 256;
     int smem = map->hdr.blob_bytes;
-    static int configured = 0;
-    if (smem > configured) {
-        SCG_CUDA_OK(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        SCG_CUDA_OK(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static ScgKernelCfg cfg_t = {}, cfg_f = {};
+    int occ = 0, rcc;
+    if ((rcc = scg_configure(cfg_t, k_step<true>, threads, (size_t)smem, &occ))) return rcc;
+    if ((rcc = scg_configure(cfg_f, k_step<false>, threads, (size_t)smem, &occ))) return rcc;
     int grid = step_grid(B, threads);
     if (cull)
         k_step<true><<<grid, threads, smem, st>>>(map->d_blob, smem, B, x, y, vx, vy, action, x2, y2, vx2, vy2, reward, flags);

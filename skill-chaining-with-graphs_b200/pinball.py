@@ -120,6 +120,54 @@ class PinballMap:
         check(lib.scg_map_grid(self._handle, C.byref(g), ptr(cs), ptr(cand)))
         return G, cs, cand[: self.n_candidates]
 
+    def in_free_space(self, x, y, clearance=None):
+        """True where a ball centre (x, y) is inside the unit square, outside every polygon and farther than
+        `clearance` (default 1.05 ball radii) from every edge (fp64 geometry, host side)."""
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        c = self.ball_r * 1.05 if clearance is None else clearance
+        ok = (x > 0) & (x < 1) & (y > 0) & (y < 1)
+        for poly in self.polygons:
+            p = poly.astype(np.float64)
+            inside = np.zeros(x.shape, dtype=bool)
+            for i in range(len(p)):
+                (x1, y1), (x2, y2) = p[i], p[(i + 1) % len(p)]
+                if y1 != y2:
+                    inside ^= ((y1 > y) != (y2 > y)) & (x < (x2 - x1) * (y - y1) / (y2 - y1) + x1)
+                dx, dy = x2 - x1, y2 - y1
+                t = np.clip(((x - x1) * dx + (y - y1) * dy) / (dx * dx + dy * dy), 0, 1)
+                ok &= np.hypot(x1 + t * dx - x, y1 + t * dy - y) > c
+            ok &= ~inside
+        return ok
+
+    def validate(self):
+        """Map sanity checks; returns a list of problems, empty when the map is sound."""
+        problems = []
+        if not 0.0 < self.ball_r < 0.1:
+            problems.append(f"ball radius {self.ball_r} outside (0, 0.1)")
+        tx, ty, tr = self.target
+        if not (0 < tx < 1 and 0 < ty < 1 and tr > 0):
+            problems.append("target outside the unit square or with non-positive radius")
+        elif not bool(self.in_free_space(tx, ty, clearance=0.0)):
+            problems.append("target centre lies inside an obstacle")
+        for i, (sx, sy) in enumerate(self.starts):
+            if not bool(self.in_free_space(float(sx), float(sy))):
+                problems.append(f"start {i} ({sx:.3f}, {sy:.3f}) is not in free space")
+        for i, poly in enumerate(self.polygons):
+            if poly.min() < -1e-6 or poly.max() > 1 + 1e-6:
+                problems.append(f"polygon {i} leaves the unit square")
+            d = np.hypot(*(np.roll(poly, -1, axis=0) - poly).T)
+            if d.min() < 1e-6:
+                problems.append(f"polygon {i} has a degenerate edge")
+            area2 = float(np.sum(poly[:, 0] * np.roll(poly[:, 1], -1) - np.roll(poly[:, 0], -1) * poly[:, 1]))
+            if abs(area2) < 1e-9:
+                problems.append(f"polygon {i} has zero area")
+        # the border must be closed: a ball cannot sit on the edge of the unit square
+        for x, y in ((0.001, 0.5), (0.999, 0.5), (0.5, 0.001), (0.5, 0.999)):
+            if bool(self.in_free_space(x, y, clearance=0.0)):
+                problems.append(f"no wall at the border near ({x}, {y}) (the bounds clamp would be reached)")
+        return problems
+
     def sample_free_states(self, rng, n, vmax=1.0):
         """Synthetic benchmark inputs: positions uniform over free space (at least 1.05 ball radii
         from every obstacle, outside every polygon), velocities uniform in [-vmax, vmax]^2."""

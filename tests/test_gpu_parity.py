@@ -763,3 +763,29 @@ def test_graph_mode_parents_match_oracle(scg, torch):
     assert np.array_equal(gag.option.cpu().numpy(), out["option"])
     assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
     assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success) and np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
+
+
+def test_map_validation(scg):
+    for name in ("easy", "hard"):
+        assert scg.PinballMap.from_name(name).validate() == []
+    walls = [p.tolist() for p in oracle.PinballMap.from_name("easy").polygons[:4]]
+    bad = scg.PinballMap(0.02, (0.5, 0.5, 0.04), [(0.5, 0.5), (0.2, 0.2)], walls + [[(0.4, 0.4), (0.6, 0.4), (0.6, 0.6), (0.4, 0.6)]])
+    probs = bad.validate()
+    assert any("target" in p for p in probs) and any("start 0" in p for p in probs) and not any("start 1" in p for p in probs)
+    open_map = scg.PinballMap(0.02, (0.9, 0.2, 0.04), [(0.2, 0.9)], [[(0.4, 0.4), (0.6, 0.4), (0.5, 0.6)]])
+    assert any("no wall" in p for p in open_map.validate())
+
+
+def test_agent_on_second_device(scg, torch):
+    """Kernel shared-memory opt-ins are per device: an agent on cuda:1 after one on cuda:0 in the same process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    res = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            _, gag = _paired_agents(scg, torch, 2048, 3, 4, "hard", 21, sync_interval=4)
+            gag.run(8)
+            torch.cuda.synchronize(dev)
+            res.append((gag.s.cpu(), gag.options.W.cpu()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-6 * max(1.0, float(res[0][1].abs().max()))
