@@ -789,3 +789,49 @@ def test_agent_on_second_device(scg, torch):
             res.append((gag.s.cpu(), gag.options.W.cpu()))
     assert torch.equal(res[0][0], res[1][0])
     assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-6 * max(1.0, float(res[0][1].abs().max()))
+
+
+@pytest.mark.parametrize("B,order,K,name", [(1, 3, 1, "easy"), (33, 1, 2, "hard"), (95, 2, 3, "easy"), (257, 4, 2, "hard"),
+                                            (64, 5, 8, "easy"), (31, 3, 16, "hard")])
+def test_agent_odd_shapes_match_oracle(scg, torch, B, order, K, name):
+    """Ragged batches (not a multiple of the warp size), every order, K = 1 and K = 16: three fused steps in one
+    launch and a sweep, against the oracle stepping the same transitions."""
+    oag, gag = _paired_agents(scg, torch, B, order, K, name, 30 + B, sync_interval=50, option_timeout=2, epsilon=0.3)
+    outs = []
+    for t in range(3):
+        out = oag.step()
+        gag.step()
+        gag.action.copy_(torch.as_tensor(out["action"]))
+        gag.invalidate()
+        assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
+        assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+        assert np.array_equal(gag.option.cpu().numpy(), out["option"])
+    assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL
+    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
+    # and the multi-step launch path: run(5) == 5 x step() on a twin (epsilon-greedy draws are keyed by env and step)
+    _, a = _paired_agents(scg, torch, B, order, K, name, 30 + B, sync_interval=4, option_timeout=2, epsilon=0.3)
+    _, b = _paired_agents(scg, torch, B, order, K, name, 30 + B, sync_interval=4, option_timeout=2, epsilon=0.3)
+    a.run(5)
+    for _ in range(5):
+        b.step()
+    assert torch.equal(a.s, b.s) and torch.equal(a.action, b.action) and torch.equal(a.option, b.option)
+    assert float((a.options.trace - b.options.trace).abs().max()) <= 1e-5 * max(1.0, float(b.options.trace.abs().max()))
+    assert float((a.options.W - b.options.W).abs().max()) <= 1e-5 * max(1.0, float(b.options.W.abs().max()))
+
+
+def test_empty_batch_and_bad_arguments(scg, torch):
+    import ctypes as C
+    ag = scg.SkillChainAgent(scg.AgentConfig(map="easy", batch=0, order=3, max_options=2))
+    ag.run(3)                                                   # no envs: nothing to do, no error
+    assert ag.t == 0 or ag.t == 3
+    with pytest.raises(ValueError):
+        scg.SkillChainAgent(scg.AgentConfig(map="easy", batch=4, window=99))
+    with pytest.raises(ValueError):
+        scg.OptionSet(17, 3, 4)
+    with pytest.raises(ValueError):
+        scg.OptionSet(2, 6, 4)
+    lib = scg.load_library()
+    assert lib.scg_agent_run(None, None, None, 1, 1, None, None) == -1
+    o = scg.OptionSet(2, 3, 4)
+    assert lib.scg_xchg_create(o.ctx, 3, 2, C.byref(C.c_void_p())) == -1
