@@ -12,8 +12,8 @@
  *   - the library never allocates or frees caller buffers; all `float*` / `int*` arguments are
  *     DEVICE pointers unless the function name ends in `_host`
  *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default)
- *   - no function synchronises the device except the `_host` variants, scg_map_create and
- *     the scratch (re)allocation inside scg_ctx_create
+ *   - no function synchronises the device except the `_host` variants, scg_map_create, scg_xchg_create and
+ *     the scratch (re)allocations inside the context (first sweep) and the map (first scg_step_host)
  *   - one host thread drives one context; entry points are re-entrant, not internally locked
  *   - actions: 0 +x, 1 +y, 2 -x, 3 -y, 4 none;  A = 5;  F = (order+1)^4;  orders 1..5
  *   - state is structure-of-arrays: x[B], y[B], vx[B], vy[B] (fp32)
@@ -80,7 +80,7 @@ int scg_reset(const scg_map_t *map, int B, const uint8_t *mask /* may be NULL = 
               float *y, float *vx, float *vy, uint64_t seed, uint32_t step, uint32_t env_offset,
               void *stream);
 /* HOST-buffer variant of scg_step (state in, state/reward/flags out; copies included) */
-int scg_step_host(const scg_map_t *map, int B, float *state_soa /* HOST [4][B] in/out */,
+int scg_step_host(scg_map_t *map, int B, float *state_soa /* HOST [4][B] in/out */,
                   const int *action /* HOST */, float *reward /* HOST */, int *flags /* HOST */,
                   void *stream);
 

@@ -1,7 +1,7 @@
 // scg_agent.cu - the fused lock-step agent step (K1 + K2 + K4 in ONE kernel) and the windowed pipeline.
 //
 // Mirrors oracle/agent.py SkillChainAgent.step, numbered steps 1-8 of its docstring (the reference
-// has no code: /root/reference/README.md:1-2).  Per env step one kernel, k_agent_step, does
+// has no code: /root/reference/README.md:1-2).  Per env step, k_agent_step does
 //   1    s2, r_env, flags = env.step(a)                                   (pinball_step, scg_step.cuh)
 //   2-3  initiation bits of s2 (K4), termination, option reward
 //   4    Q_o(s2, .) (K2), eps-greedy a2, TD error; Q_o(s, a) is carried from the previous step
@@ -10,8 +10,9 @@
 //   6-8  example-ring append, env reset, option re-selection + first action under the new option
 // Sarsa(lambda) itself runs once per window of up to win_cap steps (k_window in scg_sarsa.cu: the
 // forward-view form of oracle/option.py OptionSet.flush), so the dense per-env traces cross HBM once
-// per window instead of once per step.  Weight application (and the cross-GPU all-reduce of dW / cnt)
-// happens every sync interval.
+// per window instead of once per step.  Weight application (and the cross-GPU sum of dW / cnt, scg_xchg.cu)
+// happens every sync interval.  Because nothing couples the envs while the weights are frozen, ONE launch runs
+// all the steps of a window for every env, with the env's state in registers between the steps.
 //
 // Kernel design: one thread per env, work handed out per warp (32 envs) and interleaved over the
 // persistent CTAs so that every SM gets the same number of warps even at B = 65,536.  Each CTA stages
@@ -24,7 +25,7 @@
 #include "scg_common.cuh"
 #include "scg_step.cuh"
 
-int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace, float gl, float *dW,
+int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, float *trace, float gl, float *dW,
                       cudaStream_t st);
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
@@ -314,7 +315,9 @@ static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_age
 extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if (!ctx || !ag) return SCG_EINVAL;
     if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; return 0; }
-    int rc = scg_launch_window(ctx, ag->B, ag->win_len, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
+    // option ids in the records are 0 .. n_active (the gestating slot), and n_active only grows
+    const int k_used = std::min(ag->K, std::max(ag->n_active, 0) + 1);
+    int rc = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
                                (cudaStream_t)stream);
     if (rc) return rc;
     ag->win_len = 0;

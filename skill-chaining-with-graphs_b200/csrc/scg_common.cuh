@@ -94,6 +94,8 @@ struct scg_map {
     int *h_obst, *h_local;  // [E]
     int *h_cell_start;      // [G*G+1]
     int *h_cand;            // [n_cand]
+    float *d_stage;         // device staging of scg_step_host (state, action, reward, flags), grown on demand
+    size_t stage_cap;
 };
 
 struct scg_ctx {

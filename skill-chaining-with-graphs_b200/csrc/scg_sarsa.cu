@@ -336,8 +336,8 @@ struct WinCtl {
     int nseg, pad;
 };
 
-template <int N1, int VEC, int NT, int CH, bool MULTI>
-__global__ void __launch_bounds__(NT) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl) {
     using V = typename VecT<VEC>::type;
     constexpr int F = N1 * N1 * N1 * N1;
@@ -790,12 +790,20 @@ static int ensure_partials(scg_ctx *ctx, int n) {
     return 0;
 }
 
-template <int N1, int VEC, int NT, int CH, bool MULTI>
-static int launch_window_tm(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
+template <int N1>
+static size_t window_smem(const scg_ctx *ctx, int k_used) {
     constexpr int NN = N1 * N1;
-    const size_t smem = (((size_t)ctx->K * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
-                        (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + 2 * sizeof(WinCtl) + 36 * sizeof(float);
-    auto kern = k_window<N1, VEC, NT, CH, MULTI>;
+    return (((size_t)k_used * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
+           (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) + 2 * sizeof(WinCtl) + 36 * sizeof(float);
+}
+
+// k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
+// the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB>
+static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
+                            cudaStream_t st) {
+    const size_t smem = window_smem<N1>(ctx, k_used);
+    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB>;
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
     int rcc = scg_configure(cfgc, kern, NT, smem, &per_sm);
@@ -807,50 +815,55 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, const float4 *rec, float
     int grid = std::max(1, std::min(B, SCG_NUM_SMS * occ));
     int rc = ensure_partials(ctx, grid);
     if (rc) return rc;
-    kern<<<grid, NT, smem, st>>>(B, ctx->K, T, rec, trace, ctx->d_partial, gl);
+    kern<<<grid, NT, smem, st>>>(B, k_used, T, rec, trace, ctx->d_partial, gl);
     SCG_LAUNCH_CHECK();
     return grid;
 }
 
-template <int N1, int VEC, int NT, int CH>
-static int launch_window_t(scg_ctx *ctx, int B, int T, const float4 *rec, float *trace, float gl, cudaStream_t st) {
-    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false>(ctx, B, T, rec, trace, gl, st);
-    return launch_window_tm<N1, VEC, NT, CH, true>(ctx, B, T, rec, trace, gl, st);
+template <int N1, int VEC, int NT, int CH, int MINB = 1>
+static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
+                           cudaStream_t st) {
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB>(ctx, B, T, k_used, rec, trace, gl, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB>(ctx, B, T, k_used, rec, trace, gl, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
 // fold the T recorded steps of the window into dW and the traces
-int scg_launch_window(scg_ctx *ctx, int B, int T, const float *rec, float *trace, float gl, float *dW,
+int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, float *trace, float gl, float *dW,
                       cudaStream_t st) {
-    if (T < 1 || T > SCG_WIN_MAX) return SCG_EINVAL;
+    if (T < 1 || T > SCG_WIN_MAX || k_used < 1 || k_used > ctx->K) return SCG_EINVAL;
     const float4 *r4 = reinterpret_cast<const float4 *>(rec);
     int grid = 0, rc;
     static int win_ch3 = -1, win_ch5 = -1;   // tuning knobs: chunks per thread at orders 3 and 5
     if (win_ch3 < 0) { const char *e = getenv("SCG_WIN_CH3"); win_ch3 = e ? atoi(e) : 1; }
     if (win_ch5 < 0) { const char *e = getenv("SCG_WIN_CH5"); win_ch5 = e ? atoi(e) : 1; }
+    static int win_2cta5 = -1;
+    if (win_2cta5 < 0) { const char *e = getenv("SCG_WIN_2CTA5"); win_2cta5 = e ? atoi(e) : 0; }   // measured: 80 registers + spills, 0.345 vs 0.258 ms/step: off
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
     switch (ctx->order) {
         // <N1, floats per chunk, threads, chunks per thread>.  Measured on B200 (order 3, B = 65,536): two warps per
         // env with one chunk per thread 0.155 ms; one warp per env with two chunks per thread (SCG_WIN_CH3=2) has 18 %
         // fewer instructions but only 8 warps/SM to hide the shared-memory latency: 0.159 ms.  Order 5: 2.27 vs 2.38 ms.
-        case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, r4, trace, gl, st); break;
-        case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, r4, trace, gl, st); break;
+        case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
+        case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
         case 3:
-            if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, r4, trace, gl, st);
-            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, r4, trace, gl, st);
+            if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, st);
+            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, st);
             break;
-        case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, r4, trace, gl, st); break;
+        case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
         case 5:
-            if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, r4, trace, gl, st);
-            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, r4, trace, gl, st);
+            if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+            else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
+                grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, st);
             break;
         default: return SCG_ELIMIT;
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
     if ((rc = scg_prof_push(ctx, 1, st, true))) return rc;
     if ((rc = scg_prof_push(ctx, 2, st, false))) return rc;
-    int n = ctx->K * SCG_A * ctx->F;
+    int n = k_used * SCG_A * ctx->F;
     dim3 g((n + 255) / 256, std::min(grid, 96));
     k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
     SCG_LAUNCH_CHECK();

@@ -197,6 +197,7 @@ extern "C" int scg_map_create(const float *verts, const int *poly_start, int n_p
 extern "C" int scg_map_destroy(scg_map_t *m) {
     if (!m) return 0;
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_stage) cudaFree(m->d_stage);
     free(m->h_blob); free(m->h_edges); free(m->h_obst); free(m->h_local);
     free(m->h_cell_start); free(m->h_cand);
     free(m);
@@ -300,20 +301,19 @@ extern "C" int scg_reset(const scg_map_t *map, int B, const uint8_t *mask, float
 }
 
 // HOST-buffer variant: the call a user of PinballEnv.step makes with NumPy arrays.
-extern "C" int scg_step_host(const scg_map_t *map, int B, float *state_soa, const int *action, float *reward,
+extern "C" int scg_step_host(scg_map_t *map, int B, float *state_soa, const int *action, float *reward,
                              int *flags, void *stream) {
     if (!map || B < 0 || (B > 0 && (!state_soa || !action || !reward || !flags))) return SCG_EINVAL;
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    static float *d_buf = nullptr;
-    static size_t cap = 0;
     size_t need = (size_t)B * 7 * 4;  // 4 state + action + reward + flags
-    if (need > cap) {
-        if (d_buf) cudaFree(d_buf);
-        d_buf = nullptr; cap = 0;
-        SCG_CUDA_OK(cudaMalloc((void **)&d_buf, need));
-        cap = need;
+    if (need > map->stage_cap) {      // the staging block belongs to the map (freed by scg_map_destroy)
+        if (map->d_stage) cudaFree(map->d_stage);
+        map->d_stage = nullptr; map->stage_cap = 0;
+        SCG_CUDA_OK(cudaMalloc((void **)&map->d_stage, need));
+        map->stage_cap = need;
     }
+    float *d_buf = map->d_stage;
     float *ds = d_buf;
     int *da = (int *)(d_buf + (size_t)4 * B);
     float *dr = d_buf + (size_t)5 * B;
