@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "Pinball env-steps/s incl. option Q-eval+Sarsa(lambda) update"
 UNIT = "env-steps/s"
+MANAGE_EVERY = 64          # steps between calls of the option-creation controller (SkillChainAgent.manage)
 
 
 def workload(args):
@@ -50,6 +51,7 @@ def config_json(args, n_gpus):
         "workload": f"configs[1]: Pinball '{args.map}', {args.batch} envs per GPU, order-{args.order} Fourier "
                     f"(F={F}), {args.options} option slots (2 active initiation classifiers), "
                     f"sync every {args.sync_interval} steps",
+        "controller": f"SkillChainAgent.manage() every {MANAGE_EVERY} steps inside the timed region",
         "envs_per_gpu": args.batch, "global_envs": args.batch * n_gpus, "order": args.order,
         "options": args.options, "sync_interval": args.sync_interval, "map": args.map,
         "parallelism": f"env-sharded x{n_gpus}, sum of (dW, cnt) over ranks every sync interval "
@@ -125,8 +127,10 @@ def _cpu_worker(wl, batch, steps, seed, q, warmup=1):
     for _ in range(max(warmup, 1)):             # untimed warm-up
         ag.step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for i in range(steps):
         ag.step()
+        if (i + 1) % MANAGE_EVERY == 0:         # the option-creation controller, as in run_episode
+            ag.manage()
     q.put((batch * steps, time.perf_counter() - t0))
 
 
@@ -217,6 +221,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     ag.run(max(args.warmup, 3))
+    ag.warm_up_controller()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -227,7 +232,9 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    ag.run(args.steps)
+    for lo in range(0, args.steps, MANAGE_EVERY):               # full skill chaining: steps + the controller
+        ag.run(min(MANAGE_EVERY, args.steps - lo))
+        ag.manage()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -241,9 +248,11 @@ def run_ours(args):
         hs, ha = s2, a2
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         s2, r, f, a2, d = ag.step_host(hs, ha)
         hs, ha = s2, a2                              # views of the pinned result buffers, fed straight back
+        if (i + 1) % MANAGE_EVERY == 0:
+            ag.manage()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None

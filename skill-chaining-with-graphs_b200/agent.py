@@ -321,6 +321,21 @@ class SkillChainAgent:
         self._push_parents()
         return True
 
+    def warm_up_controller(self):
+        """Run the controller's device code path once on scratch data (torch loads its kernels lazily: the first
+        promotion would otherwise pay a few milliseconds per kind of tensor op inside the caller's loop)."""
+        torch, K = self.torch, self.options.K
+        saved = self.options.theta[K - 1].clone()
+        X = torch.tensor([[0.1, 0.2], [0.8, 0.7], [0.3, 0.9], [0.6, 0.1]], device=self.device)
+        y = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device=self.device)
+        _ = allreduce_scalar_sum(self.n_success[0:1].to(torch.int64) & 0xFFFFFFFF, self.pg)
+        _ = self.examples(0)
+        self.options.theta[K - 1].zero_()
+        self.options.fit_initiation(K - 1, X, y, 1, self.cfg.clf_lr)
+        self.options.theta[K - 1].copy_(saved)
+        self._push_parents()
+        torch.cuda.synchronize()
+
     def counters(self):
         """Host copy of the global statistics: episodes, goals, mean finished return, per-option counts."""
         st = self.stats.cpu().numpy()

@@ -131,20 +131,41 @@ __global__ void k_clf_eval(int B, const float *__restrict__ x, const float *__re
     }
 }
 
-// mean_i (p_i - y_i) psi_i with a single CTA: per-thread partial sums, warp shuffles, smem.
-__device__ __forceinline__ void clf_grad_block(int N, const float *__restrict__ X, const uint8_t *__restrict__ y,
-                                               const float th[SCG_N_PSI], float g_out[SCG_N_PSI], float *sm) {
-    float g[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        float px = X[2 * i], py = X[2 * i + 1];
-        float psi[SCG_N_PSI] = {1.f, px, py, px * px, px * py, py * py};
-        float z = 0.f;
+// mean_i (p_i - y_i) psi_i with a single CTA: per-thread partial sums, warp shuffles, smem.  Each thread keeps up to
+// CLF_CACHE of its examples in registers, so the gradient-descent loop of k_clf_fit touches global memory only for
+// the examples beyond 1024 * CLF_CACHE.
+#define CLF_CACHE 8
+struct ClfCache {
+    float x[CLF_CACHE], y[CLF_CACHE], lab[CLF_CACHE];
+};
+__device__ __forceinline__ void clf_load(int N, const float *__restrict__ X, const uint8_t *__restrict__ y, ClfCache &c) {
 #pragma unroll
-        for (int j = 0; j < SCG_N_PSI; ++j) z = fmaf(th[j], psi[j], z);
-        float d = 1.0f / (1.0f + expf(-z)) - (float)y[i];
-#pragma unroll
-        for (int j = 0; j < SCG_N_PSI; ++j) g[j] = fmaf(d, psi[j], g[j]);
+    for (int k = 0; k < CLF_CACHE; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        const bool in = i < N;
+        c.x[k] = in ? X[2 * i] : 0.f;
+        c.y[k] = in ? X[2 * i + 1] : 0.f;
+        c.lab[k] = in ? (float)y[i] : 0.f;
     }
+}
+__device__ __forceinline__ void clf_accum(float px, float py, float lab, const float th[SCG_N_PSI], float g[SCG_N_PSI]) {
+    const float psi[SCG_N_PSI] = {1.f, px, py, px * px, px * py, py * py};
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < SCG_N_PSI; ++j) z = fmaf(th[j], psi[j], z);
+    const float d = 1.0f / (1.0f + expf(-z)) - lab;
+#pragma unroll
+    for (int j = 0; j < SCG_N_PSI; ++j) g[j] = fmaf(d, psi[j], g[j]);
+}
+__device__ __forceinline__ void clf_grad_block(int N, const float *__restrict__ X, const uint8_t *__restrict__ y,
+                                               const ClfCache &c, const float th[SCG_N_PSI], float g_out[SCG_N_PSI],
+                                               float *sm) {
+    float g[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < CLF_CACHE; ++k)
+        if ((int)(threadIdx.x + k * blockDim.x) < N) clf_accum(c.x[k], c.y[k], c.lab[k], th, g);
+    for (int i = threadIdx.x + CLF_CACHE * blockDim.x; i < N; i += blockDim.x)
+        clf_accum(X[2 * i], X[2 * i + 1], (float)y[i], th, g);
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int j = 0; j < SCG_N_PSI; ++j) {
@@ -152,10 +173,13 @@ __device__ __forceinline__ void clf_grad_block(int N, const float *__restrict__ 
         if (lane == 0) sm[warp * SCG_N_PSI + j] = v;
     }
     __syncthreads();
-    if (threadIdx.x < SCG_N_PSI) {
-        float v = 0.f;
-        for (int w = 0; w < nw; ++w) v += sm[w * SCG_N_PSI + threadIdx.x];
-        sm[32 * SCG_N_PSI + threadIdx.x] = v / (float)N;
+    if (threadIdx.x < 32) {   // warp 0 folds the per-warp sums: lane (w % 32) holds warp w's value of component j
+#pragma unroll
+        for (int j = 0; j < SCG_N_PSI; ++j) {
+            float v = (lane < nw) ? sm[lane * SCG_N_PSI + j] : 0.f;
+            v = scg_warp_sum(v);
+            if (lane == 0) sm[32 * SCG_N_PSI + j] = v / (float)N;
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -169,7 +193,9 @@ __global__ void __launch_bounds__(1024) k_clf_grad(int N, const float *__restric
     float th[SCG_N_PSI], g[SCG_N_PSI];
 #pragma unroll
     for (int j = 0; j < SCG_N_PSI; ++j) th[j] = theta_k[j];
-    clf_grad_block(N, X, y, th, g, sm);
+    ClfCache c;
+    clf_load(N, X, y, c);
+    clf_grad_block(N, X, y, c, th, g, sm);
     if (threadIdx.x < SCG_N_PSI) grad[threadIdx.x] = g[threadIdx.x];
 }
 
@@ -179,8 +205,10 @@ __global__ void __launch_bounds__(1024) k_clf_fit(int N, const float *__restrict
     float th[SCG_N_PSI], g[SCG_N_PSI];
 #pragma unroll
     for (int j = 0; j < SCG_N_PSI; ++j) th[j] = theta_k[j];
+    ClfCache c;
+    clf_load(N, X, y, c);
     for (int it = 0; it < steps; ++it) {
-        clf_grad_block(N, X, y, th, g, sm);
+        clf_grad_block(N, X, y, c, th, g, sm);
 #pragma unroll
         for (int j = 0; j < SCG_N_PSI; ++j) th[j] = __fsub_rn(th[j], __fmul_rn(lr, g[j]));
     }
