@@ -154,6 +154,7 @@ typedef struct scg_agent {
     uint32_t *parents;               /* [K] */
     float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */
     int32_t *ex_count, *n_success, *n_fail; /* [K] */
+    int32_t *n_success_global;       /* [K] n_success summed over ranks as of the last cross-GPU sync (multi-rank runs) */
     /* global statistics (device), 4 x 64 bit: [0] episodes, [1] goals (uint64), [2] sum of finished returns (double) */
     int64_t *stats;
 } scg_agent_t;
@@ -187,9 +188,11 @@ int scg_xchg_local_ptr(scg_xchg_t *x, void **ptr_out);
 int scg_xchg_connect_ptrs(scg_xchg_t *x, void *const *peer_ptrs /* HOST [world] device pointers */);
 int scg_xchg_status(scg_xchg_t *x, int *timed_out);
 /* dW (reduced over this rank's envs) and cnt -> summed over ranks -> W, Wt updated; dW and cnt zeroed.
+ * nsucc_local [K] (optional): this rank's option success counters; nsucc_global [K] (optional) receives their sum
+ * over ranks, identical on every rank, so the controller needs no collective of its own.
  * Every rank must call it the same number of times. */
 int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
-                  int window_steps, void *stream);
+                  int window_steps, const int *nsucc_local, int *nsucc_global, void *stream);
 
 /* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
  * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]

@@ -40,6 +40,7 @@ class AgentStruct(C.Structure):
         ("cnt", C.c_void_p), ("parents", C.c_void_p),
         ("ex_xy", C.c_void_p), ("ex_label", C.c_void_p),
         ("ex_count", C.c_void_p), ("n_success", C.c_void_p), ("n_fail", C.c_void_p),
+        ("n_success_global", C.c_void_p),
         ("stats", C.c_void_p),
     ]
 
@@ -82,7 +83,7 @@ _SIGS = {
     "scg_xchg_local_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "scg_xchg_connect_ptrs": (C.c_int, [_P, _P]),
     "scg_xchg_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
-    "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P]),
+    "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
     "scg_profile_begin": (C.c_int, [_P, C.c_int, C.c_int]),
     "scg_profile_end": (C.c_int, [_P, _P, _P]),

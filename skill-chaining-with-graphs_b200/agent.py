@@ -91,6 +91,7 @@ class SkillChainAgent:
         self.ex_count = torch.zeros(K, **i32)
         self.n_success = torch.zeros(K, **i32)
         self.n_fail = torch.zeros(K, **i32)
+        self.n_success_global = torch.zeros(K, **i32)
         self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
         self.active_mask = 0
         self.n_active = 0
@@ -151,7 +152,8 @@ class SkillChainAgent:
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
         for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
-                     "q_carry", "win_rec", "parents", "ex_xy", "ex_label", "ex_count", "n_success", "n_fail", "stats"):
+                     "q_carry", "win_rec", "parents", "ex_xy", "ex_label", "ex_count", "n_success", "n_fail",
+                     "n_success_global", "stats"):
             setattr(g, name, getattr(self, name).data_ptr())
         g.trace, g.W, g.Wt, g.theta = o._trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
         g.dW, g.cnt = o._dW.data_ptr(), o.cnt.data_ptr()
@@ -272,7 +274,8 @@ class SkillChainAgent:
         self.flush()
         if self._xchg is not None:
             check(self.lib.scg_xchg_sync(self._xchg, o.order, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt),
-                                         self.cfg.alpha, max(int(g.window_steps), 1), _lib.current_stream()))
+                                         self.cfg.alpha, max(int(g.window_steps), 1), ptr(self.n_success),
+                                         ptr(self.n_success_global), _lib.current_stream()))
             o.window_steps = 0
         else:
             allreduce_deltas(o._dW, o.cnt, self.pg)
@@ -294,6 +297,18 @@ class SkillChainAgent:
         n = int(min(int(self.ex_count[k]) & 0xFFFFFFFF, self.cfg.example_capacity))
         return self.ex_xy[k, :n].clone(), self.ex_label[k, :n].clone()
 
+    def _fit_slot(self, g, X, y):
+        """Fit option g's initiation classifier on (X, y); across ranks every rank fits on its own examples and the
+        parameters are averaged."""
+        cfg = self.cfg
+        self.options.theta[g].zero_()
+        if X.shape[0] > 0:
+            self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
+        ws = world_size(self.pg)
+        if ws > 1:
+            th = allreduce_scalar_sum(self.options.theta[g].clone(), self.pg)
+            self.options.theta[g].copy_(th / ws)
+
     def manage(self):
         """Promote the gestating option once it has enough successes (oracle/agent.py manage).
         Multi-GPU: success counts are summed over ranks so every rank promotes at the same step;
@@ -302,18 +317,17 @@ class SkillChainAgent:
         g = self.n_active
         if g >= K - 1:
             return False
-        # the device counter is 32 bits and wraps: read it as unsigned, sum over ranks in 64 bits
-        n_succ = allreduce_scalar_sum(self.n_success[g:g + 1].to(torch.int64) & 0xFFFFFFFF, self.pg)
-        if int(n_succ) < cfg.gestation_successes:
+        if self._xchg is not None:
+            # the peer-memory sync already left the sum over ranks (as of the last sync) on every GPU: same
+            # decision everywhere, no collective in the loop
+            n_succ = int(self.n_success_global[g])
+        else:
+            # the device counter is 32 bits and wraps: read it as unsigned, sum over ranks in 64 bits
+            n_succ = int(allreduce_scalar_sum(self.n_success[g:g + 1].to(torch.int64) & 0xFFFFFFFF, self.pg))
+        if n_succ < cfg.gestation_successes:
             return False
         X, y = self.examples(g)
-        self.options.theta[g].zero_()
-        if X.shape[0] > 0:
-            self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
-        ws = world_size(self.pg)
-        if ws > 1:
-            th = allreduce_scalar_sum(self.options.theta[g].clone(), self.pg)
-            self.options.theta[g].copy_(th / ws)
+        self._fit_slot(g, X, y)
         self.active_mask |= (1 << g)
         self.n_active += 1
         n = self.n_active
@@ -322,16 +336,18 @@ class SkillChainAgent:
         return True
 
     def warm_up_controller(self):
-        """Run the controller's device code path once on scratch data (torch loads its kernels lazily: the first
-        promotion would otherwise pay a few milliseconds per kind of tensor op inside the caller's loop)."""
+        """Run the controller's device code path once on scratch data (torch loads its kernels lazily and NCCL sets
+        up a collective on first use: the first promotion would otherwise pay milliseconds inside the caller's loop)."""
         torch, K = self.torch, self.options.K
         saved = self.options.theta[K - 1].clone()
         X = torch.tensor([[0.1, 0.2], [0.8, 0.7], [0.3, 0.9], [0.6, 0.1]], device=self.device)
         y = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device=self.device)
-        _ = allreduce_scalar_sum(self.n_success[0:1].to(torch.int64) & 0xFFFFFFFF, self.pg)
+        _ = int(allreduce_scalar_sum(self.n_success[0:1].to(torch.int64) & 0xFFFFFFFF, self.pg))
+        _ = int(self.n_success_global[0])
         _ = self.examples(0)
-        self.options.theta[K - 1].zero_()
-        self.options.fit_initiation(K - 1, X, y, 1, self.cfg.clf_lr)
+        clf_steps, self.cfg.clf_steps = self.cfg.clf_steps, 1
+        self._fit_slot(K - 1, X, y)
+        self.cfg.clf_steps = clf_steps
         self.options.theta[K - 1].copy_(saved)
         self._push_parents()
         torch.cuda.synchronize()

@@ -379,7 +379,7 @@ extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *
         if (sync_interval > 0 && ag->window_steps >= sync_interval) {
             if ((rc = scg_agent_flush(ctx, ag, stream))) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, false))) return rc;
-            if (xchg) rc = scg_xchg_sync(xchg, ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream);
+            if (xchg) rc = scg_xchg_sync(xchg, ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, ag->n_success, ag->n_success_global, stream);
             else rc = scg_apply(ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream);
             if (rc) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, true))) return rc;

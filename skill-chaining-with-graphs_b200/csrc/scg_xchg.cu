@@ -23,7 +23,7 @@
 #include "scg_common.cuh"
 
 #define XCHG_SLICE 256                 // elements per CTA
-#define XCHG_HDR 16                    // per-slice header: update counts of the K options (int bits)
+#define XCHG_HDR 32                    // per-slice header: update counts [0..15] and success counters [16..31] of the K options (int bits)
 #define XCHG_ROW (XCHG_SLICE + XCHG_HDR)
 #define XCHG_MAX_WORLD 16
 
@@ -43,6 +43,8 @@ struct SyncArgs {
     float alpha, steps;
     float *W, *Wt, *dW;
     int *cnt;
+    const int *nsucc_local;   // [K] this rank's option success counters (may be NULL)
+    int *nsucc_global;        // [K] out: their sum over ranks as of this sync (may be NULL)
     unsigned int *ticket;
     size_t flag_bytes;
     unsigned char *peer[XCHG_MAX_WORLD];
@@ -73,7 +75,10 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
     // 1. publish
     const float my = (j < a.n) ? a.dW[j] : 0.f;
     xrow[i] = my;
-    if (i < a.K) xrow[XCHG_SLICE + i] = __int_as_float(a.cnt[i]);
+    if (i < a.K) {
+        xrow[XCHG_SLICE + i] = __int_as_float(a.cnt[i]);
+        xrow[XCHG_SLICE + 16 + i] = __int_as_float(a.nsucc_local ? a.nsucc_local[i] : 0);
+    }
     __syncthreads();
     // the last CTA to have read cnt zeroes it for the next window
     if (i == 0) {
@@ -108,11 +113,16 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
     }
     if (i < a.K) {
         int tot = 0;
+        long long succ = 0;   // the counters are 32-bit and wrap: summed as unsigned
         for (int r = 0; r < a.world; ++r) {
             const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
             tot += __float_as_int(r == a.rank ? xrow[XCHG_SLICE + i] : ld_sys_f32(prow + XCHG_SLICE + i));
+            if (c == 0) succ += (unsigned int)__float_as_int(r == a.rank ? xrow[XCHG_SLICE + 16 + i] : ld_sys_f32(prow + XCHG_SLICE + 16 + i));
         }
         s_cnt[i] = tot;
+        // every rank publishes the same global success count, so the option-creation controller takes the same
+        // decision everywhere without a collective of its own
+        if (c == 0 && a.nsucc_global) a.nsucc_global[i] = (int)(succ > 0x7fffffffll ? 0x7fffffffll : succ);
     }
     __syncthreads();
     if (j < a.n) {   // same arithmetic as k_apply (scg_sarsa.cu)
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
 // ---- host side ------------------------------------------------------------------------------------------
 extern "C" int scg_xchg_create(scg_ctx_t *ctx, int rank, int world, scg_xchg_t **out) {
     if (!ctx || !out || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return SCG_EINVAL;
-    if (ctx->K > XCHG_HDR) return SCG_ELIMIT;
+    if (ctx->K > 16) return SCG_ELIMIT;
     scg_xchg *x = (scg_xchg *)calloc(1, sizeof(scg_xchg));
     if (!x) return SCG_ENOMEM;
     x->rank = rank; x->world = world; x->K = ctx->K;
@@ -222,7 +232,7 @@ extern "C" int scg_xchg_status(scg_xchg_t *x, int *timed_out) {
 
 // dW (already reduced over this rank's slabs) and cnt -> summed over ranks -> applied; dW and cnt zeroed
 extern "C" int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
-                             int window_steps, void *stream) {
+                             int window_steps, const int *nsucc_local, int *nsucc_global, void *stream) {
     if (!x || !W || !Wt || !dW || !cnt) return SCG_EINVAL;
     if (K != x->K || K * SCG_A * scg_pow4(order + 1) != x->n) return SCG_EINVAL;
     for (int r = 0; r < x->world; ++r)
@@ -232,6 +242,7 @@ extern "C" int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *W
     a.seq = ++x->seq;
     a.alpha = alpha; a.steps = (float)std::max(window_steps, 1);
     a.W = W; a.Wt = Wt; a.dW = dW; a.cnt = cnt; a.ticket = x->d_ticket;
+    a.nsucc_local = nsucc_local; a.nsucc_global = nsucc_global;
     a.flag_bytes = x->flag_bytes;
     for (int r = 0; r < XCHG_MAX_WORLD; ++r) a.peer[r] = r < x->world ? x->d_peer[r] : nullptr;
     cudaStream_t st = (cudaStream_t)stream;

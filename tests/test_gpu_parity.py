@@ -574,7 +574,7 @@ def test_xchg_single_rank_equals_apply(scg, torch):
     lib = scg.load_library()
     x = C.c_void_p()
     check(lib.scg_xchg_create(b.ctx, 0, 1, C.byref(x)))
-    check(lib.scg_xchg_sync(x, order, K, ptr(b.W), ptr(b.Wt), ptr(b._dW), ptr(b.cnt), 0.07, 4, current_stream()))
+    check(lib.scg_xchg_sync(x, order, K, ptr(b.W), ptr(b.Wt), ptr(b._dW), ptr(b.cnt), 0.07, 4, None, None, current_stream()))
     torch.cuda.synchronize()
     assert torch.equal(a.W, b.W) and torch.equal(a.Wt, b.Wt)
     assert float(b._dW.abs().max()) == 0.0 and int(b.cnt.sum()) == 0
@@ -616,17 +616,20 @@ def test_xchg_two_devices_sum_and_identical_replicas(scg, torch):
         ptrs[r] = p
     for r in range(2):
         check(lib.scg_xchg_connect_ptrs(xs[r], ptrs))
+    nloc = [torch.tensor([5, 0, 7, 1], dtype=torch.int32, device=f"cuda:{r}") * (r + 1) for r in range(2)]
+    nglob = [torch.zeros(4, dtype=torch.int32, device=f"cuda:{r}") for r in range(2)]
     for it in range(3):                      # three syncs: exercises the double buffering and the sequence flags
         for r in range(2):
             with torch.cuda.device(r):
                 o = sets[r]
                 check(lib.scg_xchg_sync(xs[r], order, K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt), 0.05, 8,
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                        ptr(nloc[r]), ptr(nglob[r]), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         for r in range(2):
             torch.cuda.synchronize(r)
         ref = scg.OptionSet if False else None
         w0, w1 = sets[0].W.cpu(), sets[1].W.cpu()
         assert torch.equal(w0, w1)                                           # replicas bit-identical
+        assert nglob[0].cpu().tolist() == nglob[1].cpu().tolist() == [15, 0, 21, 3]   # success counters summed over ranks
         if it == 0:
             ora = oracle.OptionSet(K, order, 4, alpha=0.05)
             ora.W[:] = W
