@@ -373,7 +373,10 @@ class SkillChainAgent:
             self.run(k)
             steps += k
             self.manage()
-            if int(self.stats[0]) - base >= B:
+            done = self.stats[0:1] - base >= B
+            if world_size(self.pg) > 1:          # every rank must leave the loop at the same step (the syncs are collective)
+                done = allreduce_scalar_sum(done.to(self.torch.int32), self.pg) == world_size(self.pg)
+            if bool(done):
                 break
         c = self.counters()
         return dict(steps=steps, finished=c["episodes"] - base, goals=c["goals"], mean_return=c["mean_return"],
