@@ -42,13 +42,14 @@ MANAGE_EVERY = 64          # steps between calls of the option-creation controll
 def workload(args):
     return dict(map=args.map, batch=args.batch, order=args.order, max_options=args.options,
                 sync_interval=args.sync_interval, gamma=0.99, lam=0.9, alpha=1e-3, epsilon=0.05, seed=0,
-                option_timeout=250, max_episode_steps=2000)
+                option_timeout=250, max_episode_steps=2000, graph=bool(getattr(args, "graph", False)))
 
 
 def config_json(args, n_gpus):
     F = (args.order + 1) ** 4
     return {
-        "workload": f"configs[1]: Pinball '{args.map}', {args.batch} envs per GPU, order-{args.order} Fourier "
+        "workload": f"configs[{4 if getattr(args, 'graph', False) else 1}]{' option-graph variant' if getattr(args, 'graph', False) else ''}: "
+                    f"Pinball '{args.map}', {args.batch} envs per GPU, order-{args.order} Fourier "
                     f"(F={F}), {args.options} option slots (2 active initiation classifiers), "
                     f"sync every {args.sync_interval} steps",
         "controller": f"SkillChainAgent.manage() every {MANAGE_EVERY} steps inside the timed region",
@@ -123,7 +124,7 @@ def _cpu_worker(wl, batch, steps, seed, q, warmup=1):
     setup_classifiers(ag.options.theta)
     ag.active[:2] = True
     ag.n_active = 2
-    ag.parents[1], ag.parents[2] = 1, 2
+    ag.parents[1], ag.parents[2] = (np.uint32(1 | (1 << 31)), np.uint32(3 | (1 << 31))) if wl.get("graph") else (1, 2)
     for _ in range(max(warmup, 1)):             # untimed warm-up
         ag.step()
     ag.manage()
@@ -213,7 +214,8 @@ def run_ours(args):
     setup_classifiers(theta)
     ag.options.theta.copy_(torch.as_tensor(theta))
     ag.active_mask, ag.n_active = 3, 2
-    ag.parents_host[1], ag.parents_host[2] = 1, 2
+    GOAL = 1 << 31
+    ag.parents_host[1], ag.parents_host[2] = (1 | GOAL, 3 | GOAL) if args.graph else (1, 2)
     ag._push_parents()
 
     def barrier():
@@ -351,6 +353,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--graph", action="store_true", help="option-graph variant (configs[4]): an option's targets are the "
+                    "initiation sets of ALL earlier options and the goal, so chains merge")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
