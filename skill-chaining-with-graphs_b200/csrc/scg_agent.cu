@@ -33,6 +33,7 @@ struct StepArgs {
     scg_agent_t ag;
     const unsigned char *map_blob;
     int blob_bytes, w_bytes;
+    int k_stage;      // options whose weights are staged to shared memory (ids 0 .. k_stage-1 are the ones in use)
     int wait_first;   // 1: the previous launch may have written the weights - wait for it before staging them
     int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
     float4 *rec;  // this step's slab of the window: [B][2]
@@ -72,8 +73,8 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
     }
 }
 
-template <int N1, bool SMEMW, bool PAIR>
-__global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ StepArgs args) {
+template <int N1, bool SMEMW, bool PAIR, int NTH>
+__global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_constant__ StepArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
     const scg_agent_t &g = args.ag;
@@ -83,12 +84,26 @@ __global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ S
     // may have rewritten the weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
-    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? args.w_bytes : 0, &bar);
+    // the map always moves with one bulk-TMA copy; so do the weights when every option is staged (contiguous table);
+    // when only the options in use are staged, their slots are gathered feature by feature with plain 16-byte copies
+    const bool bulk_w = SMEMW && args.k_stage == g.K;
+    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, bulk_w ? args.w_bytes : 0, &bar);
+    if (SMEMW && !bulk_w) {
+        const int per_f = 2 * args.k_stage, total = (args.w_bytes >> 4);
+        const float4 *src = reinterpret_cast<const float4 *>(g.Wt);
+        float4 *dst = reinterpret_cast<float4 *>(w_smem);
+        for (int c = threadIdx.x; c < total; c += blockDim.x) {
+            const int f = c / per_f, j = c - f * per_f;
+            dst[c] = __ldg(src + (size_t)f * 2 * g.K + j);
+        }
+        __syncthreads();
+    }
     if (!args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
     const StepMap m = make_step_map(smem);
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
     const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
     const int K = g.K;
+    const int Kw = SMEMW ? args.k_stage : K;          // options per feature in the weight table being read
     const int gest = min(g.n_active, K - 1);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n_tiles = (g.B + 31) >> 5;
@@ -120,7 +135,7 @@ __global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ S
             float2 zb[4];
             scg_phasors(nx, ny, nvx, nvy, zb);
             float qb[SCG_A], qsa = qc;
-            const WCur<SMEMW> wc(Wt, K, o);
+            const WCur<SMEMW> wc(Wt, Kw, o);
             if (PAIR && s == 0) {
                 float2 za[4];
                 scg_phasors(sx, sy, svx, svy, za);
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ S
                     }
                     const int os = __shfl_sync(FULL, o_next, sl);
                     float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, K, os), qp);
+                    if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, Kw, os), qp);
 #pragma unroll
                     for (int dd = 1; dd < N1; ++dd) {                // slot head (c0 == 0) gathers the partial sums
 #pragma unroll
@@ -261,17 +276,18 @@ __global__ void __launch_bounds__(256, 2) k_agent_step(const __grid_constant__ S
 }
 
 // ---- launch plumbing --------------------------------------------------------------------------------
-template <int N1, bool SMEMW, bool PAIR>
+template <int N1, bool SMEMW, bool PAIR, int NTH>
 static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
-    auto kern = k_agent_step<N1, SMEMW, PAIR>;
+    auto kern = k_agent_step<N1, SMEMW, PAIR, NTH>;
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
-    int rcc = scg_configure(cfgc, kern, 256, smem, &per_sm);
+    int rcc = scg_configure(cfgc, kern, NTH, smem, &per_sm);
     if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
+    constexpr int WPC = NTH / 32;                       // warps (tiles in flight) per CTA
     const int n_tiles = (args.ag.B + 31) / 32;
     // enough CTAs for one warp per tile if they all fit at once, else every resident slot
-    int grid = (n_tiles + 7) / 8;
+    int grid = (n_tiles + WPC - 1) / WPC;
     if (grid > SCG_NUM_SMS) {   // same number of CTAs on every SM: as many rounds of 148 as the tiles need, if resident
         const int rounds = std::min(per_sm, (grid + SCG_NUM_SMS - 1) / SCG_NUM_SMS);
         grid = SCG_NUM_SMS * rounds;
@@ -279,7 +295,7 @@ static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
     grid = std::max(grid, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(NTH);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -292,14 +308,20 @@ static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
     return 0;
 }
 
+// mode 0: weights through the read-only global path; 1: staged to shared memory, two 256-thread CTAs per SM;
+// 2: staged, one 512-thread CTA per SM (order 5: the options in use take up to ~200 KB)
 template <int N1>
-static int launch_step_n(const StepArgs &args, bool smemw, bool pair, cudaStream_t st) {
+static int launch_step_n(const StepArgs &args, int mode, bool pair, cudaStream_t st) {
     const size_t blob = (size_t)((args.blob_bytes + 127) & ~127);
-    if (smemw) {
+    if (mode == 1) {
         const size_t smem = blob + args.w_bytes;
-        return pair ? launch_step_t<N1, true, true>(args, smem, st) : launch_step_t<N1, true, false>(args, smem, st);
+        return pair ? launch_step_t<N1, true, true, 256>(args, smem, st) : launch_step_t<N1, true, false, 256>(args, smem, st);
     }
-    return pair ? launch_step_t<N1, false, true>(args, blob, st) : launch_step_t<N1, false, false>(args, blob, st);
+    if (mode == 2) {
+        const size_t smem = blob + args.w_bytes;
+        return pair ? launch_step_t<N1, true, true, 512>(args, smem, st) : launch_step_t<N1, true, false, 512>(args, smem, st);
+    }
+    return pair ? launch_step_t<N1, false, true, 256>(args, blob, st) : launch_step_t<N1, false, false, 256>(args, blob, st);
 }
 
 static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_agent_t *ag) {
@@ -331,17 +353,22 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.ag = *ag;
     args.map_blob = map->d_blob;
     args.blob_bytes = map->hdr.blob_bytes;
-    args.w_bytes = ag->K * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
+    // only the options that can be executed (ids 0 .. n_active) need their weights on chip
+    args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1);
+    args.w_bytes = args.k_stage * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
     args.n_steps = n;
-    // weights go to shared memory when two CTAs per SM still fit next to the map
-    const bool smemw = (size_t)args.w_bytes + args.blob_bytes + 256 <= 100 * 1024;
+    // weights go to shared memory when two CTAs per SM still fit next to the map, or one big CTA
+    static int big = -1;
+    if (big < 0) { const char *e = getenv("SCG_STEP_BIG_CTA"); big = e ? atoi(e) : 1; }
+    const size_t need = (size_t)args.w_bytes + args.blob_bytes + 256;
+    const int mode = need <= 100 * 1024 ? 1 : ((big && need <= 220 * 1024) ? 2 : 0);
     const bool pair = !ag->carry_valid;
     // a step kernel directly behind another step kernel of the same window may stage the weights early
     args.wait_first = !(ag->carry_valid && ag->win_len > 0 && !(ctx->prof_on && (ctx->prof_mask & 1)));
     int rc;
     if ((rc = scg_prof_push(ctx, 0, st, false))) return rc;
-    DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, smemw, pair, st));
+    DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, mode, pair, st));
     if (rc) return rc;
     if ((rc = scg_prof_push(ctx, 0, st, true))) return rc;
     std::swap(ag->x, ag->x2); std::swap(ag->y, ag->y2);
