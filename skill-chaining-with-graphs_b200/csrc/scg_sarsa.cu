@@ -853,7 +853,9 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
             break;
         case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
         case 5:
-            if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+            if (win_ch5 == 2 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two 6-warp CTAs, two chunks per thread
+                grid = launch_window_t<6, 4, 192, 2, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+            else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, st);
             else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
                 grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, st);
             else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, st);

@@ -838,3 +838,41 @@ def test_empty_batch_and_bad_arguments(scg, torch):
     assert lib.scg_agent_run(None, None, None, 1, 1, None, None) == -1
     o = scg.OptionSet(2, 3, 4)
     assert lib.scg_xchg_create(o.ctx, 3, 2, C.byref(C.c_void_p())) == -1
+
+
+def test_full_size_order5_hard_window_and_sharding(scg, torch):
+    """configs[2] per-GPU shape (hard map, 131,072 envs, order 5, 8 option slots): 8 steps as one window == as two
+    windows of 4, and the two half-batches reproduce the whole batch (states bit-identical, dW to rounding)."""
+    global FULL_B
+    saved, FULL_B = FULL_B, 131072
+    try:
+        whole = _full_agent(scg, torch, FULL_B, 0, order=5, K=8, name="hard", window=8)
+        whole.run(8)
+        st, act = whole.s.cpu(), whole.action.cpu()
+        dW = whole.options.dW.double().cpu()
+        tr_sum = whole.options.trace.double().sum(dim=(1, 2)).cpu()
+        cnt = whole.options.cnt.cpu()
+        del whole
+        torch.cuda.empty_cache()
+        w4 = _full_agent(scg, torch, FULL_B, 0, order=5, K=8, name="hard", window=4)
+        w4.run(8)
+        assert torch.equal(w4.s.cpu(), st) and torch.equal(w4.action.cpu(), act)
+        d4 = w4.options.dW.double().cpu()
+        assert float((d4 - dW).abs().max()) <= 1e-4 * max(1.0, float(dW.abs().max()))
+        t4 = w4.options.trace.double().sum(dim=(1, 2)).cpu()
+        assert float((t4 - tr_sum).abs().max()) <= 1e-4 * max(1.0, float(tr_sum.abs().max()))
+        del w4
+        torch.cuda.empty_cache()
+        sdW, scnt, sts = torch.zeros_like(dW), torch.zeros_like(cnt), []
+        for i in range(2):
+            sh = _full_agent(scg, torch, FULL_B // 2, i * FULL_B // 2, order=5, K=8, name="hard", window=8)
+            sh.run(8)
+            sdW += sh.options.dW.double().cpu()
+            scnt += sh.options.cnt.cpu()
+            sts.append(sh.s.cpu())
+            del sh
+            torch.cuda.empty_cache()
+        assert torch.equal(torch.cat(sts, dim=1), st) and torch.equal(scnt, cnt)
+        assert float((sdW - dW).abs().max()) <= 1e-4 * max(1.0, float(dW.abs().max()))
+    finally:
+        FULL_B = saved
