@@ -352,6 +352,46 @@ class SkillChainAgent:
         self._push_parents()
         torch.cuda.synchronize()
 
+    # -- checkpoint / resume ----------------------------------------------------
+    _CKPT_TENSORS = ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "ex_xy", "ex_label", "ex_count",
+                     "n_success", "n_fail", "stats", "q_carry")
+
+    def save(self, path):
+        """Write everything needed to resume this rank (option weights, classifiers, option graph, per-env state and
+        traces, counters) to `path` (.npz).  The open window is folded in first."""
+        self.flush()
+        o, g = self.options, self._struct
+        arrs = {k: getattr(self, k).cpu().numpy() for k in self._CKPT_TENSORS}
+        arrs.update(W=o.W.cpu().numpy(), theta=o.theta.cpu().numpy(), trace=o._trace.cpu().numpy(),
+                    dW=o._dW.cpu().numpy(), cnt=o.cnt.cpu().numpy(), state=self.s.cpu().numpy(),
+                    parents=self.parents_host.copy(),
+                    meta=np.array([self.n_active, self.active_mask, int(g.step), int(g.window_steps)], dtype=np.int64))
+        np.savez(path, **arrs)
+
+    def load(self, path):
+        """Restore a checkpoint written by save() into an agent built with the same AgentConfig."""
+        torch = self.torch
+        z = np.load(path)
+        o, g = self.options, self._struct
+        if tuple(z["W"].shape) != tuple(o.W.shape) or z["state"].shape != tuple(self.s.shape):
+            raise ValueError("checkpoint does not match this agent's configuration")
+        self.flush()
+        for k in self._CKPT_TENSORS:
+            getattr(self, k).copy_(torch.as_tensor(z[k]))
+        o.W.copy_(torch.as_tensor(z["W"]))
+        o.theta.copy_(torch.as_tensor(z["theta"]))
+        o._trace.copy_(torch.as_tensor(z["trace"]))
+        o._dW.copy_(torch.as_tensor(z["dW"]))
+        o.cnt.copy_(torch.as_tensor(z["cnt"]))
+        o.pack()
+        self.s.copy_(torch.as_tensor(z["state"]))
+        self.parents_host[:] = z["parents"]
+        self._push_parents()
+        self.n_active, self.active_mask = int(z["meta"][0]), int(z["meta"][1])
+        g.step, g.window_steps, g.win_len = int(z["meta"][2]), int(z["meta"][3]), 0
+        o.window_steps = int(z["meta"][3])
+        g.carry_valid = 0
+
     def counters(self):
         """Host copy of the global statistics: episodes, goals, mean finished return, per-option counts."""
         st = self.stats.cpu().numpy()

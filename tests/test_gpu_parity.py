@@ -876,3 +876,25 @@ def test_full_size_order5_hard_window_and_sharding(scg, torch):
         assert float((sdW - dW).abs().max()) <= 1e-4 * max(1.0, float(dW.abs().max()))
     finally:
         FULL_B = saved
+
+
+def test_checkpoint_resume(scg, torch, tmp_path):
+    """save() in the middle of a sync interval, load() into a fresh agent, continue: same trajectory as the original."""
+    _, a = _paired_agents(scg, torch, 3000, 3, 4, "hard", 17, sync_interval=8, option_timeout=5, epsilon=0.1)
+    a.run(13)                                   # mid-interval: 5 steps of the second window are open
+    path = str(tmp_path / "ckpt.npz")
+    a.save(path)
+    _, b = _paired_agents(scg, torch, 3000, 3, 4, "hard", 17, sync_interval=8, option_timeout=5, epsilon=0.1)
+    b.run(3)                                    # same configuration, different history: load() must override all of it
+    b.load(path)
+    assert b.t == a.t == 13
+    a.run(11)
+    b.run(11)
+    torch.cuda.synchronize()
+    assert torch.equal(a.s, b.s) and torch.equal(a.action, b.action) and torch.equal(a.option, b.option)
+    assert float((a.options.W - b.options.W).abs().max()) <= 1e-6 * max(1.0, float(a.options.W.abs().max()))
+    assert float((a.options.trace - b.options.trace).abs().max()) <= 1e-5 * max(1.0, float(a.options.trace.abs().max()))
+    assert a.counters()["episodes"] == b.counters()["episodes"]
+    with pytest.raises(ValueError):
+        _, c = _paired_agents(scg, torch, 100, 3, 4, "hard", 1)
+        c.load(path)
