@@ -160,150 +160,6 @@ __global__ void __launch_bounds__(NT) k_trace(int B, int K, const float4 *__rest
     for (int i = threadIdx.x; i < K * NCH; i += NT) out[i] = acc[i];
 }
 
-// ---- TMA-ring variant of the sweep ----------------------------------------------------------------
-// Each env's trace is one contiguous block of A*F*4 bytes, so it moves with 1-D bulk TMA copies:
-// thread 0 keeps S-1 loads in flight into a shared-memory ring (cp.async.bulk + mbarrier
-// complete_tx), all threads update the landed block in place (decay, + phi on row a, accumulate
-// delta * e into the CTA's dW), and the block goes back with a bulk store.  No registers hold
-// in-flight data, so the load queue is deep regardless of occupancy, and the LSU only sees
-// shared-memory traffic.  Used whenever ring + accumulator fit in shared memory.
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
-                 : "memory");
-}
-
-#define SCG_MAX_STAGES 12
-
-// NT consumer threads + one producer warp.  Per stage two mbarriers: full[s] (TMA load landed) and
-// done[s] (all consumers finished updating the block in place).  The producer stores block i as soon
-// as done[i % S] fires and refills the stage of block i - D only once that block's store has read
-// its shared memory (bulk_group wait with D groups still pending), so neither side waits on a store.
-template <int N1, int CPT, int NT>
-__global__ void __launch_bounds__(NT + 32) k_trace_tma(int B, int K, int S, int D, const float4 *__restrict__ rec,
-                                                       float *trace, float *__restrict__ partial, float gl) {
-    constexpr int F = N1 * N1 * N1 * N1;
-    constexpr int AF = SCG_A * F;
-    constexpr int NCH = AF / 4;
-    constexpr uint32_t BYTES = AF * 4;
-    static_assert(F % 4 == 0 && NT * CPT >= NCH && NT % 32 == 0, "layout");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long full[SCG_MAX_STAGES], done[SCG_MAX_STAGES];
-    float4 *ring = reinterpret_cast<float4 *>(smem_raw);   // [S][NCH]
-    float4 *acc = ring + (size_t)S * NCH;                  // [K][NCH]
-
-    for (int i = threadIdx.x; i < K * NCH; i += NT + 32) acc[i] = vzero4();
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&done[s])), "r"(NT));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int stride = gridDim.x;
-    const int n_mine = (B - (int)blockIdx.x + stride - 1) / stride;   // envs blockIdx.x + i*stride < B
-
-    if (threadIdx.x >= NT) {
-        // ---- producer warp: one lane drives the TMA queue ----
-        if (threadIdx.x == NT) {
-            int pre = n_mine < S ? n_mine : S;
-            for (int i = 0; i < pre; ++i)
-                tma_load_1d(smem_addr(ring + (size_t)i * NCH), trace + (size_t)(blockIdx.x + i * stride) * AF, BYTES,
-                            smem_addr(&full[i]));
-            for (int i = 0; i < n_mine; ++i) {
-                const int s = i % S;
-                const int b = blockIdx.x + i * stride;
-                mbar_wait(smem_addr(&done[s]), (uint32_t)((i / S) & 1));
-                const uint32_t meta = __float_as_uint(__ldg(reinterpret_cast<const float *>(rec + (size_t)b * 3 + 2) + 1));
-                if (meta & SCG_META_ACTIVE) tma_store_1d(trace + (size_t)b * AF, smem_addr(ring + (size_t)s * NCH), BYTES);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                const int j = i - D;
-                if (j >= 0 && j + S < n_mine) {
-                    // all but the D most recent stores have read their shared memory: block j's stage is free
-                    switch (D) {
-                        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
-                        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
-                        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
-                        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
-                        case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
-                        case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
-                        default: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
-                    }
-                    const int sp = j % S;
-                    tma_load_1d(smem_addr(ring + (size_t)sp * NCH),
-                                trace + (size_t)(blockIdx.x + (j + S) * stride) * AF, BYTES, smem_addr(&full[sp]));
-                }
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
-    } else {
-        // ---- consumers: thread t owns the same chunk(s) of every block ----
-        int row[CPT];
-        uint32_t dig[CPT][4];
-        bool own[CPT];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            int c = threadIdx.x + i * NT;
-            own[i] = c < NCH;
-            int e0 = (own[i] ? c : 0) * 4;
-            row[i] = e0 / F;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dig[i][v] = pack_digits<N1>((e0 + v) % F);
-        }
-        for (int i = 0; i < n_mine; ++i) {
-            const int s = i % S;
-            const int b = blockIdx.x + i * stride;
-            const float2 dm = __ldg(reinterpret_cast<const float2 *>(rec + (size_t)b * 3 + 2));
-            const uint32_t meta = __float_as_uint(dm.y);
-            float4 *buf = ring + (size_t)s * NCH;
-            mbar_wait(smem_addr(&full[s]), (uint32_t)((i / S) & 1));
-            if (meta & SCG_META_ACTIVE) {
-                const float delta = dm.x;
-                const int a = meta & 7, o = (meta >> 8) & 0xFF;
-                const bool zero_after = (meta & SCG_META_ZERO_AFTER) != 0;
-                float4 *ap = acc + (size_t)o * NCH;
-#pragma unroll
-                for (int k = 0; k < CPT; ++k) {
-                    if (!own[k]) continue;
-                    int c = threadIdx.x + k * NT;
-                    float4 v = vscale(buf[c], gl);
-                    if (row[k] == a) {
-                        Phasors ph = make_phasors(__ldg(rec + (size_t)b * 3), __ldg(rec + (size_t)b * 3 + 1));
-                        v = add_phi(v, ph, dig[k]);
-                    }
-                    ap[c] = vfma(delta, v, ap[c]);
-                    buf[c] = zero_after ? vzero4() : v;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> TMA store
-            }
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&done[s])) : "memory");
-        }
-    }
-    __syncthreads();
-    float4 *out = reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * K * AF);
-    for (int i = threadIdx.x; i < K * NCH; i += NT + 32) out[i] = acc[i];
-}
-
 // ---- windowed (forward-view) sweep: the agent pipeline's K3 --------------------------------------
 // Mirrors oracle/option.py OptionSet.flush.  The fused step kernel left, for each of the T steps of the
 // window, a 32-byte record per env (state, delta, action / option / termination bits).  One CTA sweeps
@@ -709,37 +565,6 @@ static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, 
     return grid;
 }
 
-template <int N1, int CPT, int NT>
-static int launch_trace_tma_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, float gl, cudaStream_t st) {
-    const size_t block = (size_t)SCG_A * ctx->F * sizeof(float);
-    const size_t acc = (size_t)ctx->K * block;
-    const size_t budget = 220 * 1024;
-    if (acc + 3 * block > budget) return 0;   // not enough room for a useful ring: caller falls back
-    // stages: enough for ~48 KB in flight per CTA, within the budget, and leaving room for >= 2 CTAs/SM if possible
-    int S = (int)std::min<size_t>(SCG_MAX_STAGES, (budget - acc) / block);
-    int want = (int)std::max<size_t>(3, std::min<size_t>(SCG_MAX_STAGES, (48 * 1024 + block - 1) / block + 1));
-    S = std::min(S, want);
-    static int s_env = -1, d_env = -1;
-    if (s_env < 0) { const char *e = getenv("SCG_TRACE_STAGES"); s_env = e ? atoi(e) : 0; }
-    if (d_env < 0) { const char *e = getenv("SCG_TRACE_LAG"); d_env = e ? atoi(e) : 0; }
-    if (s_env >= 2 && s_env <= SCG_MAX_STAGES && acc + (size_t)s_env * block <= budget) S = s_env;
-    int D = std::min(S / 2, 4);
-    if (d_env >= 1 && d_env < S && d_env <= 6) D = d_env;
-    size_t smem = acc + (size_t)S * block;
-    auto kern = k_trace_tma<N1, CPT, NT>;
-    static ScgKernelCfg cfgc = {};
-    int per_sm = 0;
-    int rcc = scg_configure(cfgc, kern, NT + 32, smem, &per_sm);
-    if (rcc) return rcc;
-    if (per_sm < 1) return 0;
-    int grid = std::max(1, std::min(B, SCG_NUM_SMS * per_sm));
-    int rc = ensure_partials(ctx, grid);
-    if (rc) return rc;
-    kern<<<grid, NT + 32, smem, st>>>(B, ctx->K, S, D, rec, trace, ctx->d_partial, gl);
-    SCG_LAUNCH_CHECK();
-    return grid;
-}
-
 int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float gl, float *dW, cudaStream_t st) {
     int grid = 0;
     const float4 *r4 = reinterpret_cast<const float4 *>(rec);
@@ -748,18 +573,10 @@ int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float 
         const char *ev = getenv("SCG_TRACE_U");
         u3 = ev ? atoi(ev) : 4;
     }
-    static int use_tma = -1;
-    if (use_tma < 0) { const char *e = getenv("SCG_TRACE_TMA"); use_tma = e ? atoi(e) : 0; }
-    if (use_tma) {   // opt-in (SCG_TRACE_TMA=1): measured slower than the register path on B200 (0.165 vs 0.129 ms, order 3)
-        switch (ctx->order) {
-            case 1: grid = launch_trace_tma_t<2, 1, 32>(ctx, B, r4, trace, gl, st); break;
-            case 3: grid = launch_trace_tma_t<4, 1, 320>(ctx, B, r4, trace, gl, st); break;
-            case 5: grid = launch_trace_tma_t<6, 2, 832>(ctx, B, r4, trace, gl, st); break;
-            default: break;   // F not a multiple of 4: blocks are not 16-byte aligned, register path below
-        }
-        if (grid < 0) return grid;
-    }
-    if (grid == 0) switch (ctx->order) {
+    // (A bulk-TMA ring variant of this sweep - cp.async.bulk loads into a shared-memory ring, in-place update, bulk
+    // stores - was measured slower on B200: 0.165 vs 0.129 ms at order 3, B = 65,536; with 5 KiB blocks the mbarrier
+    // round trips cost more than register-held loads save.  Removed.)
+    switch (ctx->order) {
         case 1: grid = launch_trace_t<2, 4, 1, 32, 4>(ctx, B, r4, trace, gl, st); break;
         case 2: grid = launch_trace_t<3, 1, 2, 224, 2>(ctx, B, r4, trace, gl, st); break;
         case 3:
@@ -773,7 +590,7 @@ int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float 
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
     int n = ctx->K * SCG_A * ctx->F;
-    dim3 g((n + 255) / 256, std::min(grid, 32));
+    dim3 g((n + 255) / 256, std::min(grid, 96));
     k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
     SCG_LAUNCH_CHECK();
     return 0;

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--min", type=int, default=4096)
     ap.add_argument("--max", type=int, default=1 << 24)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--grid", type=int, default=0, help="broad-phase grid resolution (0 = library default)")
     args = ap.parse_args()
     import torch
     import skill_chaining_with_graphs_b200 as scg
@@ -28,7 +29,7 @@ def main():
     peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     for name in ("easy", "hard"):
-        gmap = scg.PinballMap.from_name(name)
+        gmap = scg.PinballMap.from_name(name, args.grid)
         rng = np.random.default_rng(0)
         base = gmap.sample_free_states(rng, 1 << 16)
         B = args.min
@@ -56,7 +57,8 @@ def main():
             rate = B / (ms * 1e-3)
             print(json.dumps({"config": "configs[3] step-only sweep", "map": name, "envs": B, "ms_per_launch": ms,
                               "env_steps_per_s": rate, "algorithmic_GBps": rate * 44 / 1e9, "hbm_peak_GBps": peak,
-                              "frac_of_hbm_peak": rate * 44 / 1e9 / peak, "edges": gmap.n_edges}), flush=True)
+                              "frac_of_hbm_peak": rate * 44 / 1e9 / peak, "edges": gmap.n_edges, "grid": args.grid or 64,
+                              "grid_candidates": gmap.n_candidates}), flush=True)
             del S, S2, A, r, f
             B *= 4
 
