@@ -107,6 +107,7 @@ class SkillChainAgent:
         self.options.pack()
         self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT, soa=s))
         self._struct = self._make_struct()
+        self.options._on_weights_changed = self._weights_changed
         self._xchg = None
         if world_size(self.pg) > 1 and cfg.sync_backend == "p2p":
             self._xchg = self._connect_peers()
@@ -179,6 +180,12 @@ class SkillChainAgent:
     def state(self):
         """(B, 4) copy of the current state."""
         return self.s.t().contiguous()
+
+    def _weights_changed(self, applied=False):
+        """Hook called by the OptionSet when its weights change (set_weights, apply)."""
+        self._struct.carry_valid = 0
+        if applied:
+            self._struct.window_steps = 0
 
     def invalidate(self):
         """Call after changing state, action, option or weights from outside: the carried Q_o(s, a)

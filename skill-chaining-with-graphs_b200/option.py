@@ -90,6 +90,7 @@ class OptionSet:
         self._trace = torch.zeros((self.B, N_ACTIONS, self.F), **z)
         self._dW = torch.zeros((self.K, N_ACTIONS, self.F), **z)
         self._pre_read = None        # set by SkillChainAgent: folds its open window in before a read
+        self._on_weights_changed = None   # set by SkillChainAgent: its carried Q_o(s, a) goes stale
         self.cnt = torch.zeros(self.K, dtype=torch.int32, device=self.device)
         self.window_steps = 0
         self._ctx = C.c_void_p()
@@ -125,6 +126,8 @@ class OptionSet:
     def set_weights(self, W):
         self.W.copy_(_dev(W, self.torch.float32).reshape(self.K, N_ACTIONS, self.F))
         self.pack()
+        if self._on_weights_changed is not None:
+            self._on_weights_changed()
 
     def pack(self):
         check(self.lib.scg_pack_weights(self.order, self.K, ptr(self.W), ptr(self.Wt), _lib.current_stream()))
@@ -191,6 +194,8 @@ class OptionSet:
         check(self.lib.scg_apply(self.order, self.K, ptr(self.W), ptr(self.Wt), ptr(self._dW), ptr(self.cnt),
                                  self.alpha, max(self.window_steps, 1), _lib.current_stream()))
         self.window_steps = 0
+        if self._on_weights_changed is not None:
+            self._on_weights_changed(applied=True)
 
     # -- K4 --------------------------------------------------------------------------------------
     def initiation_prob(self, state):
