@@ -68,6 +68,7 @@ class AgentConfig:
     clf_steps: int = 200
     clf_lr: float = 1.0
     graph: bool = False
+    windowed: bool = False      # Sarsa(lambda) in the forward-view window form (OptionSet.flush) instead of the dense sweep
 
 
 class SkillChainAgent:
@@ -77,7 +78,7 @@ class SkillChainAgent:
         B, K = cfg.batch, cfg.max_options
         self.env = PinballEnv(self.map, B, seed=cfg.seed, env_offset=cfg.env_offset)
         self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon,
-                                 cfg.seed, cfg.env_offset)
+                                 cfg.seed, cfg.env_offset, windowed=cfg.windowed)
         self.active = np.zeros(K, dtype=bool)
         self.parents = np.zeros(K, dtype=np.uint32)
         self.parents[0] = GOAL_BIT

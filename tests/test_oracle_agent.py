@@ -105,3 +105,25 @@ def test_sync_interval_only_changes_when_weights_move():
         if i < 3:
             assert np.all(b.options.W == 0) and b.options.cnt.sum() == 16 * (i + 1)
     assert np.abs(a.options.W).max() > 0 and np.abs(b.options.W).max() > 0 and b.options.cnt.sum() == 0
+
+
+def test_windowed_agent_equals_dense_agent():
+    """The whole agent with Sarsa(lambda) in the forward-view window form == with the dense per-step sweep
+    (weights only move at syncs, so the TD errors, hence the trajectories, are the same; traces and weights agree
+    to rounding)."""
+    kw = dict(map="hard", batch=96, order=2, max_options=3, seed=5, sync_interval=6, option_timeout=4, epsilon=0.2,
+              alpha=0.01)
+    d = oracle.SkillChainAgent(oracle.AgentConfig(**kw))
+    w = oracle.SkillChainAgent(oracle.AgentConfig(windowed=True, **kw))
+    rng = np.random.default_rng(0)
+    W = (rng.standard_normal(d.options.W.shape) * 0.2).astype(np.float32)
+    d.options.W[:] = W; w.options.W[:] = W
+    for t in range(20):
+        od, ow = d.step(), w.step()
+        assert np.array_equal(od["state"], ow["state"]) and np.array_equal(od["action"], ow["action"])
+        assert np.allclose(od["delta"], ow["delta"], atol=1e-5 * max(1.0, np.abs(od["delta"]).max()))
+        if (t + 1) % 6 == 0:
+            assert np.abs(d.options.W - w.options.W).max() < 1e-6
+    w.options.flush()
+    assert np.abs(d.options.trace - w.options.trace).max() < 1e-5
+    assert (d.n_success + d.n_fail).sum() > 50
