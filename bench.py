@@ -45,6 +45,11 @@ def workload(args):
                 option_timeout=250, max_episode_steps=2000, graph=bool(getattr(args, "graph", False)))
 
 
+def gpu_only(args):
+    """AgentConfig fields that only the GPU backend has."""
+    return dict(sync_backend=args.sync_backend, window=args.window)
+
+
 def config_json(args, n_gpus):
     F = (args.order + 1) ** 4
     return {
@@ -206,7 +211,7 @@ def run_ours(args):
     gmap = scg.PinballMap.from_name(args.map)
     rng = np.random.default_rng(1234 + rank)
     S = gmap.sample_free_states(rng, B)
-    cfg = scg.AgentConfig(**wl, env_offset=rank * B, sync_backend=args.sync_backend)
+    cfg = scg.AgentConfig(**wl, env_offset=rank * B, **gpu_only(args))
     ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
     wrng = np.random.default_rng(7)                     # same weights on every rank
     ag.options.set_weights((wrng.standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32))
@@ -248,7 +253,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     kind_ms, kind_n = ag.profile_end()
     launches = lib.scg_launch_count() - launches0
-    n_side = 8 * args.sync_interval
+    n_side = 8 * max(args.sync_interval, ag.win_cap)
     ag.profile_begin(4 * n_side + 16, kinds=(0, 2, 3))          # untimed side pass: step kernel, reduction, apply / exchange
     ag.run(n_side)
     torch.cuda.synchronize()
@@ -353,6 +358,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--window", type=int, default=0, help="steps per trace sweep (0 = min(sync interval, 8))")
     ap.add_argument("--graph", action="store_true", help="option-graph variant (configs[4]): an option's targets are the "
                     "initiation sets of ALL earlier options and the goal, so chains merge")
     args = ap.parse_args()
