@@ -94,6 +94,7 @@ __device__ __forceinline__ void pinball_step(const StepMap &m, float &x, float &
             int ci = (int)(x * m.gf), cj = (int)(y * m.gf);  // exact: G is a power of two
             uint32_t cell = m.cells[ci * m.G + cj];
             int cnt = cell & 0xFF, start = cell >> 8;
+#pragma unroll 1   // lists are short (0-4 edges): the unrolled-by-4 prologue cost more than it saved
             for (int j = 0; j < cnt; ++j) {
                 int e = m.cand[start + j];
                 float4 ea = m.ea[e];
