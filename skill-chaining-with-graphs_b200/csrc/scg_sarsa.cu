@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
             const uint32_t a = meta & 7u, o = (meta >> 8) & 0xFFu;
             float D = act ? r_dm.x : 0.f, M = !act ? 1.f : (dn ? 0.f : gl);
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
+            for (int off = 1; off < (MULTI ? 32 : SCG_WIN_TB); off <<= 1) {   // T <= 8 steps without MULTI: 3 rounds
                 const float D2 = __shfl_down_sync(FULL, D, off), M2 = __shfl_down_sync(FULL, M, off);
                 if (t + off < 32) { D = fmaf(M, D2, D); M *= M2; }
             }
@@ -655,6 +655,8 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     static int win_ch3 = -1, win_ch5 = -1;   // tuning knobs: chunks per thread at orders 3 and 5
     if (win_ch3 < 0) { const char *e = getenv("SCG_WIN_CH3"); win_ch3 = e ? atoi(e) : 1; }
     if (win_ch5 < 0) { const char *e = getenv("SCG_WIN_CH5"); win_ch5 = e ? atoi(e) : 1; }
+    static int win_9cta3 = -1;
+    if (win_9cta3 < 0) { const char *e = getenv("SCG_WIN_9CTA3"); win_9cta3 = e ? atoi(e) : 0; }
     static int win_2cta5 = -1;
     if (win_2cta5 < 0) { const char *e = getenv("SCG_WIN_2CTA5"); win_2cta5 = e ? atoi(e) : 0; }   // measured: 80 registers + spills, 0.345 vs 0.258 ms/step: off
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
@@ -665,7 +667,9 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
         case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
         case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
         case 3:
-            if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, st);
+            if (win_ch3 == 1 && win_9cta3 && 9 * (window_smem<4>(ctx, k_used) + 1024) <= 227 * 1024)   // nine CTAs per SM (<= 112 registers)
+                grid = launch_window_t<4, 4, 64, 1, 9>(ctx, B, T, k_used, r4, trace, gl, st);
+            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, st);
             else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, st);
             break;
         case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
