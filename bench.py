@@ -213,6 +213,8 @@ def run_ours(args):
     S = gmap.sample_free_states(rng, B)
     cfg = scg.AgentConfig(**wl, env_offset=rank * B, **gpu_only(args))
     ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
+    if world > 1 and args.sync_backend == "p2p" and ag._xchg is None:
+        args.sync_backend = "nccl"                      # the agent fell back (it said why on stderr): report what ran
     wrng = np.random.default_rng(7)                     # same weights on every rank
     ag.options.set_weights((wrng.standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32))
     theta = np.zeros((args.options, 6), dtype=np.float32)

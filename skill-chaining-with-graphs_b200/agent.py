@@ -110,23 +110,46 @@ class SkillChainAgent:
         self.options._on_weights_changed = self._weights_changed
         self._xchg = None
         if world_size(self.pg) > 1 and cfg.sync_backend == "p2p":
-            self._xchg = self._connect_peers()
+            # every rank must end up on the same backend: agree on whether the peer mapping worked everywhere
+            try:
+                x, err = self._connect_peers(), None
+            except Exception as e:          # e.g. CUDA IPC unavailable between these devices
+                x, err = None, e
+            ok = torch.tensor([1 if x is not None else 0], dtype=torch.int32, device=dev)
+            ok = int(allreduce_scalar_sum(ok, self.pg))
+            if ok == world_size(self.pg):
+                self._xchg = x
+            else:
+                if x is not None:
+                    self.lib.scg_xchg_destroy(x)
+                import sys
+                print(f"[scg] peer-memory sync unavailable on {world_size(self.pg) - ok} rank(s) ({err}); "
+                      "using the NCCL all-reduce path", file=sys.stderr)
 
     def _connect_peers(self):
         """Create this rank's exchange buffer and map every peer's through CUDA IPC (handles travel over
-        torch.distributed once)."""
+        torch.distributed once).  The handle exchange is collective, so a rank that failed locally still takes part
+        and every rank then sees the failure."""
         dist = self.torch.distributed
         rank, world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
-        x = C.c_void_p()
-        check(self.lib.scg_xchg_create(self.options.ctx, rank, world, C.byref(x)))
-        nb = self.lib.scg_xchg_handle_bytes()
-        buf = (C.c_ubyte * nb)()
-        check(self.lib.scg_xchg_handle(x, buf))
+        x, mine, err = C.c_void_p(), None, None
+        try:
+            check(self.lib.scg_xchg_create(self.options.ctx, rank, world, C.byref(x)))
+            buf = (C.c_ubyte * self.lib.scg_xchg_handle_bytes())()
+            check(self.lib.scg_xchg_handle(x, buf))
+            mine = bytes(buf)
+        except Exception as e:
+            err = e
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(buf), group=self.pg)
-        blob = b"".join(handles)
-        check(self.lib.scg_xchg_connect(x, C.c_char_p(blob)))
-        dist.barrier(group=self.pg)
+        dist.all_gather_object(handles, mine, group=self.pg)
+        try:
+            if err is not None or any(h is None for h in handles):
+                raise err or _lib.ScgError("a peer could not export its exchange buffer")
+            check(self.lib.scg_xchg_connect(x, C.c_char_p(b"".join(handles))))
+        except Exception:
+            if x:
+                self.lib.scg_xchg_destroy(x)
+            raise
         return x
 
     def __del__(self):
