@@ -200,12 +200,54 @@ template <> struct WCur<true> {
 // table of z_3 powers.  Each feature is consumed by five FFMAs the moment it is formed.
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
+#pragma unroll
+    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
+    if constexpr (N1 <= 4) {
+        // small orders: the N1^2 products z_2^c2 z_3^c3 fit in registers, so a feature is Re(z01 * p23[j]) with one
+        // complex multiply per (c0, c1) pair instead of one per (c0, c1, c2) triple
+        float2 p23[N1 * N1];
+        {
+            float2 p2 = make_float2(1.f, 0.f);
+#pragma unroll
+            for (int c2 = 0; c2 < N1; ++c2) {
+                float2 v = p2;
+#pragma unroll
+                for (int c3 = 0; c3 < N1; ++c3) {
+                    p23[c2 * N1 + c3] = v;
+                    v = scg_cmul(v, z[3]);
+                }
+                p2 = scg_cmul(p2, z[2]);
+            }
+        }
+        float2 z0 = make_float2(1.f, 0.f);
+        int f = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N1; ++c0) {
+            float2 z01 = z0;
+#pragma unroll 1
+            for (int c1 = 0; c1 < N1; ++c1) {
+#pragma unroll
+                for (int j = 0; j < N1 * N1; ++j) {
+                    float phi = fmaf(z01.x, p23[j].x, -z01.y * p23[j].y);
+                    float4 wa, wb;
+                    w.load(f + j, wa, wb);
+                    q[0] = fmaf(wa.x, phi, q[0]);
+                    q[1] = fmaf(wa.y, phi, q[1]);
+                    q[2] = fmaf(wa.z, phi, q[2]);
+                    q[3] = fmaf(wa.w, phi, q[3]);
+                    q[4] = fmaf(wb.x, phi, q[4]);
+                }
+                f += N1 * N1;
+                z01 = scg_cmul(z01, z[1]);
+            }
+            z0 = scg_cmul(z0, z[0]);
+        }
+        return;
+    }
     float2 p3[N1];
     p3[0] = make_float2(1.f, 0.f);
 #pragma unroll
     for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
-#pragma unroll
-    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
     float2 z0 = make_float2(1.f, 0.f);
     int f = 0;
 #pragma unroll 1
