@@ -192,8 +192,8 @@ struct WinCtl {
     int nseg, pad;
 };
 
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
+__global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl) {
     using V = typename VecT<VEC>::type;
     constexpr int F = N1 * N1 * N1 * N1;
@@ -212,6 +212,11 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
     float *glpow = reinterpret_cast<float *>(ctl + 2);                                     // [36]: gl^n
 
     const int tid = threadIdx.x;
+    // CTRL: one extra warp (threads NT .. NT+31) only runs the per-env scan, so that no work warp is slower than the
+    // others at the per-env barrier (worth it when a CTA has many work warps: orders 4 and 5)
+    constexpr int NTT = NT + (CTRL ? 32 : 0);
+    const bool scan_warp = CTRL ? (tid >= NT) : (tid < 32);
+    const bool worker = tid < NT;
     // thread t owns chunks t, t + NT, ... of every action row (each a coalesced access across the CTA)
     bool own[CH];
 #pragma unroll
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
         e_mul[k] = half ? 0.25f : 1.f; e_add[k] = half ? 0.5f : 0.f;
         e_ca[k] = (float)(ij / N1); e_cb[k] = (float)(ij % N1);
     }
-    for (int i = tid; i < K * AF; i += NT) acc[i] = 0.f;
+    for (int i = tid; i < K * AF; i += NTT) acc[i] = 0.f;
     if (tid == 0) {
         float p = 1.f;
         for (int n = 0; n < 36; ++n) { glpow[n] = p; p *= gl; }
@@ -269,13 +274,15 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
     }
 
     auto load_rec = [&](WinItem it) {                    // records of a work item -> registers
+        if (worker) {
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const int t = min(it.blk * SCG_WIN_TB + e_tt[k], T - 1);
-            r_sv[k] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + e_half[k]);
+            for (int k = 0; k < EPT; ++k) {
+                const int t = min(it.blk * SCG_WIN_TB + e_tt[k], T - 1);
+                r_sv[k] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + e_half[k]);
+            }
         }
-        if (it.blk == 0 && tid < T)
-            r_dm = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)tid * B + it.b) * 2 + 1));
+        if (it.blk == 0 && scan_warp && (tid & 31) < T)
+            r_dm = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)(tid & 31) * B + it.b) * 2 + 1));
     };
     auto load_trace = [&](int b) {
         const V *tp = reinterpret_cast<const V *>(trace + (size_t)b * AF);
@@ -290,21 +297,23 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
     // registers -> pair tables (buffer `par`) and, for an env's first block, its control block (buffer `epar`)
     auto build = [&](WinItem it, int par, int epar) {
         float2 *tb = tab + par * TABN;
+        if (worker) {
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            const float s0 = fmaf(r_sv[k].x, e_mul[k], e_add[k]), s1 = fmaf(r_sv[k].y, e_mul[k], e_add[k]);
-            // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
-            const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
-            const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
-            const int idx = tid + k * NT;
-            if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
+            for (int k = 0; k < EPT; ++k) {
+                const float s0 = fmaf(r_sv[k].x, e_mul[k], e_add[k]), s1 = fmaf(r_sv[k].y, e_mul[k], e_add[k]);
+                // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
+                const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
+                const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
+                const int idx = tid + k * NT;
+                if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
+            }
         }
-        if (it.blk == 0 && tid < 32) {
+        if (it.blk == 0 && scan_warp) {
             // warp 0, lane = step: backward recursion G_t = delta_t + m_t G_{t+1} as a suffix scan over (m, delta)
             // pairs, m_t = 0 after a termination, gl otherwise (1 for a step the env sat out)
             WinCtl &cb = ctl[epar];
             const unsigned FULL = 0xffffffffu;
-            const int t = tid;
+            const int t = tid & 31;
             const uint32_t meta = (t < T) ? __float_as_uint(r_dm.y) : 0u;
             const bool act = (meta & SCG_META_ACTIVE) != 0;
             const bool dn = act && (meta & SCG_META_ZERO_AFTER);
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(NT, MINB) k_window(int B, int K, int T, const 
         nxt = nx2;
     }
     float *out = partial + (size_t)blockIdx.x * K * AF;
-    for (int i = tid; i < K * AF; i += NT) out[i] = acc[i];
+    for (int i = tid; i < K * AF; i += NTT) out[i] = acc[i];
 }
 
 // dW[j] += sum over slabs; grid (ceil(n/256), slices); one atomic per address per slice.  Each thread keeps four
@@ -616,14 +625,15 @@ static size_t window_smem(const scg_ctx *ctx, int k_used) {
 
 // k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
 // the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                             cudaStream_t st) {
     const size_t smem = window_smem<N1>(ctx, k_used);
-    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB>;
+    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL>;
+    constexpr int NTT = NT + (CTRL ? 32 : 0);
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
-    int rcc = scg_configure(cfgc, kern, NT, smem, &per_sm);
+    int rcc = scg_configure(cfgc, kern, NTT, smem, &per_sm);
     if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
     static int cap = -1;
@@ -632,16 +642,16 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4
     int grid = std::max(1, std::min(B, SCG_NUM_SMS * occ));
     int rc = ensure_partials(ctx, grid);
     if (rc) return rc;
-    kern<<<grid, NT, smem, st>>>(B, k_used, T, rec, trace, ctx->d_partial, gl);
+    kern<<<grid, NTT, smem, st>>>(B, k_used, T, rec, trace, ctx->d_partial, gl);
     SCG_LAUNCH_CHECK();
     return grid;
 }
 
-template <int N1, int VEC, int NT, int CH, int MINB = 1>
+template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false>
 static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                            cudaStream_t st) {
-    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB>(ctx, B, T, k_used, rec, trace, gl, st);
-    return launch_window_tm<N1, VEC, NT, CH, true, MINB>(ctx, B, T, k_used, rec, trace, gl, st);
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
@@ -655,6 +665,8 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     static int win_ch3 = -1, win_ch5 = -1;   // tuning knobs: chunks per thread at orders 3 and 5
     if (win_ch3 < 0) { const char *e = getenv("SCG_WIN_CH3"); win_ch3 = e ? atoi(e) : 1; }
     if (win_ch5 < 0) { const char *e = getenv("SCG_WIN_CH5"); win_ch5 = e ? atoi(e) : 1; }
+    static int win_ctrl5 = -1;   // order 5: a 12th warp that only runs the per-env scan
+    if (win_ctrl5 < 0) { const char *e = getenv("SCG_WIN_CTRL5"); win_ctrl5 = e ? atoi(e) : 1; }
     static int win_9cta3 = -1;
     if (win_9cta3 < 0) { const char *e = getenv("SCG_WIN_9CTA3"); win_9cta3 = e ? atoi(e) : 0; }
     static int win_2cta5 = -1;
@@ -679,6 +691,7 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
             else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, st);
             else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
                 grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+            else if (win_ctrl5) grid = launch_window_t<6, 4, 352, 1, 1, true>(ctx, B, T, k_used, r4, trace, gl, st);
             else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, st);
             break;
         default: return SCG_ELIMIT;
