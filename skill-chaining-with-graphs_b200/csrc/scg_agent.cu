@@ -346,8 +346,10 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     return 0;
 }
 
-// n consecutive steps (1 <= n <= win_cap - win_len) in one launch
-static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n, void *stream) {
+// n consecutive steps (1 <= n <= win_cap - win_len) in one launch; a full window is swept right away unless the
+// caller defers that (defer_flush) to queue something of its own first
+static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n, void *stream,
+                       bool defer_flush = false) {
     cudaStream_t st = (cudaStream_t)stream;
     StepArgs args;
     args.ag = *ag;
@@ -377,7 +379,7 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     ag->window_steps += n;
     ag->win_len += n;
     ag->carry_valid = 1;
-    if (ag->win_len >= ag->win_cap) return scg_agent_flush(ctx, ag, stream);
+    if (ag->win_len >= ag->win_cap && !defer_flush) return scg_agent_flush(ctx, ag, stream);
     return 0;
 }
 
@@ -446,7 +448,9 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_age
     }
     SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
     ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
-    if ((rc = scg_agent_step(map, ctx, ag, stream))) return rc;
+    if ((rc = check_agent(map, ctx, ag))) return rc;
+    if (ag->B == 0) return 0;
+    if ((rc = agent_steps(map, ctx, ag, 1, stream, /*defer_flush=*/true))) return rc;
     {   // the step swapped the buffers: x..vy is the new state
         void *dst[4] = {h_state2_soa, h_state2_soa + ag->B, h_state2_soa + 2 * (size_t)ag->B, h_state2_soa + 3 * (size_t)ag->B};
         const void *src[4] = {ag->x, ag->y, ag->vx, ag->vy};
@@ -457,7 +461,12 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_age
         const void *src[4] = {ag->reward, ag->flags, ag->action, ag->delta};
         if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
     }
-    SCG_CUDA_OK(cudaStreamSynchronize(st));
+    // The results do not depend on the trace sweep: when this step filled the window, the sweep is queued behind the
+    // copies and the host only waits for the copies, so the sweep overlaps the caller's next host-side work and H2D.
+    if (!ctx->host_ev) SCG_CUDA_OK(cudaEventCreateWithFlags(&ctx->host_ev, cudaEventDisableTiming));
+    SCG_CUDA_OK(cudaEventRecord(ctx->host_ev, st));
+    if (ag->win_len >= ag->win_cap && (rc = scg_agent_flush(ctx, ag, stream))) return rc;
+    SCG_CUDA_OK(cudaEventSynchronize(ctx->host_ev));
     return 0;
 }
 

@@ -105,6 +105,7 @@ struct scg_ctx {
     float *d_rec;        // records for the standalone scg_sarsa_update, grown on demand
     int rec_capacity;
     int win_grid;        // CTAs of the window kernel (0 = not configured yet)
+    cudaEvent_t host_ev; // "results copied" marker of scg_agent_step_host
     // optional per-kernel timing of the agent pipeline (scg_profile_begin / scg_profile_end)
     cudaEvent_t *prof_ev;  // [prof_cap][2] start/stop pairs
     int *prof_kind;        // [prof_cap]

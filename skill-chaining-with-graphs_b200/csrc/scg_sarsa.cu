@@ -725,6 +725,7 @@ extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
     if (!c) return 0;
     if (c->d_partial) cudaFree(c->d_partial);
     if (c->d_rec) cudaFree(c->d_rec);
+    if (c->host_ev) cudaEventDestroy(c->host_ev);
     for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
     free(c->prof_ev);
     free(c->prof_kind);
