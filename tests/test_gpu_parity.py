@@ -898,3 +898,65 @@ def test_checkpoint_resume(scg, torch, tmp_path):
     with pytest.raises(ValueError):
         _, c = _paired_agents(scg, torch, 100, 3, 4, "hard", 1)
         c.load(path)
+
+
+def test_two_device_agents_equal_single_device_agent(scg, torch):
+    """Row (e) end to end: the env batch split over two GPUs (one agent per device, weight deltas exchanged by the
+    peer-memory kernel every sync interval) reproduces the single-GPU run: states bit-identical, replicas identical,
+    weights equal to rounding."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check
+    lib = scg.load_library()
+    Bh = 4096
+    kw = dict(window=0, order=3, K=4, name="hard")
+    global FULL_B
+    saved, FULL_B = FULL_B, 2 * Bh
+    halves, xs = [], []
+    try:
+        with torch.cuda.device(0):
+            whole = _full_agent(scg, torch, 2 * Bh, 0, **kw)
+            whole.cfg.sync_interval = 8
+        for r in range(2):
+            with torch.cuda.device(r):
+                h = _full_agent(scg, torch, Bh, r * Bh, **kw)
+                h.cfg.sync_interval = 8
+                x = C.c_void_p()
+                check(lib.scg_xchg_create(h.options.ctx, r, 2, C.byref(x)))
+                halves.append(h); xs.append(x)
+        for r in range(2):
+            with torch.cuda.device(r):
+                torch.zeros(1, device=f"cuda:{1 - r}").to(f"cuda:{r}")      # peer access both ways
+        ptrs = (C.c_void_p * 2)()
+        for r in range(2):
+            p = C.c_void_p()
+            check(lib.scg_xchg_local_ptr(xs[r], C.byref(p)))
+            ptrs[r] = p
+        for r in range(2):
+            check(lib.scg_xchg_connect_ptrs(xs[r], ptrs))
+            halves[r]._xchg = xs[r]
+        for _ in range(3):                       # three sync intervals, launched back to back without host syncs
+            for r in range(2):
+                with torch.cuda.device(r):
+                    halves[r].run(8)
+        with torch.cuda.device(0):
+            whole.run(24)
+        for r in range(2):
+            torch.cuda.synchronize(r)
+        st = torch.cat([halves[0].s.cpu(), halves[1].s.cpu()], dim=1)
+        assert torch.equal(st, whole.s.cpu())
+        assert torch.equal(halves[0].options.W.cpu(), halves[1].options.W.cpu())
+        assert not halves[0].peer_sync_timed_out() and not halves[1].peer_sync_timed_out()
+        w = whole.options.W.cpu()
+        assert float((halves[0].options.W.cpu() - w).abs().max()) <= 1e-6 * max(1.0, float(w.abs().max()))
+        assert float(w.abs().max()) > 0
+        g = halves[0].n_success_global.cpu()
+        assert torch.equal(g, halves[1].n_success_global.cpu())
+    finally:
+        FULL_B = saved
+        for r in range(2):
+            if r < len(halves):
+                halves[r]._xchg = None
+        for x in xs:
+            lib.scg_xchg_destroy(x)
