@@ -278,11 +278,23 @@ def run_ours(args):
             ag.manage()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    # informational: the same loop for a caller that needs the state only once per sync interval (run_host)
+    T = args.sync_interval
+    hs, ha = ag.s.cpu().numpy().copy(), ag.action.cpu().numpy().copy()
+    for _ in range(2):
+        hs, ha, r, f, d = ag.run_host(hs, ha, T)
+    barrier()
+    t0 = time.perf_counter()
+    n_calls = max(args.steps // T, 1)
+    for _ in range(n_calls):
+        hs, ha, r, f, d = ag.run_host(hs, ha, T)
+    torch.cuda.synchronize()
+    e2e_win_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms, e2e_win_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, e2e_win_ms = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         F = (args.order + 1) ** 4
         total_env_steps = B * world * args.steps
@@ -331,6 +343,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": B * ag.HOST_H2D_BYTES_PER_ENV,
                     "d2h_bytes_per_step": B * ag.HOST_D2H_BYTES_PER_ENV,
                     "api": "SkillChainAgent.step_host -> scg_agent_step_host (pinned host buffers)"},
+            "e2e_per_sync_interval": {"value": B * world * n_calls * T / (e2e_win_ms * 1e-3), "unit": UNIT,
+                                      "h2d_bytes_per_call": B * 20, "d2h_bytes_per_call": B * 32, "steps_per_call": T,
+                                      "api": "SkillChainAgent.run_host: host state in / out once per sync interval "
+                                             "(informational; `e2e` above copies every step)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

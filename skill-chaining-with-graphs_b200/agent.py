@@ -284,6 +284,41 @@ class SkillChainAgent:
             self.sync()
         return cur_np["s2"], cur_np["r"], cur_np["f"], cur_np["a2"], cur_np["d"]
 
+    def run_host(self, state, action, n_steps):
+        """`n_steps` steps for a caller that only needs the state every `n_steps` steps: `state` (4, B) and `action`
+        (B,) go host->device once, the steps run device-resident (with the syncs that fall due), and (state, action,
+        last reward, last flags, last td_error) come back once, as views of pinned host buffers that the next call
+        overwrites (feeding them straight back skips the host-side copy)."""
+        torch = self.torch
+        B = self.cfg.batch
+        if getattr(self, "_hostw", None) is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            h = dict(s=pin((4, B), torch.float32), a=pin((B,), torch.int32), s2=pin((4, B), torch.float32),
+                     out=pin((4, B), torch.float32))
+            h["a2"] = h["out"][2].view(torch.int32)
+            self._hostw = h
+            self._hostw_np = dict(s=h["s"].numpy(), a=h["a"].numpy(), s2=h["s2"].numpy(), a2=h["a2"].numpy(),
+                                  r=h["out"][0].numpy(), f=h["out"][1].view(torch.int32).numpy(), d=h["out"][3].numpy())
+        h, hn = self._hostw, self._hostw_np
+        if state is hn["s2"]:
+            src_s = h["s2"]
+        else:
+            hn["s"][...] = state
+            src_s = h["s"]
+        if action is hn["a2"]:
+            src_a = h["a2"]
+        else:
+            hn["a"][...] = action
+            src_a = h["a"]
+        self.s.copy_(src_s, non_blocking=True)
+        self.action.copy_(src_a, non_blocking=True)
+        self.invalidate()
+        self.run(n_steps)
+        h["s2"].copy_(self.s, non_blocking=True)
+        h["out"].copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return hn["s2"], hn["a2"], hn["r"], hn["f"], hn["d"]
+
     HOST_H2D_BYTES_PER_ENV = 20      # state 16 + action 4
     HOST_D2H_BYTES_PER_ENV = 32      # next state 16 + reward 4 + flags 4 + next action 4 + TD error 4
 

@@ -960,3 +960,17 @@ def test_two_device_agents_equal_single_device_agent(scg, torch):
                 halves[r]._xchg = None
         for x in xs:
             lib.scg_xchg_destroy(x)
+
+
+def test_run_host_equals_run(scg, torch):
+    """run_host (host state in / out once per call) == the device-resident run."""
+    (_, a), (_, b) = (_paired_agents(scg, torch, 3000, 3, 3, "easy", 8, sync_interval=4, epsilon=0.05) for _ in range(2))
+    hs, ha = b.s.cpu().numpy().copy(), b.action.cpu().numpy().copy()
+    for _ in range(3):
+        a.run(4)
+        hs, ha, r, f, d = b.run_host(hs, ha, 4)
+    assert np.array_equal(hs, a.s.cpu().numpy()) and np.array_equal(ha, a.action.cpu().numpy())
+    # (the host path re-evaluates Q_o(s, a) at the start of every call instead of carrying it: TD errors agree to rounding)
+    assert np.array_equal(f, a.flags.cpu().numpy())
+    assert rel_err(d, a.delta.cpu().numpy()) < 1e-5
+    assert float((a.options.W - b.options.W).abs().max()) <= 1e-5 * max(1.0, float(a.options.W.abs().max()))
