@@ -105,6 +105,9 @@ int scg_td_error(int order, int K, int B, const float *x, const float *y, const 
  * trace is [B][A][F]; dW [K][A][F] and cnt [K] accumulate over the sync window. */
 int scg_ctx_create(int order, int K, scg_ctx_t **out);
 int scg_ctx_destroy(scg_ctx_t *ctx);
+/* on != 0: the per-CTA dW slabs are summed in a fixed order (no floating-point atomics), so a run is reproducible bit
+ * for bit; off (default): one atomic per address per slice, ~1 us per step faster at configs[1]. */
+int scg_ctx_set_deterministic(scg_ctx_t *ctx, int on);
 int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const float *y, const float *vx,
                      const float *vy, const int *a, const int *option, const float *delta,
                      const uint8_t *done, const uint8_t *mask /* may be NULL */, float gamma_lambda,

@@ -67,6 +67,7 @@ _SIGS = {
     "scg_td_error": (C.c_int, [C.c_int, C.c_int, C.c_int] + [_P] * 14 + [C.c_float, _P, _P]),
     "scg_ctx_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_P)]),
     "scg_ctx_destroy": (C.c_int, [_P]),
+    "scg_ctx_set_deterministic": (C.c_int, [_P, C.c_int]),
     "scg_sarsa_update": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_float, _P, _P, _P, _P]),
     "scg_apply": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P]),
     "scg_clf_eval": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, _P, _P]),

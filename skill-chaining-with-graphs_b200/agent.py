@@ -46,6 +46,7 @@ class AgentConfig:
     graph: bool = False
     cull: bool = True
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
+    deterministic: bool = False   # fixed-order reduction of the weight deltas: runs reproduce bit for bit (slightly slower)
     sync_backend: str = "p2p"   # multi-rank weight-delta exchange: "p2p" (one kernel over NVLink peer memory) or "nccl"
 
 
@@ -63,7 +64,7 @@ class SkillChainAgent:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon, cfg.seed,
-                                 cfg.env_offset, dev)
+                                 cfg.env_offset, dev, deterministic=cfg.deterministic)
         self.options._pre_read = self.flush        # dW / trace reads see the open window folded in
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)

@@ -102,6 +102,9 @@ struct scg_ctx {
     int order, K, F;
     int n_partials;      // CTAs of the trace kernel
     float *d_partial;    // [n_partials][K][A*F]
+    float *d_red;        // [SCG_RED_SLICES][K][A*F] second-stage scratch of the slab reduction
+    unsigned int *d_tickets;   // one "blocks done" counter per 256-element column of the reduction
+    int deterministic;         // 1: fixed-order slab reduction (scg_ctx_set_deterministic)
     float *d_rec;        // records for the standalone scg_sarsa_update, grown on demand
     int rec_capacity;
     int win_grid;        // CTAs of the window kernel (0 = not configured yet)

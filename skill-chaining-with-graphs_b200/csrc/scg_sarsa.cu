@@ -489,23 +489,70 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     for (int i = tid; i < K * AF; i += NTT) out[i] = acc[i];
 }
 
-// dW[j] += sum over slabs; grid (ceil(n/256), slices); one atomic per address per slice.  Each thread keeps four
-// independent loads in flight (the slabs were just written and mostly sit in L2).
-__global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const float *__restrict__ partial,
-                                                float *__restrict__ dW) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+// dW[j] += sum over the per-CTA slabs.  Block (x, y) sums every SCG_RED_SLICES-th slab, four loads in flight per thread
+// (the slabs were just written and mostly sit in L2).  Fast mode (default): one atomicAdd per address per slice, so the
+// order of the last additions is not fixed and weights agree run-to-run to rounding.  Deterministic mode
+// (scg_ctx_set_deterministic; 1.3 -> 2.2 us per step at configs[1]): the slice sums go to a small scratch and the last
+// block of column x to finish - an integer ticket per column - adds them in a fixed order: same inputs, same bits.
+#define SCG_RED_SLICES 96
+__global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const float *__restrict__ partial, float *red,
+                                                unsigned int *tickets, float *__restrict__ dW) {
+    __shared__ bool last;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = gridDim.y;
-    int p = blockIdx.y;
-    for (; p + 3 * gy < n_partials; p += 4 * gy) {
-        s0 += partial[(size_t)p * n + j];
-        s1 += partial[(size_t)(p + gy) * n + j];
-        s2 += partial[(size_t)(p + 2 * gy) * n + j];
-        s3 += partial[(size_t)(p + 3 * gy) * n + j];
+    float mine = 0.f;
+    if (j < n) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = blockIdx.y;
+        for (; p + 3 * gy < n_partials; p += 4 * gy) {
+            s0 += partial[(size_t)p * n + j];
+            s1 += partial[(size_t)(p + gy) * n + j];
+            s2 += partial[(size_t)(p + 2 * gy) * n + j];
+            s3 += partial[(size_t)(p + 3 * gy) * n + j];
+        }
+        for (; p < n_partials; p += gy) s0 += partial[(size_t)p * n + j];
+        mine = (s0 + s1) + (s2 + s3);
     }
-    for (; p < n_partials; p += gy) s0 += partial[(size_t)p * n + j];
-    atomicAdd(dW + j, (s0 + s1) + (s2 + s3));
+    if (!tickets) {                              // fast mode: one atomic per address per slice (order not fixed)
+        if (j < n) atomicAdd(dW + j, mine);
+        return;
+    }
+    if (j < n) red[(size_t)blockIdx.y * n + j] = mine;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(tickets + blockIdx.x, 1u);
+        last = (t == (unsigned int)gy - 1u);
+        if (last) tickets[blockIdx.x] = 0u;      // ready for the next reduction
+    }
+    __syncthreads();
+    if (last && j < n) {
+        __threadfence();
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;     // fixed association: four interleaved chains, then a fixed tree
+        int y = 0;
+        for (; y + 3 < gy; y += 4) {
+            t0 += __ldcg(red + (size_t)y * n + j);
+            t1 += __ldcg(red + (size_t)(y + 1) * n + j);
+            t2 += __ldcg(red + (size_t)(y + 2) * n + j);
+            t3 += __ldcg(red + (size_t)(y + 3) * n + j);
+        }
+        for (; y < gy; ++y) t0 += __ldcg(red + (size_t)y * n + j);
+        dW[j] += (t0 + t1) + (t2 + t3);
+    }
+}
+
+// slabs -> dW on stream st
+static int reduce_slabs(scg_ctx *ctx, int n_slabs, int n, float *dW, cudaStream_t st) {
+    const int nx_max = (ctx->K * SCG_A * ctx->F + 255) / 256;
+    if (ctx->deterministic && !ctx->d_red) {
+        SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_red, (size_t)SCG_RED_SLICES * ctx->K * SCG_A * ctx->F * sizeof(float)));
+        SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_tickets, (size_t)nx_max * sizeof(unsigned int)));
+        SCG_CUDA_OK(cudaMemsetAsync(ctx->d_tickets, 0, (size_t)nx_max * sizeof(unsigned int), st));
+    }
+    dim3 g((n + 255) / 256, std::min(n_slabs, SCG_RED_SLICES));
+    k_reduce<<<g, 256, 0, st>>>(n_slabs, n, ctx->d_partial, ctx->d_red, ctx->deterministic ? ctx->d_tickets : nullptr, dW);
+    SCG_LAUNCH_CHECK();
+    return 0;
 }
 
 __global__ void k_make_rec(int B, const float *__restrict__ x, const float *__restrict__ y,
@@ -598,11 +645,7 @@ int scg_launch_trace(scg_ctx *ctx, int B, const float *rec, float *trace, float 
         default: return SCG_ELIMIT;
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
-    int n = ctx->K * SCG_A * ctx->F;
-    dim3 g((n + 255) / 256, std::min(grid, 96));
-    k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
-    SCG_LAUNCH_CHECK();
-    return 0;
+    return reduce_slabs(ctx, grid, ctx->K * SCG_A * ctx->F, dW, st);
 }
 
 static int ensure_partials(scg_ctx *ctx, int n) {
@@ -699,10 +742,7 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
     if ((rc = scg_prof_push(ctx, 1, st, true))) return rc;
     if ((rc = scg_prof_push(ctx, 2, st, false))) return rc;
-    int n = k_used * SCG_A * ctx->F;
-    dim3 g((n + 255) / 256, std::min(grid, 96));
-    k_reduce<<<g, 256, 0, st>>>(grid, n, ctx->d_partial, dW);
-    SCG_LAUNCH_CHECK();
+    if ((rc = reduce_slabs(ctx, grid, k_used * SCG_A * ctx->F, dW, st))) return rc;
     return scg_prof_push(ctx, 2, st, true);
 }
 
@@ -721,10 +761,18 @@ extern "C" int scg_ctx_create(int order, int K, scg_ctx_t **out) {
     return 0;
 }
 
+extern "C" int scg_ctx_set_deterministic(scg_ctx_t *c, int on) {
+    if (!c) return SCG_EINVAL;
+    c->deterministic = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
     if (!c) return 0;
     if (c->d_partial) cudaFree(c->d_partial);
     if (c->d_rec) cudaFree(c->d_rec);
+    if (c->d_red) cudaFree(c->d_red);
+    if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->host_ev) cudaEventDestroy(c->host_ev);
     for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
     free(c->prof_ev);
