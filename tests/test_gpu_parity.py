@@ -303,11 +303,13 @@ def _paired_agents(scg, torch, B, order, K, name, seed, **kw):
     return oag, gag
 
 
-def test_agent_step_matches_oracle_one_step(scg, torch):
+@pytest.mark.parametrize("cull", [True, False])
+def test_agent_step_matches_oracle_one_step(scg, torch, cull):
     """One fused step from identical state and weights, with two active options so termination,
-    option reward, example recording, reset and re-selection all fire."""
+    option reward, example recording, reset and re-selection all fire.  cull: broad-phase grid or every edge - both
+    must give the oracle's bits."""
     B, K = 6000, 4
-    oag, gag = _paired_agents(scg, torch, B, 3, K, "easy", 2, sync_interval=3, option_timeout=3, epsilon=0.2)
+    oag, gag = _paired_agents(scg, torch, B, 3, K, "easy", 2, sync_interval=3, option_timeout=3, epsilon=0.2, cull=cull)
     theta = np.zeros((K, 6), dtype=np.float32)
     theta[0] = [-1.0, 2.0, 0.0, 0.0, 0.0, 0.0]       # x >= 0.5
     theta[1] = [-0.6, 0.0, 2.0, 0.0, 0.0, 0.0]       # y >= 0.3
