@@ -47,6 +47,7 @@ extern "C" {
 #define SCG_EINVAL (-1)   /* bad argument */
 #define SCG_ENOMEM (-2)   /* host allocation failed */
 #define SCG_ELIMIT (-3)   /* map / order / K exceeds a compiled-in limit */
+#define SCG_EPEER (-4)    /* a peer rank did not arrive at a cross-GPU exchange within the timeout (sticky) */
 
 typedef struct scg_map scg_map_t; /* opaque: edge table + broad-phase grid, host and device copies */
 typedef struct scg_ctx scg_ctx_t; /* opaque: device scratch for the Sarsa(lambda) reduction */
@@ -189,7 +190,11 @@ int scg_xchg_handle(scg_xchg_t *x, void *handle_out /* HOST */);
 int scg_xchg_connect(scg_xchg_t *x, const void *all_handles /* HOST [world][handle_bytes] */);
 int scg_xchg_local_ptr(scg_xchg_t *x, void **ptr_out);
 int scg_xchg_connect_ptrs(scg_xchg_t *x, void *const *peer_ptrs /* HOST [world] device pointers */);
+/* *timed_out != 0: some exchange gave up waiting for a peer.  The flag is sticky and lives in host-mapped memory (no
+ * device synchronisation to read it); from then on scg_xchg_sync and scg_agent_run return SCG_EPEER. */
 int scg_xchg_status(scg_xchg_t *x, int *timed_out);
+/* how long an exchange waits for its peers before giving up (default 30 s) */
+int scg_xchg_set_timeout(scg_xchg_t *x, double seconds);
 /* dW (reduced over this rank's envs) and cnt -> summed over ranks -> W, Wt updated; dW and cnt zeroed.
  * nsucc_local [K] (optional): this rank's option success counters; nsucc_global [K] (optional) receives their sum
  * over ranks, identical on every rank, so the controller needs no collective of its own.

@@ -117,7 +117,12 @@ class SkillChainAgent:
         return out.astype(np.int32)
 
     # -- one lock-step agent step -------------------------------------------------------------
-    def step(self):
+    def step(self, follow=None):
+        """One lock-step agent step.  `follow` (tests only) = dict(action=int32 (B,), option=int32 (B,)): the action and
+        option every env holds AFTER this step in another implementation's run of the same step.  The oracle still
+        computes its own choices (returned as own_a2 / own_action / own_option, with the Q rows they were taken
+        from) but continues with the followed ones, so two implementations can be compared over many steps without
+        argmax near-ties (which legitimately differ between fp32 summation orders) sending the trajectories apart."""
         cfg, env, opts = self.cfg, self.env, self.options
         t = self.t
         B = cfg.batch
@@ -135,7 +140,11 @@ class SkillChainAgent:
         ep_timeout = (self.ep_steps >= cfg.max_episode_steps) & ~env_done
         term = env_done | hit | (self.t_opt >= cfg.option_timeout) | left | ep_timeout
         r = (r_env + np.where(hit & ~env_done, f32(cfg.option_bonus), f32(0.0))).astype(np.float32)
-        a2 = opts.act(s2, o, step=t, stream=STREAM_ACTION)
+        Q2 = opts.q(s2, o)
+        a2 = epsilon_greedy(Q2, opts.epsilon, opts.seed, opts.env_ids, t, STREAM_ACTION)
+        own_a2 = a2
+        if follow is not None:      # where the option terminated a2 does not enter the update (done = term)
+            a2 = np.where(term, a2, np.asarray(follow["action"], dtype=np.int32)).astype(np.int32)
         delta = opts.update(s, a, r, s2, a2, term, o)
         self.last_delta = delta
         self.ep_return += r_env
@@ -159,22 +168,34 @@ class SkillChainAgent:
             self.ep_steps[reset] = 0
         s_next = env.state
         a_next, o_next = a2.copy(), o.copy()
+        own_action, own_o, Qsel = own_a2.copy(), o.copy(), Q2
         if term.any():
             bits_next = self.initiation_bits(s_next)
             o_sel = self.choose_option(bits_next)
             o_next = np.where(term, o_sel, o).astype(np.int32)
-            Q = opts.q(s_next, o_next)
-            a_sel = epsilon_greedy(Q, opts.epsilon, opts.seed, opts.env_ids, t, STREAM_RESELECT)
+            if follow is not None:  # evaluate the first action under the followed option
+                own_o = o_next
+                o_next = np.where(term, np.asarray(follow["option"], dtype=np.int32), o).astype(np.int32)
+            Qn = opts.q(s_next, o_next)
+            a_sel = epsilon_greedy(Qn, opts.epsilon, opts.seed, opts.env_ids, t, STREAM_RESELECT)
             a_next = np.where(term, a_sel, a2).astype(np.int32)
+            own_action = np.where(term, a_sel, own_a2).astype(np.int32)
+            Qsel = np.where(term[:, None], Qn, Q2)
             self.t_opt[term] = 0
             self.start_xy[term] = s_next[term, :2]
+        extra = {}
+        if follow is not None:
+            # own_action / own_option: what the oracle would have chosen itself; Qsel: the Q row each own_action was
+            # the eps-greedy choice from (under the followed option where the option was re-selected)
+            extra = dict(own_action=own_action, own_option=own_o, Qsel=Qsel)
+            a_next = np.asarray(follow["action"], dtype=np.int32).copy()
         self.option, self.action = o_next, a_next
         opts.tick()
         self.t += 1
         if self.t % cfg.sync_interval == 0:
             opts.apply()
         return dict(state=s_next.copy(), reward=r, env_done=env_done, term=term, hit=hit, delta=delta,
-                    option=o_next.copy(), action=a_next.copy())
+                    option=o_next.copy(), action=a_next.copy(), **extra)
 
     # -- low-rate controller ------------------------------------------------------------------
     def examples(self, k):

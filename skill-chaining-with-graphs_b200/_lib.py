@@ -84,6 +84,7 @@ _SIGS = {
     "scg_xchg_local_ptr": (C.c_int, [_P, C.POINTER(_P)]),
     "scg_xchg_connect_ptrs": (C.c_int, [_P, _P]),
     "scg_xchg_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "scg_xchg_set_timeout": (C.c_int, [_P, C.c_double]),
     "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
     "scg_profile_begin": (C.c_int, [_P, C.c_int, C.c_int]),

@@ -13,6 +13,10 @@
 // a couple of NVLink round trips.  CTA c only ever waits for CTA c of the peers, which signals before it waits,
 // so no grid-wide barrier (and no co-residency assumption beyond one CTA) is needed.  The exchange buffer is
 // double-buffered by sequence parity: a rank can only be one sync ahead of the slowest reader.
+// A peer that does not show up within the timeout (default 30 s, scg_xchg_set_timeout) is FATAL for the exchange: the
+// waiting CTA raises a sticky flag in host-mapped memory and returns without applying or zeroing its slice; every later
+// scg_xchg_sync / scg_agent_run on this handle returns SCG_EPEER (the host reads the flag without a device sync), so a
+// stalled or dead rank can never silently de-synchronise the weight replicas.
 // Peer buffers are mapped with CUDA IPC (one process per GPU) or passed as plain pointers (one process, several
 // devices with peer access enabled - used by the two-device test).
 #include <stdlib.h>
@@ -35,6 +39,9 @@ struct scg_xchg {
     unsigned char *d_peer[XCHG_MAX_WORLD];       // mapped bases of every rank's block (own entry = d_local)
     bool ipc_opened[XCHG_MAX_WORLD];
     unsigned int *d_ticket;                      // last-CTA-done counter
+    volatile uint32_t *h_status;                 // host-mapped sticky "a peer timed out" flag (written by the kernel)
+    uint32_t *d_status;                          // its device alias
+    long long timeout_cycles;                    // peer wait limit in SM clock cycles
 };
 
 struct SyncArgs {
@@ -46,6 +53,8 @@ struct SyncArgs {
     const int *nsucc_local;   // [K] this rank's option success counters (may be NULL)
     int *nsucc_global;        // [K] out: their sum over ranks as of this sync (may be NULL)
     unsigned int *ticket;
+    uint32_t *status;         // host-mapped sticky timeout flag
+    long long timeout_cycles;
     size_t flag_bytes;
     unsigned char *peer[XCHG_MAX_WORLD];
 };
@@ -68,6 +77,8 @@ template <int N1>
 __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ SyncArgs a) {
     constexpr int F = N1 * N1 * N1 * N1;
     __shared__ int s_cnt[SCG_MAX_OPTIONS];
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
     const int c = blockIdx.x, i = threadIdx.x, j = c * XCHG_SLICE + i;
     const int buf = a.seq & 1;
     unsigned char *mine = a.peer[a.rank];
@@ -80,15 +91,6 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
         xrow[XCHG_SLICE + 16 + i] = __int_as_float(a.nsucc_local ? a.nsucc_local[i] : 0);
     }
     __syncthreads();
-    // the last CTA to have read cnt zeroes it for the next window
-    if (i == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(a.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            for (int k = 0; k < a.K; ++k) a.cnt[k] = 0;
-            *a.ticket = 0u;
-        }
-    }
     // 2. signal every peer, 3. wait for every peer (one thread per peer)
     if (i < a.world && i != a.rank) {
         __threadfence_system();
@@ -97,13 +99,16 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
         const uint32_t *lf = reinterpret_cast<const uint32_t *>(mine) + (size_t)i * a.slices + c;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(lf) - a.seq) < 0) {
-            if (clock64() - t0 > 4000000000ll) {      // ~2 s: a peer died; record it instead of hanging the GPU
-                reinterpret_cast<uint32_t *>(mine)[(size_t)a.world * a.slices] = 1u;
+            if (clock64() - t0 > a.timeout_cycles) {  // the peer never came: fatal for this exchange (see the header)
+                *reinterpret_cast<volatile uint32_t *>(a.status) = 1u;
+                __threadfence_system();
+                s_timeout = 1;
                 break;
             }
         }
     }
     __syncthreads();
+    if (s_timeout) return;                            // no apply, dW of this slice kept
     // 4. sum in rank order, apply
     float v = 0.f;
     for (int r = 0; r < a.world; ++r) {
@@ -141,6 +146,15 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
         a.Wt[((size_t)f * a.K + k) * SCG_WT_STRIDE + act] = w;
         a.dW[j] = 0.f;
     }
+    // the last CTA to finish zeroes cnt for the next window (every CTA read it when it published)
+    if (i == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            for (int k = 0; k < a.K; ++k) a.cnt[k] = 0;
+            *a.ticket = 0u;
+        }
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -158,10 +172,20 @@ extern "C" int scg_xchg_create(scg_ctx_t *ctx, int rank, int world, scg_xchg_t *
     if (e == cudaSuccess) e = cudaMemset(x->d_local, 0, x->bytes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&x->d_ticket, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(x->d_ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&x->h_status, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *x->h_status = 0u;
+        e = cudaHostGetDevicePointer((void **)&x->d_status, (void *)x->h_status, 0);
+    }
+    int dev = 0, khz = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    x->timeout_cycles = 30ll * 1000ll * (long long)(khz > 0 ? khz : 2000000);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (x->d_local) cudaFree(x->d_local);
         if (x->d_ticket) cudaFree(x->d_ticket);
+        if (x->h_status) cudaFreeHost((void *)x->h_status);
         free(x);
         return (int)e;
     }
@@ -176,7 +200,17 @@ extern "C" int scg_xchg_destroy(scg_xchg_t *x) {
         if (x->ipc_opened[r]) cudaIpcCloseMemHandle(x->d_peer[r]);
     if (x->d_local) cudaFree(x->d_local);
     if (x->d_ticket) cudaFree(x->d_ticket);
+    if (x->h_status) cudaFreeHost((void *)x->h_status);
     free(x);
+    return 0;
+}
+
+extern "C" int scg_xchg_set_timeout(scg_xchg_t *x, double seconds) {
+    if (!x || !(seconds > 0.0)) return SCG_EINVAL;
+    int dev = 0, khz = 0;
+    SCG_CUDA_OK(cudaGetDevice(&dev));
+    SCG_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    x->timeout_cycles = (long long)(seconds * 1000.0 * (double)(khz > 0 ? khz : 2000000));
     return 0;
 }
 
@@ -223,10 +257,7 @@ extern "C" int scg_xchg_connect_ptrs(scg_xchg_t *x, void *const *peer_ptrs) {
 
 extern "C" int scg_xchg_status(scg_xchg_t *x, int *timed_out) {
     if (!x || !timed_out) return SCG_EINVAL;
-    uint32_t v = 0;
-    SCG_CUDA_OK(cudaMemcpy(&v, x->d_local + ((size_t)x->world * x->slices) * sizeof(uint32_t), sizeof(v),
-                           cudaMemcpyDeviceToHost));
-    *timed_out = (int)v;
+    *timed_out = (int)*x->h_status;     // host-mapped: no device synchronisation (sticky once set)
     return 0;
 }
 
@@ -237,11 +268,13 @@ extern "C" int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *W
     if (K != x->K || K * SCG_A * scg_pow4(order + 1) != x->n) return SCG_EINVAL;
     for (int r = 0; r < x->world; ++r)
         if (!x->d_peer[r]) return SCG_EINVAL;   // not connected
+    if (*x->h_status) return SCG_EPEER;         // an earlier exchange timed out: the replicas are no longer in step
     SyncArgs a;
     a.n = x->n; a.K = K; a.slices = x->slices; a.rank = x->rank; a.world = x->world;
     a.seq = ++x->seq;
     a.alpha = alpha; a.steps = (float)std::max(window_steps, 1);
     a.W = W; a.Wt = Wt; a.dW = dW; a.cnt = cnt; a.ticket = x->d_ticket;
+    a.status = x->d_status; a.timeout_cycles = x->timeout_cycles;
     a.nsucc_local = nsucc_local; a.nsucc_global = nsucc_global;
     a.flag_bytes = x->flag_bytes;
     for (int r = 0; r < XCHG_MAX_WORLD; ++r) a.peer[r] = r < x->world ? x->d_peer[r] : nullptr;

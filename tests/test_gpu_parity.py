@@ -16,10 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def rel_err(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+from oracle.compare import assert_close  # noqa: E402  element-wise |a-b| <= rtol*|b| + rtol*typical(b)
 
 
 @pytest.fixture(scope="module")
@@ -189,7 +186,7 @@ def test_q_select_td_match_oracle(scg, torch, order, K):
     gset.set_weights(W)
     oQ = oset.q(S, opt)
     gQ = gset.q(S, opt).cpu().numpy()
-    assert rel_err(gQ, oQ) < RTOL
+    assert_close(gQ, oQ)
     # selection: identical uniforms; feed the ORACLE's Q so argmax cannot flip on rounding
     oa = oracle.option.epsilon_greedy(oQ, oset.epsilon, 5, oset.env_ids, 17, 0)
     ga = gset.select(torch.as_tensor(oQ).cuda(), 17, 0).cpu().numpy()
@@ -198,7 +195,7 @@ def test_q_select_td_match_oracle(scg, torch, order, K):
     done = rng.random(B) < 0.2
     od = oset.td_error(S, A, r, S2, A2, done, opt)
     gd = gset.td_error(S, A, r, S2, A2, done, opt).cpu().numpy()
-    assert rel_err(gd, od) < RTOL
+    assert_close(gd, od)
 
 
 # ---- K3 ------------------------------------------------------------------------------------------
@@ -225,17 +222,17 @@ def test_sarsa_updates_match_oracle(scg, torch, order, K):
         od = oset.update(S, A, r, S2, A2, done, opt, mask=mask)
         gd = gset.update(S, A, r, S2, A2, done, opt, mask=mask).cpu().numpy()
         oset.tick(); gset.tick()
-        assert rel_err(gd, od) < RTOL, f"TD error, update {it}"
-        assert rel_err(gset.trace.cpu().numpy(), oset.trace) < RTOL, f"trace, update {it}"
+        assert_close(gd, od, what=f"TD error, update {it}")
+        assert_close(gset.trace.cpu().numpy(), oset.trace, what=f"trace, update {it}")
         assert np.array_equal(gset.cnt.cpu().numpy(), oset.cnt), f"cnt, update {it}"
-        assert rel_err(gset.dW.cpu().numpy(), oset.dW) < RTOL, f"dW, update {it}"
+        assert_close(gset.dW.cpu().numpy(), oset.dW, what=f"dW, update {it}")
         if it % 2 == 1:
             oset.apply(); gset.apply()
-            assert rel_err(gset.W.cpu().numpy(), oset.W) < RTOL, f"W after apply, update {it}"
+            assert_close(gset.W.cpu().numpy(), oset.W, what=f"W after apply, update {it}")
             assert float(gset.dW.abs().max()) == 0.0 and int(gset.cnt.sum()) == 0
     S, _ = _states(omap, B, seed=99)
     opt = rng.integers(0, K, B).astype(np.int32)
-    assert rel_err(gset.q(S, opt).cpu().numpy(), oset.q(S, opt)) < RTOL
+    assert_close(gset.q(S, opt).cpu().numpy(), oset.q(S, opt))
 
 
 def test_sarsa_b1_classical(scg, torch):
@@ -254,8 +251,8 @@ def test_sarsa_b1_classical(scg, torch):
         od = oset.update(S, A, r, S2, A2, done, o)
         gd = gset.update(S, A, r, S2, A2, done, o).cpu().numpy()
         oset.tick(); gset.tick(); oset.apply(); gset.apply()
-        assert rel_err(gd, od) < RTOL
-        assert rel_err(gset.W.cpu().numpy(), oset.W) < RTOL
+        assert_close(gd, od)
+        assert_close(gset.W.cpu().numpy(), oset.W)
     assert float(gset.trace.abs().max()) == 0.0      # done on the last update zeroed the trace
 
 
@@ -269,18 +266,18 @@ def test_classifier_eval_grad_fit_match_oracle(scg, torch):
     oset.theta[:] = theta
     gset.theta.copy_(torch.as_tensor(theta))
     S = rng.random((B, 4)).astype(np.float32)
-    assert rel_err(gset.initiation_prob(S).cpu().numpy(), oset.initiation_prob(S)) < RTOL
+    assert_close(gset.initiation_prob(S).cpu().numpy(), oset.initiation_prob(S))
     X = rng.random((1000, 2)).astype(np.float32)
     y = ((X[:, 0] - 0.6) ** 2 + (X[:, 1] - 0.4) ** 2 < 0.08).astype(np.uint8)
-    assert rel_err(gset.clf_grad(2, X, y).cpu().numpy(), oset.clf_grad(2, X, y)) < RTOL
+    assert_close(gset.clf_grad(2, X, y).cpu().numpy(), oset.clf_grad(2, X, y))
     oset.theta[1] = 0
     gset.theta[1].zero_()
     ot = oset.fit_initiation(1, X, y, steps=150, lr=2.0)
     gt = gset.fit_initiation(1, X, y, steps=150, lr=2.0).cpu().numpy()
-    assert rel_err(gt, ot) < RTOL
+    assert_close(gt, ot)
     op = oset.initiation_prob(np.concatenate([X, np.zeros_like(X)], axis=1))[:, 1]
     gp = gset.initiation_prob(np.concatenate([X, np.zeros_like(X)], axis=1))[:, 1].cpu().numpy()
-    assert rel_err(gp, op) < RTOL
+    assert_close(gp, op)
 
 
 # ---- fused agent step ------------------------------------------------------------------------------
@@ -333,7 +330,7 @@ def test_agent_step_matches_oracle_one_step(scg, torch, cull):
     out = oag.step()
     gag.step()
     torch.cuda.synchronize()
-    assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+    assert_close(gag.delta.cpu().numpy(), out["delta"])
     assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
     assert np.array_equal(gag.option.cpu().numpy(), out["option"])
     # actions come from an argmax over Q: compare where the oracle's top-2 gap is not a rounding tie
@@ -349,8 +346,8 @@ def test_agent_step_matches_oracle_one_step(scg, torch, cull):
     assert np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
     assert np.array_equal(gag.ex_count.cpu().numpy(), oag.ex_count)
     assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
-    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
-    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL
+    assert_close(gag.options.dW.cpu().numpy(), oag.options.dW)
+    assert_close(gag.options.trace.cpu().numpy(), oag.options.trace)
     assert out["term"].sum() > 100 and out["hit"].sum() > 10
     for k in range(K):                                # same example multiset per option
         n = int(oag.ex_count[k])
@@ -360,18 +357,108 @@ def test_agent_step_matches_oracle_one_step(scg, torch, cull):
         assert np.array_equal(ox[np.lexsort(ox.T)], gx[np.lexsort(gx.T)])
 
 
-def test_agent_multi_step_statistics(scg, torch):
-    """Several fused steps including a sync: weights stay close to the oracle's (trajectories can
-    differ only through argmax near-ties, which the tiny weights make rare)."""
-    B = 3000
-    oag, gag = _paired_agents(scg, torch, B, 3, 2, "easy", 4, sync_interval=2, epsilon=0.0, alpha=1e-4)
-    for _ in range(4):
-        oag.step()
-        gag.step()
+def _set_gpu_options(gag, torch, theta, n_active, graph=False):
+    """GPU twin of oracle_replay.activate."""
+    gag.options.theta.copy_(torch.as_tensor(theta))
+    gag.n_active = n_active
+    gag.active_mask = (1 << n_active) - 1
+    gag.parents_host[:] = 0
+    gag.parents_host[0] = 1 << 31
+    for n in range(1, min(n_active + 1, gag.options.K)):
+        gag.parents_host[n] = (((1 << n) - 1) | (1 << 31)) if graph else (1 << (n - 1))
+    gag._push_parents()
+
+
+def _gpu_run_window(gag, torch, n):
+    """n free-running GPU steps in ONE call (one multi-step launch when the window allows); returns what the step
+    kernel recorded: pre-step states (n, B, 4), TD errors (n, B), and the (action, option) each env held before every
+    step plus after the last one (n + 1, B)."""
+    wl0 = int(gag._struct.win_len)
+    assert wl0 + n <= gag.win_cap
+    gag.run(n)
     torch.cuda.synchronize()
-    same = (gag.state.cpu().numpy() == oag.env.state).all(axis=1).mean()
-    assert same > 0.98
-    assert rel_err(gag.options.W.cpu().numpy(), oag.options.W) < 5e-3
+    rec = gag.win_rec[wl0:wl0 + n].cpu().numpy()                      # (n, B, 8)
+    meta = rec[:, :, 5].copy().view(np.uint32)
+    acts = np.concatenate([(meta & 7).astype(np.int32), gag.action.cpu().numpy()[None]], axis=0)
+    opts = np.concatenate([((meta >> 8) & 0xFF).astype(np.int32), gag.option.cpu().numpy()[None]], axis=0)
+    return rec[:, :, :4].copy(), rec[:, :, 4].copy(), acts, opts, ((meta >> 16) & 1).astype(bool)
+
+
+def _check_choices(out, action, option, what):
+    """The oracle's own choices against the followed (GPU) ones: options must agree, actions may differ only at a
+    near-tie of the oracle's Q row (the two sides sum F products in different orders)."""
+    assert np.array_equal(out["own_option"], option), f"{what}: option choice differs"
+    dis = out["own_action"] != action
+    if dis.any():
+        Q = out["Qsel"][dis].astype(np.float64)
+        gap = Q.max(axis=1) - Q[np.arange(len(Q)), action[dis]]
+        assert gap.max() <= 1e-4 * max(1e-30, float(np.abs(out["Qsel"]).mean())), f"{what}: action differs without a Q tie"
+    return int(dis.sum())
+
+
+@pytest.mark.parametrize("order,K,n_active,name,B,launch", [
+    (3, 4, 2, "easy", 3000, "window"),        # weights staged in shared memory (bulk copy), one launch per window
+    (3, 4, 2, "easy", 3000, "step"),          # one launch per step: carried Q across launches
+    (3, 6, 3, "hard", 2000, "window"),        # staged, gathered (k_stage < K)
+    (5, 8, 2, "hard", 500, "window"),         # order 5: one 512-thread CTA per SM, weights staged
+    (5, 8, 6, "hard", 500, "window"),         # order 5 with 7 options in use: weights through the global read-only path
+    (5, 8, 6, "hard", 500, "step"),
+])
+def test_fused_pipeline_multi_window_tight(scg, torch, order, K, n_active, name, B, launch):
+    """The whole fused pipeline across weight applies, at the stated bar: k_agent_step -> k_window -> k_reduce ->
+    k_apply -> next window's Q from the refreshed packed weights.  13 steps, alpha > 0, a sync every 4 steps.  The GPU
+    runs free; the oracle follows its choices.  Per step: pre-step states bit-identical, TD errors element-wise 1e-4.
+    launch == "window": one multi-step launch per window and the sync inside scg_agent_run (the bench path): W
+    element-wise after every apply.  launch == "step": one launch per step (Q carried across launches), syncs driven by
+    hand so that dW, cnt and the traces are also compared before every apply."""
+    from oracle_replay import activate, default_theta
+    manual = launch == "step"
+    kw = dict(sync_interval=1000 if manual else 4, option_timeout=5, epsilon=0.1, alpha=5e-3, max_episode_steps=9)
+    oag, gag = _paired_agents(scg, torch, B, order, K, name, 13, window=4, **kw)
+    theta = default_theta(K)
+    activate(oag, theta, n_active)
+    _set_gpu_options(gag, torch, theta, n_active)
+    opt0 = np.random.default_rng(3).integers(0, n_active + 1, B).astype(np.int32)
+    oag.option = opt0.copy()
+    gag.option.copy_(torch.as_tensor(opt0))
+    W0 = oag.options.W.copy()
+    n_dis, n_term = 0, 0
+    for w in range(4):
+        n = 4 if w < 3 else 1
+        if not manual:
+            pre, dl, acts, opts, term = _gpu_run_window(gag, torch, n)
+        else:
+            parts = [_gpu_run_window(gag, torch, 1) for _ in range(n)]
+            pre = np.concatenate([p[0] for p in parts]); dl = np.concatenate([p[1] for p in parts])
+            acts = np.concatenate([p[2][:1] for p in parts] + [parts[-1][2][1:]])
+            opts = np.concatenate([p[3][:1] for p in parts] + [parts[-1][3][1:]])
+            term = np.concatenate([p[4] for p in parts])
+        for t in range(n):
+            what = f"window {w} step {t}"
+            assert np.array_equal(oag.env.state.view(np.uint32), pre[t].view(np.uint32)), f"{what}: pre-step state"
+            assert np.array_equal(oag.action, acts[t]) and np.array_equal(oag.option, opts[t])
+            out = oag.step(follow=dict(action=acts[t + 1], option=opts[t + 1]))
+            assert np.array_equal(out["term"], term[t]), f"{what}: termination flags"
+            assert_close(dl[t], out["delta"], what=f"{what}: TD error")
+            n_dis += _check_choices(out, acts[t + 1], opts[t + 1], what)
+            n_term += int(out["term"].sum())
+        assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), oag.env.state.view(np.uint32))
+        if w < 3:
+            if manual:
+                assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+                assert_close(gag.options.dW.cpu().numpy(), oag.options.dW, what=f"dW of window {w}")
+                assert_close(gag.options.trace.cpu().numpy(), oag.options.trace, what=f"traces after window {w}")
+                gag.sync()
+                oag.options.apply()
+            assert_close(gag.options.W.cpu().numpy(), oag.options.W, what=f"W after apply {w}")
+            assert_close(gag.options.W.cpu().numpy() - W0, oag.options.W - W0, what=f"W - W0 after apply {w}")
+            assert np.abs(oag.options.W - W0).max() > 1e-3       # the applies really moved the weights
+    assert n_term > B // 2 and n_dis <= B // 50
+    assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+    assert_close(gag.options.trace.cpu().numpy(), oag.options.trace, what="traces")
+    assert_close(gag.options.dW.cpu().numpy(), oag.options.dW, what="dW of the open window")
+    assert np.array_equal(gag.t_opt.cpu().numpy(), oag.t_opt) and np.array_equal(gag.ep_steps.cpu().numpy(), oag.ep_steps)
+    assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success) and np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
 
 
 def test_agent_run_and_manage_promotes_option(scg, torch):
@@ -433,11 +520,11 @@ def test_windowed_sweep_equals_oracle_dense_traces(scg, torch, order, K, window,
         gag.option.copy_(torch.as_tensor(out["option"]))
         gag.invalidate()
         assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
-        assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+        assert_close(gag.delta.cpu().numpy(), out["delta"])
     assert out is not None and int(gag._struct.win_len) == (n_steps % window)
     assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
-    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL      # property flushes the window
-    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
+    assert_close(gag.options.trace.cpu().numpy(), oag.options.trace)      # property flushes the window
+    assert_close(gag.options.dW.cpu().numpy(), oag.options.dW)
     assert int(gag._struct.win_len) == 0
     assert oag.n_fail.sum() + oag.n_success.sum() > B // 4                          # terminations inside the window
 
@@ -502,7 +589,7 @@ def test_golden_features_q(scg, torch, order):
     assert np.abs(scg.FourierBasis(order).features(g["state"]).cpu().numpy() - g["phi"]).max() < 2e-5
     s = scg.OptionSet(g["W"].shape[0], order, len(g["state"]))
     s.set_weights(g["W"])
-    assert rel_err(s.q(g["state"], g["option"]).cpu().numpy(), g["Q"]) < RTOL
+    assert_close(s.q(g["state"], g["option"]).cpu().numpy(), g["Q"])
 
 
 def test_golden_sarsa_and_classifier(scg, torch):
@@ -513,21 +600,22 @@ def test_golden_sarsa_and_classifier(scg, torch):
     for it in range(6):
         d = s.update(g["S"][it], g["A"][it], g["r"][it], g["S2"][it], g["A2"][it], g["done"][it], g["option"][it])
         s.tick()
-        assert rel_err(d.cpu().numpy(), g["delta"][it]) < RTOL
+        assert_close(d.cpu().numpy(), g["delta"][it])
         if it == 2:
-            assert rel_err(s.dW.cpu().numpy(), g["dW3"]) < RTOL and np.array_equal(s.cnt.cpu().numpy(), g["cnt3"])
-            assert rel_err(s.trace.double().sum(dim=2).cpu().numpy(), g["trace3_sum"]) < RTOL
+            assert_close(s.dW.cpu().numpy(), g["dW3"])
+            assert np.array_equal(s.cnt.cpu().numpy(), g["cnt3"])
+            assert_close(s.trace.double().sum(dim=2).cpu().numpy(), g["trace3_sum"])
             s.apply()
-            assert rel_err(s.W.cpu().numpy(), g["W3"]) < RTOL
-    assert rel_err(s.dW.cpu().numpy(), g["dW_end"]) < RTOL
-    assert rel_err(s.trace.double().sum(dim=2).cpu().numpy(), g["trace_end_sum"]) < RTOL
+            assert_close(s.W.cpu().numpy(), g["W3"])
+    assert_close(s.dW.cpu().numpy(), g["dW_end"])
+    assert_close(s.trace.double().sum(dim=2).cpu().numpy(), g["trace_end_sum"])
     c = np.load(os.path.join(GOLD, "classifier.npz"))
     k = scg.OptionSet(2, 1, 1)
     k.theta[0].copy_(torch.as_tensor(c["theta0"]))
-    assert rel_err(k.clf_grad(0, c["X"], c["y"]).cpu().numpy(), c["grad0"]) < RTOL
-    assert rel_err(k.fit_initiation(1, c["X"], c["y"], steps=100, lr=2.0).cpu().numpy(), c["theta1_fit"]) < RTOL
+    assert_close(k.clf_grad(0, c["X"], c["y"]).cpu().numpy(), c["grad0"])
+    assert_close(k.fit_initiation(1, c["X"], c["y"], steps=100, lr=2.0).cpu().numpy(), c["theta1_fit"])
     S4 = np.concatenate([c["X"], np.zeros_like(c["X"])], axis=1)
-    assert rel_err(k.initiation_prob(S4).cpu().numpy(), c["prob"]) < RTOL
+    assert_close(k.initiation_prob(S4).cpu().numpy(), c["prob"])
 
 
 def test_golden_agent_step(scg, torch):
@@ -548,13 +636,13 @@ def test_golden_agent_step(scg, torch):
     ag.step()
     torch.cuda.synchronize()
     assert np.array_equal(ag.state.cpu().numpy().view(np.uint32), g["next_state"].view(np.uint32))
-    assert rel_err(ag.delta.cpu().numpy(), g["delta"]) < RTOL
+    assert_close(ag.delta.cpu().numpy(), g["delta"])
     assert np.array_equal(ag.option.cpu().numpy(), g["next_option"])
     assert np.array_equal(ag.t_opt.cpu().numpy(), g["t_opt_after"])
     assert np.array_equal(ag.n_success.cpu().numpy(), g["n_success"]) and np.array_equal(ag.n_fail.cpu().numpy(), g["n_fail"])
     assert np.array_equal(ag.options.cnt.cpu().numpy(), g["cnt"])
-    assert rel_err(ag.options.dW.cpu().numpy(), g["dW"]) < RTOL
-    assert rel_err(ag.options.trace.double().sum(dim=2).cpu().numpy(), g["trace_sum"]) < RTOL
+    assert_close(ag.options.dW.cpu().numpy(), g["dW"])
+    assert_close(ag.options.trace.double().sum(dim=2).cpu().numpy(), g["trace_sum"])
 
 
 # ---- cross-GPU exchange kernel --------------------------------------------------------------------------
@@ -638,7 +726,7 @@ def test_xchg_two_devices_sum_and_identical_replicas(scg, torch):
             ora.W[:] = W
             ora.window_steps = 8
             ora.apply((dWs[0].astype(np.float64) + dWs[1]), cnts[0] + cnts[1])
-            assert rel_err(w0.numpy(), ora.W) < 1e-6
+            assert_close(w0.numpy(), ora.W, rtol=1e-6)
         for r in range(2):                   # next round: new deltas
             with torch.cuda.device(r):
                 assert float(sets[r]._dW.abs().max()) == 0.0 and int(sets[r].cnt.sum()) == 0
@@ -649,6 +737,114 @@ def test_xchg_two_devices_sum_and_identical_replicas(scg, torch):
         check(lib.scg_xchg_status(xs[r], C.byref(t)))
         assert t.value == 0
         lib.scg_xchg_destroy(xs[r])
+
+
+def _connect_ranks_one_process(lib, xs):
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check
+    ptrs = (C.c_void_p * len(xs))()
+    for r, x in enumerate(xs):
+        p = C.c_void_p()
+        check(lib.scg_xchg_local_ptr(x, C.byref(p)))
+        ptrs[r] = p
+    for x in xs:
+        check(lib.scg_xchg_connect_ptrs(x, ptrs))
+
+
+@pytest.mark.parametrize("world,order,K", [(2, 3, 4), (4, 5, 8), (3, 2, 3)])
+def test_xchg_ranks_on_one_device_sum_and_identical_replicas(scg, torch, world, order, K):
+    """The multi-rank exchange kernel on ONE GPU: `world` exchange contexts on cuda:0, one stream per rank, plain
+    device pointers as peer mappings.  Same code path as one process per GPU (publish, per-slice flags, rank-ordered
+    sum, apply); runs on the driver's single-GPU box."""
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check, ptr
+    lib = scg.load_library()
+    rng = np.random.default_rng(40 + world)
+    F = (order + 1) ** 4
+    W = (rng.standard_normal((K, 5, F)) * 0.1).astype(np.float32)
+    dWs = [rng.standard_normal((K, 5, F)).astype(np.float32) for _ in range(world)]
+    cnts = [rng.integers(0, 9, K).astype(np.int32) for _ in range(world)]
+    cnts[0][K - 1] = 0
+    for c in cnts[1:]:
+        c[K - 1] = 0                                         # an option nobody executed: its weights must not move
+    sets, xs, streams = [], [], [torch.cuda.Stream() for _ in range(world)]
+    for r in range(world):
+        o = scg.OptionSet(K, order, 4, alpha=0.05)
+        o.set_weights(W)
+        o._dW.copy_(torch.as_tensor(dWs[r]))
+        o.cnt.copy_(torch.as_tensor(cnts[r]))
+        x = C.c_void_p()
+        check(lib.scg_xchg_create(o.ctx, r, world, C.byref(x)))
+        sets.append(o); xs.append(x)
+    _connect_ranks_one_process(lib, xs)
+    nloc = [torch.arange(K, dtype=torch.int32, device="cuda") * (r + 1) for r in range(world)]
+    nglob = [torch.zeros(K, dtype=torch.int32, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    try:
+        for it in range(3):                                  # three syncs: double buffering and sequence flags
+            for r in range(world):
+                o = sets[r]
+                check(lib.scg_xchg_sync(xs[r], order, K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt), 0.05, 8,
+                                        ptr(nloc[r]), ptr(nglob[r]), C.c_void_p(streams[r].cuda_stream)))
+            torch.cuda.synchronize()
+            for r in range(1, world):
+                assert torch.equal(sets[r].W, sets[0].W) and torch.equal(sets[r].Wt, sets[0].Wt)   # bit-identical replicas
+                assert torch.equal(nglob[r], nglob[0])
+            assert nglob[0].cpu().tolist() == [k * world * (world + 1) // 2 for k in range(K)]
+            if it == 0:
+                ora = oracle.OptionSet(K, order, 4, alpha=0.05)
+                ora.W[:] = W
+                ora.window_steps = 8
+                ora.apply(sum(d.astype(np.float64) for d in dWs), sum(cnts))
+                assert_close(sets[0].W.cpu().numpy() - W, ora.W - W, what="summed update")
+                assert np.array_equal(sets[0].W.cpu().numpy()[K - 1], W[K - 1])
+            for r in range(world):
+                assert float(sets[r]._dW.abs().max()) == 0.0 and int(sets[r].cnt.sum()) == 0
+                sets[r]._dW.copy_(torch.as_tensor(dWs[r] * (it + 2)))
+                sets[r].cnt.copy_(torch.as_tensor(cnts[r]))
+            torch.cuda.synchronize()
+        for x in xs:
+            t = C.c_int(7)
+            check(lib.scg_xchg_status(x, C.byref(t)))
+            assert t.value == 0
+    finally:
+        for x in xs:
+            lib.scg_xchg_destroy(x)
+
+
+def test_xchg_missing_peer_is_fatal_not_silent(scg, torch):
+    """A rank whose peer never arrives gives up after the timeout WITHOUT applying or zeroing anything, and every later
+    exchange on that handle fails with SCG_EPEER (a silent partial apply would de-synchronise the replicas)."""
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check, ptr, current_stream
+    lib = scg.load_library()
+    K, order = 2, 2
+    sets, xs = [], []
+    for r in range(2):
+        o = scg.OptionSet(K, order, 4, alpha=0.05)
+        o.set_weights(np.full((K, 5, 81), 0.25, dtype=np.float32))
+        o._dW.fill_(1.0)
+        o.cnt.fill_(3)
+        x = C.c_void_p()
+        check(lib.scg_xchg_create(o.ctx, r, 2, C.byref(x)))
+        sets.append(o); xs.append(x)
+    _connect_ranks_one_process(lib, xs)
+    try:
+        check(lib.scg_xchg_set_timeout(xs[0], 0.05))
+        o = sets[0]
+        check(lib.scg_xchg_sync(xs[0], order, K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt), 0.05, 8, None, None,
+                                current_stream()))          # rank 1 never calls
+        torch.cuda.synchronize()
+        t = C.c_int(0)
+        check(lib.scg_xchg_status(xs[0], C.byref(t)))
+        assert t.value == 1
+        assert float((o.W - 0.25).abs().max()) == 0.0 and float((o._dW - 1.0).abs().max()) == 0.0   # nothing applied
+        rc = lib.scg_xchg_sync(xs[0], order, K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt), 0.05, 8, None, None,
+                               current_stream())
+        assert rc == -4 and b"peer" in lib.scg_error_string(rc)
+    finally:
+        for x in xs:
+            lib.scg_xchg_destroy(x)
 
 
 # ---- BASELINE.json full sizes: size-independent properties ----------------------------------------------
@@ -741,6 +937,87 @@ def test_full_size_step_properties(scg, torch):
     assert np.array_equal(ns[idx].view(np.uint32), ons.view(np.uint32)) and np.array_equal(r[idx], orr)
 
 
+def _full_size_vs_oracle(scg, torch, name, B, order, K, n_active, T, shard, graph=False):
+    """One T-step window of the free-running GPU agent at a BASELINE.json batch size, one multi-step launch, then the
+    sweep and the apply - against the oracle replaying the same steps in follow mode, sharded over host processes."""
+    import os
+    from oracle_replay import default_theta, replay_sharded
+    omap = oracle.PinballMap.from_name(name)
+    gmap = scg.PinballMap.from_name(name)
+    S = omap.sample_free_states(np.random.default_rng(77), B)
+    hp = dict(map=name, order=order, max_options=K, seed=21, sync_interval=1000, epsilon=0.05, alpha=1e-3,
+              option_timeout=6, max_episode_steps=2000, graph=graph)
+    gag = scg.SkillChainAgent(scg.AgentConfig(batch=B, window=T, **hp), gmap, initial_states=S)
+    W = (np.random.default_rng(5).standard_normal(tuple(gag.options.W.shape)) * 0.1).astype(np.float32)
+    gag.options.set_weights(W)
+    theta = default_theta(K)
+    _set_gpu_options(gag, torch, theta, n_active, graph)
+    opt0 = (np.arange(B) % (n_active + 1)).astype(np.int32)
+    gag.option.copy_(torch.as_tensor(opt0))
+    A0 = gag.action.cpu().numpy().copy()
+    pre, dl, acts, opts, term = _gpu_run_window(gag, torch, T)
+    assert int(gag._struct.win_len) == 0                           # the full window was swept
+    g_dW = gag.options.dW.double().cpu().numpy()
+    g_cnt = gag.options.cnt.cpu().numpy().astype(np.int64)
+    g_rows = gag.options._trace.double().sum(dim=2).cpu().numpy()
+    probe = np.random.default_rng(1).choice(B, 64, replace=False)   # a few envs' traces in full
+    g_probe = gag.options._trace[torch.as_tensor(probe).cuda()].cpu().numpy()
+    gag.cfg.sync_interval = T
+    gag.sync()
+    g_W = gag.options.W.cpu().numpy()
+    jobs = []
+    for lo in range(0, B, shard):
+        hi = min(B, lo + shard)
+        jobs.append(dict(cfg=dict(batch=hi - lo, env_offset=lo, **hp), S0=S[lo:hi], W=W, theta=theta, n_active=n_active,
+                         graph=graph, actions=acts[:, lo:hi], options=opts[:, lo:hi], want_trace=False,
+                         probe=sorted(int(i - lo) for i in probe if lo <= i < hi)))
+    assert np.array_equal(acts[0], A0) and np.array_equal(opts[0], opt0)
+    res = replay_sharded(jobs, procs=min(32, len(os.sched_getaffinity(0))))
+    o_pre = np.concatenate([r["pre_state"] for r in res], axis=1)
+    assert np.array_equal(o_pre.view(np.uint32), pre.view(np.uint32)), "pre-step states of the window"
+    assert np.array_equal(np.concatenate([r["state"] for r in res]).view(np.uint32),
+                          gag.state.cpu().numpy().view(np.uint32))
+    o_dl = np.concatenate([r["delta"] for r in res], axis=1)
+    for t in range(T):
+        assert_close(dl[t], o_dl[t], what=f"TD errors of step {t}")
+    assert sum(r["n_dis_option"] for r in res) == 0
+    n_dis = sum(r["n_dis_action"] for r in res)
+    assert n_dis <= B * T // 200 and max(r["worst_gap"] for r in res) <= 1e-4, (n_dis, max(r["worst_gap"] for r in res))
+    o_cnt = sum(r["cnt"] for r in res)
+    o_dW = sum(r["dW"] for r in res)
+    assert np.array_equal(g_cnt, o_cnt) and int(o_cnt.sum()) == B * T
+    assert_close(g_dW, o_dW, what="dW of the window")
+    assert_close(g_rows, np.concatenate([r["trace_rowsum"] for r in res]), what="per-env trace row sums")
+    ora = oracle.OptionSet(K, order, 1, alpha=hp["alpha"])
+    ora.W[:] = W
+    ora.window_steps = T
+    ora.apply(o_dW, o_cnt)
+    assert_close(g_W - W, ora.W - W, what="weight update of the apply")
+    assert_close(g_W, ora.W, what="W after the apply")
+    for k in ("n_success", "n_fail", "ex_count"):
+        assert np.array_equal(getattr(gag, k).cpu().numpy().astype(np.int64), sum(r[k] for r in res)), k
+    assert term.sum() > B // 4
+    # the probed envs' full traces (shards return them in ascending env order)
+    assert_close(g_probe[np.argsort(probe)], np.concatenate([r["trace_probe"] for r in res]), what="probed traces")
+
+
+def test_full_size_configs1_window_vs_oracle(scg, torch):
+    """BASELINE.json configs[1] at full size (easy, 65,536 envs, order 3, 4 option slots, 2 active classifiers): one
+    8-step window in one launch + sweep + apply against the oracle (16 shards on the host cores)."""
+    _full_size_vs_oracle(scg, torch, "easy", 65536, 3, 4, 2, 8, 4096)
+
+
+def test_full_size_configs2_window_vs_oracle(scg, torch):
+    """BASELINE.json configs[2] per-GPU shape (hard, 131,072 envs, order 5, 8 option slots, 3 active): one 4-step
+    window against the oracle (64 shards on the host cores)."""
+    _full_size_vs_oracle(scg, torch, "hard", 131072, 5, 8, 3, 4, 2048)
+
+
+def test_full_size_configs4_graph_window_vs_oracle(scg, torch):
+    """configs[4] (option-graph variant) at a quarter of the per-GPU size: parents = all earlier options + goal."""
+    _full_size_vs_oracle(scg, torch, "hard", 32768, 5, 8, 3, 4, 2048, graph=True)
+
+
 def test_graph_mode_parents_match_oracle(scg, torch):
     """Option-graph variant: an option whose parents are several initiation sets and the goal terminates on any of
     them (oracle/agent.py, graph=True); one fused step against the oracle."""
@@ -767,7 +1044,7 @@ def test_graph_mode_parents_match_oracle(scg, torch):
     assert out["hit"].sum() > 20
     assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
     assert np.array_equal(gag.option.cpu().numpy(), out["option"])
-    assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+    assert_close(gag.delta.cpu().numpy(), out["delta"])
     assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success) and np.array_equal(gag.n_fail.cpu().numpy(), oag.n_fail)
 
 
@@ -810,11 +1087,11 @@ def test_agent_odd_shapes_match_oracle(scg, torch, B, order, K, name):
         gag.action.copy_(torch.as_tensor(out["action"]))
         gag.invalidate()
         assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), out["state"].view(np.uint32))
-        assert rel_err(gag.delta.cpu().numpy(), out["delta"]) < RTOL
+        assert_close(gag.delta.cpu().numpy(), out["delta"])
         assert np.array_equal(gag.option.cpu().numpy(), out["option"])
     assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
-    assert rel_err(gag.options.trace.cpu().numpy(), oag.options.trace) < RTOL
-    assert rel_err(gag.options.dW.cpu().numpy(), oag.options.dW) < RTOL
+    assert_close(gag.options.trace.cpu().numpy(), oag.options.trace)
+    assert_close(gag.options.dW.cpu().numpy(), oag.options.dW)
     # and the multi-step launch path: run(5) == 5 x step() on a twin (epsilon-greedy draws are keyed by env and step)
     _, a = _paired_agents(scg, torch, B, order, K, name, 30 + B, sync_interval=4, option_timeout=2, epsilon=0.3)
     _, b = _paired_agents(scg, torch, B, order, K, name, 30 + B, sync_interval=4, option_timeout=2, epsilon=0.3)
@@ -975,7 +1252,7 @@ def test_run_host_equals_run(scg, torch):
     assert np.array_equal(hs, a.s.cpu().numpy()) and np.array_equal(ha, a.action.cpu().numpy())
     # (the host path re-evaluates Q_o(s, a) at the start of every call instead of carrying it: TD errors agree to rounding)
     assert np.array_equal(f, a.flags.cpu().numpy())
-    assert rel_err(d, a.delta.cpu().numpy()) < 1e-5
+    assert_close(d, a.delta.cpu().numpy(), rtol=1e-5)
     assert float((a.options.W - b.options.W).abs().max()) <= 1e-5 * max(1.0, float(a.options.W.abs().max()))
 
 
@@ -994,7 +1271,8 @@ def test_host_step_equals_device_steps_large_ragged_batch(scg, torch):
         assert np.array_equal(hs, a.s.cpu().numpy()), f"state, step {t}"
         assert np.array_equal(ha, a.action.cpu().numpy()) and np.array_equal(f, a.flags.cpu().numpy())
         # (the slab reduction adds with atomics: after the first apply the weights, hence the TD errors, agree to rounding)
-        assert np.array_equal(r, a.reward.cpu().numpy()) and rel_err(d, a.delta.cpu().numpy()) < 1e-5
+        assert np.array_equal(r, a.reward.cpu().numpy())
+        assert_close(d, a.delta.cpu().numpy(), rtol=1e-5)
     torch.cuda.synchronize()
     assert torch.equal(a.option, c.option) and torch.equal(a.options.cnt, c.options.cnt)
     assert float((c.options.W - a.options.W).abs().max()) <= 1e-6 * max(1.0, float(a.options.W.abs().max()))
