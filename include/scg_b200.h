@@ -133,31 +133,53 @@ int scg_clf_fit(int N, const float *X, const uint8_t *y, float *theta_k /* [6] i
  * records of up to win_cap steps are folded into dW and the per-env traces by ONE trace sweep per
  * window (scg_agent_flush), so the dense traces are read and written once per window, not per step. */
 #define SCG_WIN_MAX 32
+
+/* Device-resident controller state (oracle/agent.py: n_active, active, parents).  The step kernel reads it every step;
+ * scg_agent_manage's kernel promotes the gestating option in place, so option creation needs no host round trip. */
+typedef struct scg_ctl {
+    int32_t n_active;              /* options 0 .. n_active-1 are active; slot n_active is the gestating learner */
+    uint32_t active_mask;          /* bit k set <=> option k is active */
+    int32_t n_promotions;          /* promotions decided on the device so far */
+    uint32_t last_promotion_step;  /* agent step at which the last one was decided */
+    uint32_t manage_calls;         /* scg_agent_manage launches completed (sequence number of the host mirror) */
+    uint32_t reserved[3];
+    uint32_t parents[SCG_MAX_OPTIONS]; /* bit j: the initiation set of option j is a target of option k; bit 31: the goal */
+} scg_ctl_t;
+
 typedef struct scg_agent {
     /* sizes and hyper-parameters */
-    int32_t B, K, order, n_active;
-    uint32_t active_mask, env_offset, step, example_capacity;
+    int32_t B, K, order;
+    int32_t n_active;                /* the caller's LOWER BOUND of ctl->n_active: sizes the on-chip weight staging and the
+                                        sweep's accumulator (options 0 .. n_active); options beyond it still work, through
+                                        the global-memory paths.  scg_agent_run raises it from the host mirror by itself. */
+    uint32_t graph, env_offset, step, example_capacity;
     uint64_t seed;
     float gamma, lambda, epsilon, option_bonus;
     int32_t option_timeout, max_episode_steps, cull, carry_valid;
     float alpha; int32_t window_steps, win_cap, win_len;
+    int32_t ring_len;                /* slabs of the open window whose option terminations are already in the example rings */
+    int32_t gestation_successes, clf_steps; float clf_lr;   /* controller: promotion threshold, classifier fit */
     /* per-env state (device) */
     float *x, *y, *vx, *vy;          /* current state s */
     float *x2, *y2, *vx2, *vy2;      /* the other state buffer: a step writes s' here, then the two swap */
     int32_t *action, *option, *t_opt, *ep_steps;
     float *start_xy;                 /* [B][2] position where the current option execution began */
     float *ep_return;                /* [B] running task return */
+    int32_t *ep_count;               /* [B] finished episodes of each env */
+    float *last_return;              /* [B] task return of each env's last finished episode */
     float *reward; int32_t *flags;   /* [B] outputs of the env step */
     float *delta;                    /* [B] TD errors of this step */
     float *q_carry;                  /* [B] Q_o(s, a) of the pending (state, action), valid iff carry_valid */
     float *win_rec;                  /* [win_cap][B][8] step records of the open window */
+    uint8_t *win_ev;                 /* [win_cap][B] option-termination events of the open window (0 = none) */
     float *trace;                    /* [B][A][F], as of the last flush */
     /* per-option state (device) */
     float *W, *Wt, *theta, *dW;      /* [K][A][F], [F][K][8], [K][6], [K][A][F] */
     int32_t *cnt;                    /* [K] */
-    uint32_t *parents;               /* [K] */
+    scg_ctl_t *ctl;                  /* controller state */
     float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */
-    int32_t *ex_count, *n_success, *n_fail; /* [K] */
+    int64_t *ex_count;               /* [K] examples ever appended; slot of the next one = ex_count % cap */
+    int32_t *n_success, *n_fail;     /* [K] */
     int32_t *n_success_global;       /* [K] n_success summed over ranks as of the last cross-GPU sync (multi-rank runs) */
     /* global statistics (device), 4 x 64 bit: [0] episodes, [1] goals (uint64), [2] sum of finished returns (double) */
     int64_t *stats;
@@ -168,8 +190,27 @@ typedef struct scg_agent {
  * win_len reaches win_cap.  Clear carry_valid whenever state, action, option or weights are changed
  * from outside (scg_apply changes the weights: callers clear it after every apply). */
 int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
-/* Fold the open window into dW and the traces (no-op when win_len == 0). */
+/* Fold the open window into dW and the traces (no-op when win_len == 0); appends its examples first. */
 int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
+/* Append the option-termination examples of the open window's not yet processed steps to the example rings
+ * (oracle/agent.py step, item 6).  Deterministic: the examples of a step are appended in env order, steps in order,
+ * exactly the oracle's sequence, whatever the launch geometry; when more than `example_capacity` examples of one option
+ * arrive, the last `example_capacity` survive.  Called by flush and manage; call it before reading the rings. */
+int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
+/* The option-creation controller (oracle/agent.py manage) as ONE kernel on `stream`, no host round trip: if the
+ * gestating option g = ctl->n_active has at least gestation_successes successes (n_success[g]; across ranks:
+ * n_success_global[g] as of the last exchange, identical on every rank), its initiation classifier is fit on its
+ * example ring (clf_steps gradient steps from theta = 0; across ranks on the UNION of the ranks' rings: the per-step
+ * gradient sums and example counts are exchanged over NVLink peer memory and added in rank order, so theta is
+ * bit-identical on every rank and equal to a single fit on the concatenated examples), option g becomes active and
+ * slot g + 1 starts gestating with parents {g} (chain) or {0..g, goal} (graph != 0).  The new state is also written to a
+ * host-mapped mirror (scg_agent_poll).  xchg: NULL for a single rank.  Every rank must call it at the same steps. */
+int scg_agent_manage(scg_ctx_t *ctx, scg_agent_t *ag, scg_xchg_t *xchg, void *stream);
+/* Host copy of the controller state as of the last completed scg_agent_manage / scg_agent_set_ctl, without
+ * synchronising the device (the values only ever grow, so a stale copy is a valid lower bound). */
+int scg_agent_poll(scg_ctx_t *ctx, scg_ctl_t *out /* HOST */);
+/* Overwrite the controller state from the host (tests, checkpoints): device copy on `stream` + the mirror. */
+int scg_agent_set_ctl(scg_ctx_t *ctx, scg_agent_t *ag, const scg_ctl_t *in /* HOST */, void *stream);
 /* n_steps steps in one call; when sync_interval > 0 also flush + apply every sync_interval steps:
  * scg_apply for a single rank (xchg == NULL), scg_xchg_sync across ranks otherwise.  With
  * sync_interval == 0 the caller flushes, sums dW / cnt over ranks and applies. */

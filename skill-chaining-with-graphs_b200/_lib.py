@@ -19,25 +19,35 @@ class ScgError(RuntimeError):
     pass
 
 
+class CtlStruct(C.Structure):
+    """struct scg_ctl of include/scg_b200.h: the device-resident controller state."""
+    _fields_ = [
+        ("n_active", C.c_int32), ("active_mask", C.c_uint32), ("n_promotions", C.c_int32),
+        ("last_promotion_step", C.c_uint32), ("manage_calls", C.c_uint32), ("reserved", C.c_uint32 * 3),
+        ("parents", C.c_uint32 * MAX_OPTIONS),
+    ]
+
+
 class AgentStruct(C.Structure):
     """struct scg_agent of include/scg_b200.h (field order and types must match)."""
     _fields_ = [
         ("B", C.c_int32), ("K", C.c_int32), ("order", C.c_int32), ("n_active", C.c_int32),
-        ("active_mask", C.c_uint32), ("env_offset", C.c_uint32), ("step", C.c_uint32),
+        ("graph", C.c_uint32), ("env_offset", C.c_uint32), ("step", C.c_uint32),
         ("example_capacity", C.c_uint32),
         ("seed", C.c_uint64),
         ("gamma", C.c_float), ("lam", C.c_float), ("epsilon", C.c_float), ("option_bonus", C.c_float),
         ("option_timeout", C.c_int32), ("max_episode_steps", C.c_int32), ("cull", C.c_int32),
         ("carry_valid", C.c_int32),
         ("alpha", C.c_float), ("window_steps", C.c_int32), ("win_cap", C.c_int32), ("win_len", C.c_int32),
+        ("ring_len", C.c_int32), ("gestation_successes", C.c_int32), ("clf_steps", C.c_int32), ("clf_lr", C.c_float),
         ("x", C.c_void_p), ("y", C.c_void_p), ("vx", C.c_void_p), ("vy", C.c_void_p),
         ("x2", C.c_void_p), ("y2", C.c_void_p), ("vx2", C.c_void_p), ("vy2", C.c_void_p),
         ("action", C.c_void_p), ("option", C.c_void_p), ("t_opt", C.c_void_p), ("ep_steps", C.c_void_p),
-        ("start_xy", C.c_void_p), ("ep_return", C.c_void_p),
+        ("start_xy", C.c_void_p), ("ep_return", C.c_void_p), ("ep_count", C.c_void_p), ("last_return", C.c_void_p),
         ("reward", C.c_void_p), ("flags", C.c_void_p), ("delta", C.c_void_p), ("q_carry", C.c_void_p),
-        ("win_rec", C.c_void_p), ("trace", C.c_void_p),
+        ("win_rec", C.c_void_p), ("win_ev", C.c_void_p), ("trace", C.c_void_p),
         ("W", C.c_void_p), ("Wt", C.c_void_p), ("theta", C.c_void_p), ("dW", C.c_void_p),
-        ("cnt", C.c_void_p), ("parents", C.c_void_p),
+        ("cnt", C.c_void_p), ("ctl", C.c_void_p),
         ("ex_xy", C.c_void_p), ("ex_label", C.c_void_p),
         ("ex_count", C.c_void_p), ("n_success", C.c_void_p), ("n_fail", C.c_void_p),
         ("n_success_global", C.c_void_p),
@@ -75,6 +85,10 @@ _SIGS = {
     "scg_clf_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_float, _P]),
     "scg_agent_step": (C.c_int, [_P, _P, C.POINTER(AgentStruct), _P]),
     "scg_agent_flush": (C.c_int, [_P, C.POINTER(AgentStruct), _P]),
+    "scg_agent_ring": (C.c_int, [_P, C.POINTER(AgentStruct), _P]),
+    "scg_agent_manage": (C.c_int, [_P, C.POINTER(AgentStruct), _P, _P]),
+    "scg_agent_poll": (C.c_int, [_P, C.POINTER(CtlStruct)]),
+    "scg_agent_set_ctl": (C.c_int, [_P, C.POINTER(AgentStruct), C.POINTER(CtlStruct), _P]),
     "scg_agent_run": (C.c_int, [_P, _P, C.POINTER(AgentStruct), C.c_int, C.c_int, _P, _P]),
     "scg_xchg_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "scg_xchg_destroy": (C.c_int, [_P]),

@@ -8,8 +8,14 @@ cross-GPU weight-delta sync.  Same interface and semantics as the CPU oracle's S
     stats = agent.run_episode(max_steps=2000)
 
 Multi-GPU: one process per GPU, each owning a contiguous env slice (`env_offset`); every
-`sync_interval` steps dW and cnt are all-reduced (sum) over NCCL and every rank applies the same
-update (weights stay bit-identical across ranks).
+`sync_interval` steps dW and cnt are summed over ranks by ONE kernel over NVLink peer memory (k_sync,
+csrc/scg_xchg.cu; `sync_backend="nccl"` keeps an NCCL all-reduce path) and every rank applies the same update
+(weights stay bit-identical across ranks).
+
+The option-creation controller runs on the device (csrc/scg_ctl.cu): manage() queues one kernel that checks the
+gestating option's success count, fits its initiation classifier on its example ring (across ranks: on the union of
+the ranks' rings, exchanged over peer memory) and promotes it in device memory; the host only learns of it from a
+host-mapped mirror and never waits for the device.
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -17,10 +23,10 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import check, ptr, AgentStruct, GOAL_BIT, N_ACTIONS
+from ._lib import check, ptr, AgentStruct, CtlStruct, GOAL_BIT, N_ACTIONS
 from .option import OptionSet
 from .pinball import PinballMap
-from .sync import allreduce_deltas, allreduce_scalar_sum, world_size
+from .sync import allreduce_deltas, allreduce_scalar_sum, fit_union, world_size
 
 
 @dataclass
@@ -48,6 +54,7 @@ class AgentConfig:
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
     deterministic: bool = False   # fixed-order reduction of the weight deltas: runs reproduce bit for bit (slightly slower)
     sync_backend: str = "p2p"   # multi-rank weight-delta exchange: "p2p" (one kernel over NVLink peer memory) or "nccl"
+    sync_timeout_s: float = 30.0   # how long a peer-memory exchange waits for the other ranks before failing (ScgError)
 
 
 class SkillChainAgent:
@@ -81,21 +88,23 @@ class SkillChainAgent:
         self.ep_steps = torch.zeros(B, **i32)
         self.start_xy = torch.zeros((B, 2), **f32)
         self.ep_return = torch.zeros(B, **f32)
+        self.ep_count = torch.zeros(B, **i32)               # finished episodes per env
+        self.last_return = torch.zeros(B, **f32)            # task return of each env's last finished episode
         self.q_carry = torch.zeros(B, **f32)
         self.win_rec = torch.zeros((self.win_cap, B, 8), **f32)
-        self.parents = torch.zeros(K, dtype=torch.int32, device=dev)
-        self.parents_host = np.zeros(K, dtype=np.uint32)
-        self.parents_host[0] = GOAL_BIT
-        self._push_parents()
-        self.ex_xy = torch.zeros((K, cfg.example_capacity, 2), **f32)
-        self.ex_label = torch.zeros((K, cfg.example_capacity), dtype=torch.uint8, device=dev)
-        self.ex_count = torch.zeros(K, **i32)
+        self.win_ev = torch.zeros((self.win_cap, max(B, 1)), dtype=torch.uint8, device=dev)
+        # controller state: a device block (struct scg_ctl) the kernels read and scg_agent_manage updates in place
+        self.ctl = torch.zeros(32, **i32)
+        self._ctl = CtlStruct()
+        self._ctl.parents[0] = GOAL_BIT
+        self.parents_host = np.ctypeslib.as_array(self._ctl.parents)[:K]     # view: edit, then _push_parents()
+        self._ex_xy = torch.zeros((K, cfg.example_capacity, 2), **f32)
+        self._ex_label = torch.zeros((K, cfg.example_capacity), dtype=torch.uint8, device=dev)
+        self._ex_count = torch.zeros(K, dtype=torch.int64, device=dev)
         self.n_success = torch.zeros(K, **i32)
         self.n_fail = torch.zeros(K, **i32)
         self.n_success_global = torch.zeros(K, **i32)
         self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
-        self.active_mask = 0
-        self.n_active = 0
         # initial state, option and action (oracle/agent.py __init__)
         s = self._sbuf[0]
         if initial_states is not None:
@@ -108,6 +117,7 @@ class SkillChainAgent:
         self.options.pack()
         self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT, soa=s))
         self._struct = self._make_struct()
+        self._push_ctl()
         self.options._on_weights_changed = self._weights_changed
         self._xchg = None
         if world_size(self.pg) > 1 and cfg.sync_backend == "p2p":
@@ -120,6 +130,7 @@ class SkillChainAgent:
             ok = int(allreduce_scalar_sum(ok, self.pg))
             if ok == world_size(self.pg):
                 self._xchg = x
+                check(self.lib.scg_xchg_set_timeout(x, float(cfg.sync_timeout_s)))
             else:
                 if x is not None:
                     self.lib.scg_xchg_destroy(x)
@@ -161,9 +172,76 @@ class SkillChainAgent:
         except Exception:
             pass
 
+    # -- controller state --------------------------------------------------------------------------
+    def _push_ctl(self):
+        """Host copy of the controller state -> device block and host mirror (setup, tests, checkpoints)."""
+        g = self._struct
+        check(self.lib.scg_agent_set_ctl(self.options.ctx, C.byref(g), C.byref(self._ctl), _lib.current_stream()))
+
+    _push_parents = _push_ctl
+
+    def _poll(self):
+        """Pick up promotions the device has made since the last look (host-mapped mirror, no device sync)."""
+        m = CtlStruct()
+        check(self.lib.scg_agent_poll(self.options.ctx, C.byref(m)))
+        if m.n_promotions > self._ctl.n_promotions or m.manage_calls > self._ctl.manage_calls:
+            C.memmove(C.byref(self._ctl), C.byref(m), C.sizeof(CtlStruct))
+            self._struct.n_active = max(int(self._struct.n_active), int(m.n_active))
+
+    @property
+    def n_active(self):
+        """Number of active options as far as the host knows (exact after controller_state(sync=True))."""
+        self._poll()
+        return int(self._ctl.n_active)
+
+    @n_active.setter
+    def n_active(self, v):
+        self.controller_state(sync=True)       # start from the device's current state, then override
+        self._ctl.n_active = int(v)
+        self._push_ctl()
+
+    @property
+    def active_mask(self):
+        self._poll()
+        return int(self._ctl.active_mask)
+
+    @active_mask.setter
+    def active_mask(self, v):
+        self.controller_state(sync=True)
+        self._ctl.active_mask = int(v)
+        self._push_ctl()
+
+    def controller_state(self, sync=True):
+        """dict(n_active, active_mask, n_promotions, last_promotion_step, parents); sync=True waits for the stream so
+        the values are exact, sync=False returns what the mirror shows now."""
+        if sync:
+            self.torch.cuda.current_stream().synchronize()
+        self._poll()
+        c = self._ctl
+        return dict(n_active=int(c.n_active), active_mask=int(c.active_mask), n_promotions=int(c.n_promotions),
+                    last_promotion_step=int(c.last_promotion_step), parents=[int(v) for v in c.parents[:self.options.K]])
+
+    # example rings: the step kernel leaves termination events with the step records; they reach the rings at the next
+    # flush / manage, or here when somebody looks
+    def _ring(self):
+        check(self.lib.scg_agent_ring(self.options.ctx, C.byref(self._struct), _lib.current_stream()))
+
+    @property
+    def ex_xy(self):
+        self._ring()
+        return self._ex_xy
+
+    @property
+    def ex_label(self):
+        self._ring()
+        return self._ex_label
+
+    @property
+    def ex_count(self):
+        self._ring()
+        return self._ex_count
+
     # -- plumbing --------------------------------------------------------------------------------
-    def _push_parents(self):
-        self.parents.copy_(self.torch.from_numpy(self.parents_host.view(np.int32)))
 
     def _make_struct(self):
         cfg, o, g = self.cfg, self.options, AgentStruct()
@@ -172,22 +250,26 @@ class SkillChainAgent:
         g.gamma, g.lam, g.epsilon, g.option_bonus = cfg.gamma, cfg.lam, cfg.epsilon, cfg.option_bonus
         g.option_timeout, g.max_episode_steps, g.cull = cfg.option_timeout, cfg.max_episode_steps, int(cfg.cull)
         g.alpha, g.win_cap = cfg.alpha, self.win_cap
-        g.step = g.window_steps = g.win_len = g.carry_valid = 0
+        g.step = g.window_steps = g.win_len = g.carry_valid = g.ring_len = g.n_active = 0
+        g.graph, g.gestation_successes = int(bool(cfg.graph)), int(cfg.gestation_successes)
+        g.clf_steps, g.clf_lr = int(cfg.clf_steps), float(cfg.clf_lr)
         s, s2 = self._sbuf
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
         for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
-                     "q_carry", "win_rec", "parents", "ex_xy", "ex_label", "ex_count", "n_success", "n_fail",
-                     "n_success_global", "stats"):
+                     "q_carry", "win_rec", "win_ev", "ctl", "n_success", "n_fail", "n_success_global", "stats",
+                     "ep_count", "last_return"):
             setattr(g, name, getattr(self, name).data_ptr())
+        g.ex_xy, g.ex_label, g.ex_count = self._ex_xy.data_ptr(), self._ex_label.data_ptr(), self._ex_count.data_ptr()
         g.trace, g.W, g.Wt, g.theta = o._trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
         g.dW, g.cnt = o._dW.data_ptr(), o.cnt.data_ptr()
         return g
 
     def _sync_struct(self):
-        """Push the host-side controller state the kernels read."""
         g = self._struct
-        g.n_active, g.active_mask = self.n_active, self.active_mask
+        if self._xchg is not None and self.peer_sync_timed_out():
+            raise _lib.ScgError("a peer rank did not arrive at a cross-GPU weight exchange within "
+                                f"{self.cfg.sync_timeout_s} s: the weight replicas are out of step")
         return g
 
     @property
@@ -360,78 +442,92 @@ class SkillChainAgent:
 
     # -- low-rate controller ---------------------------------------------------------------------
     def examples(self, k):
-        n = int(min(int(self.ex_count[k]) & 0xFFFFFFFF, self.cfg.example_capacity))
-        return self.ex_xy[k, :n].clone(), self.ex_label[k, :n].clone()
+        n = int(min(int(self.ex_count[k]), self.cfg.example_capacity))
+        return self._ex_xy[k, :n].clone(), self._ex_label[k, :n].clone()
 
-    def _fit_slot(self, g, X, y):
-        """Fit option g's initiation classifier on (X, y); across ranks every rank fits on its own examples and the
-        parameters are averaged."""
-        cfg = self.cfg
-        self.options.theta[g].zero_()
-        if X.shape[0] > 0:
-            self.options.fit_initiation(g, X, y, cfg.clf_steps, cfg.clf_lr)
-        ws = world_size(self.pg)
-        if ws > 1:
-            th = allreduce_scalar_sum(self.options.theta[g].clone(), self.pg)
-            self.options.theta[g].copy_(th / ws)
-
-    def manage(self):
-        """Promote the gestating option once it has enough successes (oracle/agent.py manage).
-        Multi-GPU: success counts are summed over ranks so every rank promotes at the same step;
-        each rank fits on its own examples and theta is averaged."""
-        cfg, K, torch = self.cfg, self.options.K, self.torch
-        g = self.n_active
-        if g >= K - 1:
-            return False
-        if self._xchg is not None:
-            # the peer-memory sync already left the sum over ranks (as of the last sync) on every GPU: same
-            # decision everywhere, no collective in the loop
-            n_succ = int(self.n_success_global[g])
+    def manage(self, wait=False):
+        """The option-creation controller (oracle/agent.py manage): promote the gestating option once it has enough
+        successes.  Queues ONE kernel on the stream (scg_agent_manage): decision, classifier fit and promotion all happen
+        in device memory, so the agent loop never waits for the host.  Multi-GPU: success counts are the sums the last
+        weight exchange left on every rank (same decision everywhere), and the classifier is fit on the union of the
+        ranks' example rings - per-step gradient sums travel over NVLink peer memory and are added in rank order, so
+        theta is bit-identical on every rank and equal to one fit on the concatenated examples.  Call it right after a
+        sync (manage_every a multiple of sync_interval) for the counts to be current.
+        Returns True if the host has learned of a new promotion since the last call: exact with wait=True (waits for
+        the stream), otherwise possibly one call late."""
+        before = int(self._ctl.n_promotions)
+        if world_size(self.pg) > 1 and self._xchg is None:
+            self._manage_host()                    # NCCL backend: host-driven, same union fit through all-reduces
         else:
-            # the device counter is 32 bits and wraps: read it as unsigned, sum over ranks in 64 bits
-            n_succ = int(allreduce_scalar_sum(self.n_success[g:g + 1].to(torch.int64) & 0xFFFFFFFF, self.pg))
+            g = self._sync_struct()
+            check(self.lib.scg_agent_manage(self.options.ctx, C.byref(g), self._xchg, _lib.current_stream()))
+        if wait:
+            self.torch.cuda.current_stream().synchronize()
+        self._poll()
+        return int(self._ctl.n_promotions) > before
+
+    def _manage_host(self):
+        """manage() for the NCCL backend (no peer mapping): the counters and the per-step gradient sums of the fit go
+        through all-reduces; every rank ends with the same theta, equal to one fit on the union of the rings."""
+        cfg, K, torch = self.cfg, self.options.K, self.torch
+        self._poll()
+        g = int(self._ctl.n_active)
+        if g >= K - 1:
+            return
+        # the device counter is 32 bits and wraps: read it as unsigned, sum over ranks in 64 bits
+        n_succ = int(allreduce_scalar_sum(self.n_success[g:g + 1].to(torch.int64) & 0xFFFFFFFF, self.pg))
         if n_succ < cfg.gestation_successes:
-            return False
+            return
         X, y = self.examples(g)
-        self._fit_slot(g, X, y)
-        self.active_mask |= (1 << g)
-        self.n_active += 1
-        n = self.n_active
-        self.parents_host[n] = ((1 << n) - 1) | GOAL_BIT if cfg.graph else (1 << (n - 1))
-        self._push_parents()
-        return True
+        o = self.options
+
+        def grad_sum(theta):                      # this rank's sum_i (p_i - y_i) psi_i
+            if X.shape[0] == 0:
+                return torch.zeros(6, dtype=torch.float32, device=self.device)
+            o.theta[g].copy_(theta)
+            return o.clf_grad(g, X, y) * float(X.shape[0])
+
+        theta = fit_union(grad_sum, int(X.shape[0]), torch.zeros(6, dtype=torch.float32, device=self.device),
+                          cfg.clf_steps, cfg.clf_lr, self.pg)
+        o.theta[g].copy_(theta)
+        n = g + 1
+        self._ctl.active_mask |= (1 << g)
+        self._ctl.n_active = n
+        self._ctl.n_promotions += 1
+        self._ctl.last_promotion_step = int(self._struct.step)
+        self.parents_host[n] = (((1 << n) - 1) | GOAL_BIT) if cfg.graph else (1 << (n - 1))
+        self._push_ctl()
 
     def warm_up_controller(self):
-        """Run the controller's device code path once on scratch data (torch loads its kernels lazily and NCCL sets
-        up a collective on first use: the first promotion would otherwise pay milliseconds inside the caller's loop)."""
-        torch, K = self.torch, self.options.K
-        saved = self.options.theta[K - 1].clone()
-        X = torch.tensor([[0.1, 0.2], [0.8, 0.7], [0.3, 0.9], [0.6, 0.1]], device=self.device)
-        y = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device=self.device)
-        _ = int(allreduce_scalar_sum(self.n_success[0:1].to(torch.int64) & 0xFFFFFFFF, self.pg))
-        _ = int(self.n_success_global[0])
-        _ = self.examples(0)
-        clf_steps, self.cfg.clf_steps = self.cfg.clf_steps, 1
-        self._fit_slot(K - 1, X, y)
-        self.cfg.clf_steps = clf_steps
-        self.options.theta[K - 1].copy_(saved)
-        self._push_parents()
+        """Run the controller's code path once without effect (first launches load the kernels lazily; with the NCCL
+        backend the first collective sets up its communicator): a later promotion then costs what it costs in steady
+        state.  Restores everything it touched."""
+        torch = self.torch
+        if world_size(self.pg) > 1 and self._xchg is None:
+            _ = int(allreduce_scalar_sum(self.n_success[0:1].to(torch.int64) & 0xFFFFFFFF, self.pg))
+            _ = fit_union(lambda th: th * 0, 0, torch.zeros(6, dtype=torch.float32, device=self.device), 1, 1.0, self.pg)
+        else:
+            thr, self._struct.gestation_successes = self._struct.gestation_successes, 0x7FFFFFFF   # never promotes
+            check(self.lib.scg_agent_manage(self.options.ctx, C.byref(self._struct), self._xchg, _lib.current_stream()))
+            self._struct.gestation_successes = thr
         torch.cuda.synchronize()
 
     # -- checkpoint / resume (SURVEY.md section 5) ----------------------------------------------------
-    _CKPT_TENSORS = ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "ex_xy", "ex_label", "ex_count",
-                     "n_success", "n_fail", "stats", "q_carry")
+    _CKPT_TENSORS = ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "_ex_xy", "_ex_label", "_ex_count",
+                     "n_success", "n_fail", "n_success_global", "stats", "q_carry", "ep_count", "last_return")
 
     def save(self, path):
         """Write everything needed to resume this rank (option weights, classifiers, option graph, per-env state and
         traces, counters) to `path` (.npz).  The open window is folded in first."""
         self.flush()
         o, g = self.options, self._struct
-        arrs = {k: getattr(self, k).cpu().numpy() for k in self._CKPT_TENSORS}
+        c = self.controller_state(sync=True)
+        arrs = {k.lstrip("_"): getattr(self, k).cpu().numpy() for k in self._CKPT_TENSORS}
         arrs.update(W=o.W.cpu().numpy(), theta=o.theta.cpu().numpy(), trace=o._trace.cpu().numpy(),
                     dW=o._dW.cpu().numpy(), cnt=o.cnt.cpu().numpy(), state=self.s.cpu().numpy(),
-                    parents=self.parents_host.copy(),
-                    meta=np.array([self.n_active, self.active_mask, int(g.step), int(g.window_steps)], dtype=np.int64))
+                    parents=np.array(c["parents"], dtype=np.uint32),
+                    meta=np.array([c["n_active"], c["active_mask"], int(g.step), int(g.window_steps), c["n_promotions"],
+                                   c["last_promotion_step"]], dtype=np.int64))
         np.savez(path, **arrs)
 
     def load(self, path):
@@ -443,7 +539,7 @@ class SkillChainAgent:
             raise ValueError("checkpoint does not match this agent's configuration")
         self.flush()
         for k in self._CKPT_TENSORS:
-            getattr(self, k).copy_(torch.as_tensor(z[k]))
+            getattr(self, k).copy_(torch.as_tensor(z[k.lstrip("_")]))
         o.W.copy_(torch.as_tensor(z["W"]))
         o.theta.copy_(torch.as_tensor(z["theta"]))
         o._trace.copy_(torch.as_tensor(z["trace"]))
@@ -451,10 +547,14 @@ class SkillChainAgent:
         o.cnt.copy_(torch.as_tensor(z["cnt"]))
         o.pack()
         self.s.copy_(torch.as_tensor(z["state"]))
+        self.torch.cuda.current_stream().synchronize()
+        self._poll()
         self.parents_host[:] = z["parents"]
-        self._push_parents()
-        self.n_active, self.active_mask = int(z["meta"][0]), int(z["meta"][1])
-        g.step, g.window_steps, g.win_len = int(z["meta"][2]), int(z["meta"][3]), 0
+        self._ctl.n_active, self._ctl.active_mask = int(z["meta"][0]), int(z["meta"][1])
+        if len(z["meta"]) > 4:
+            self._ctl.n_promotions, self._ctl.last_promotion_step = int(z["meta"][4]), int(z["meta"][5])
+        self._push_ctl()
+        g.step, g.window_steps, g.win_len, g.ring_len = int(z["meta"][2]), int(z["meta"][3]), 0, 0
         o.window_steps = int(z["meta"][3])
         g.carry_valid = 0
 
@@ -468,22 +568,30 @@ class SkillChainAgent:
                     n_fail=self.n_fail.cpu().numpy().view(np.uint32).astype(np.int64),
                     n_active=self.n_active)
 
-    def run_episode(self, max_steps=2000, manage_every=64):
-        """Step until every env has finished at least one more episode (checked every
-        `manage_every` steps, where the controller also runs), or `max_steps` steps."""
-        base = int(self.stats[0])
+    def run_episode(self, max_steps=2000, manage_every=64, check_every=None):
+        """Step until every env has finished at least one more episode, or `max_steps` steps (oracle/agent.py
+        run_episode: same stopping rule, same statistics).  The controller runs every `manage_every` steps.  The
+        stopping rule is evaluated every `check_every` steps (default: manage_every; the oracle checks after every step,
+        so check_every=1 reproduces its step count exactly, at the price of one host read per step)."""
+        torch = self.torch
+        check_every = int(check_every or manage_every)
+        base = self.ep_count.clone()
+        goals0 = int(self.stats[1])
         steps = 0
-        B = self.cfg.batch
         while steps < max_steps:
-            k = min(manage_every, max_steps - steps)
+            k = min(check_every - steps % check_every, manage_every - steps % manage_every, max_steps - steps)
             self.run(k)
             steps += k
-            self.manage()
-            done = self.stats[0:1] - base >= B
-            if world_size(self.pg) > 1:          # every rank must leave the loop at the same step (the syncs are collective)
-                done = allreduce_scalar_sum(done.to(self.torch.int32), self.pg) == world_size(self.pg)
-            if bool(done):
-                break
-        c = self.counters()
-        return dict(steps=steps, finished=c["episodes"] - base, goals=c["goals"], mean_return=c["mean_return"],
-                    n_active=self.n_active, env_steps=steps * B)
+            if steps % manage_every == 0:
+                self.manage()
+            if steps % check_every == 0 or steps == max_steps:
+                done = (self.ep_count > base).all().to(torch.int32)
+                if world_size(self.pg) > 1:      # every rank must leave the loop at the same step (the syncs are collective)
+                    done = allreduce_scalar_sum(done, self.pg) == world_size(self.pg)
+                if bool(done):
+                    break
+        fin = self.ep_count > base
+        n_fin = int(fin.sum())
+        mean_ret = float(self.last_return[fin].double().mean()) if n_fin else float("nan")
+        return dict(steps=steps, finished=n_fin, goals=int(self.stats[1]), goals_this_call=int(self.stats[1]) - goals0,
+                    mean_return=mean_ret, n_active=self.controller_state(sync=True)["n_active"], env_steps=steps * self.cfg.batch)

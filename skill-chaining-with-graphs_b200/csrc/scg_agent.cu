@@ -37,6 +37,7 @@ struct StepArgs {
     int wait_first;   // 1: the previous launch may have written the weights - wait for it before staging them
     int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
     float4 *rec;  // this step's slab of the window: [B][2]
+    uint8_t *ev;  // this step's slab of the event bytes: [B]
 };
 
 // bulk-TMA staging of up to two global blocks into shared memory behind one mbarrier
@@ -104,7 +105,11 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
     const int K = g.K;
     const int Kw = SMEMW ? args.k_stage : K;          // options per feature in the weight table being read
-    const int gest = min(g.n_active, K - 1);
+    // controller state lives on the device (scg_agent_manage promotes options in place): the launch was sized with the
+    // host's lower bound of n_active (k_stage), the truth is read here
+    const int n_act = g.ctl->n_active;
+    const uint32_t amask = g.ctl->active_mask;
+    const int gest = min(n_act, K - 1);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n_tiles = (g.B + 31) >> 5;
     constexpr unsigned FULL = 0xffffffffu;
@@ -135,25 +140,29 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
             float2 zb[4];
             scg_phasors(nx, ny, nvx, nvy, zb);
             float qb[SCG_A], qsa = qc;
-            const WCur<SMEMW> wc(Wt, Kw, o);
+            // an option promoted after the host sized this launch (o >= k_stage) is not in the staged table: the warp
+            // then reads the weights through the global path for this step (rare and transient)
+            const bool unstaged = SMEMW && __any_sync(FULL, o >= args.k_stage);
             if (PAIR && s == 0) {
                 float2 za[4];
                 scg_phasors(sx, sy, svx, svy, za);
                 float qa[SCG_A];
-                scg_q_pair<N1, SMEMW>(za, zb, wc, qa, qb);
+                if (unstaged) scg_q_pair<N1, false>(za, zb, WCur<false>(g.Wt, K, o), qa, qb);
+                else scg_q_pair<N1, SMEMW>(za, zb, WCur<SMEMW>(Wt, Kw, o), qa, qb);
                 qsa = 0.f;
 #pragma unroll
                 for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
             } else {
-                scg_q_one<N1, SMEMW>(zb, wc, qb);
+                if (unstaged) scg_q_one<N1, false>(zb, WCur<false>(g.Wt, K, o), qb);
+                else scg_q_one<N1, SMEMW>(zb, WCur<SMEMW>(Wt, Kw, o), qb);
             }
             // 2-3: initiation bits of s2, termination, option reward
-            const uint32_t bits = scg_init_bits(g.theta, K, g.active_mask, nx, ny);
-            const uint32_t pm = g.parents[o];
+            const uint32_t bits = scg_init_bits(g.theta, K, amask, nx, ny);
+            const uint32_t pm = g.ctl->parents[o];
             const bool hit = (((pm & SCG_GOAL_BIT) != 0) && env_done) || ((bits & pm & ~SCG_GOAL_BIT) != 0);
             t_opt += 1;
             ep += 1;
-            const bool left = ((g.active_mask >> o) & 1u) && !((bits >> o) & 1u);
+            const bool left = ((amask >> o) & 1u) && !((bits >> o) & 1u);
             const bool ep_timeout = (ep >= g.max_episode_steps) && !env_done;
             const bool term = env_done || hit || (t_opt >= g.option_timeout) || left || ep_timeout;
             const float r = __fadd_rn(r_env, (hit && !env_done) ? g.option_bonus : 0.f);
@@ -174,16 +183,11 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                 const uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
                 float4 *rec = args.rec + ((size_t)s * g.B + b) * 2;
                 rec[0] = make_float4(sx, sy, svx, svy);
-                rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
-                // 6: example for option o's initiation classifier
-                if (term) {
-                    const uint32_t eslot = (uint32_t)atomicAdd(g.ex_count + o, 1) % g.example_capacity;   // unsigned: safe past 2^31 appends
-                    const size_t ei = (size_t)o * g.example_capacity + eslot;
-                    g.ex_xy[2 * ei] = stx;
-                    g.ex_xy[2 * ei + 1] = sty;
-                    g.ex_label[ei] = hit ? 1 : 0;
-                    atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
-                }
+                // 6: example for option o's initiation classifier: the event byte and the option's start position go
+                // with the record; k_ring appends them to the ring in the oracle's order (step, then env)
+                rec[1] = make_float4(delta, __uint_as_float(meta), stx, sty);
+                args.ev[(size_t)s * g.B + b] = term ? (uint8_t)(SCG_EV_TERM | (hit ? SCG_EV_HIT : 0) | o) : (uint8_t)0;
+                if (term) atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
                 // 7: env reset
                 if (reset) {
                     const uint4 rr = scg_draw(g.seed, env, step, SCG_STREAM_RESET);
@@ -194,6 +198,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 0, 1ull);
                     if (env_done) atomicAdd(reinterpret_cast<unsigned long long *>(g.stats) + 1, 1ull);
                     atomicAdd(reinterpret_cast<double *>(g.stats) + 2, (double)ret);
+                    g.ep_count[b] += 1;
+                    g.last_return[b] = ret;
                     ret = 0.f;
                     ep = 0;
                 }
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
             if (tmask) {
                 float2 zn[4] = {zb[0], zb[1], zb[2], zb[3]};
                 if (tv) {
-                    const uint32_t bn = reset ? scg_init_bits(g.theta, K, g.active_mask, nx, ny) : bits;
+                    const uint32_t bn = reset ? scg_init_bits(g.theta, K, amask, nx, ny) : bits;
                     o_next = bn ? (__ffs(bn) - 1) : gest;
                     if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
                 }
@@ -227,7 +233,11 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     }
                     const int os = __shfl_sync(FULL, o_next, sl);
                     float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, Kw, os), qp);
+                    if (SMEMW && __any_sync(FULL, have && os >= args.k_stage)) {
+                        if (have) scg_q_c0<N1, false>(c0, zs, WCur<false>(g.Wt, K, os), qp);
+                    } else {
+                        if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, Kw, os), qp);
+                    }
 #pragma unroll
                     for (int dd = 1; dd < N1; ++dd) {                // slot head (c0 == 0) gathers the partial sums
 #pragma unroll
@@ -330,19 +340,24 @@ static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_age
     if (ag->K < 1 || ag->K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
     if (ag->B < 0 || ag->win_cap < 1 || ag->win_cap > SCG_WIN_MAX || ag->win_len < 0 || ag->win_len >= ag->win_cap)
         return SCG_EINVAL;
+    if (ag->n_active < 0 || ag->n_active > ag->K - 1 || !ag->ctl || !ag->win_ev) return SCG_EINVAL;
     if (map->hdr.blob_bytes > 160 * 1024) return SCG_ELIMIT;
     return 0;
 }
 
 extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if (!ctx || !ag) return SCG_EINVAL;
-    if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; return 0; }
-    // option ids in the records are 0 .. n_active (the gestating slot), and n_active only grows
+    if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; ag->ring_len = 0; return 0; }
+    int rc = scg_agent_ring(ctx, ag, stream);      // the window's option terminations -> example rings
+    if (rc) return rc;
+    // option ids in the records are 0 .. n_active (the gestating slot); n_active is the host's lower bound of the
+    // device's value: records of an option promoted since then are folded through the sweep's global-memory path
     const int k_used = std::min(ag->K, std::max(ag->n_active, 0) + 1);
-    int rc = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
+    rc = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
                                (cudaStream_t)stream);
     if (rc) return rc;
     ag->win_len = 0;
+    ag->ring_len = 0;
     return 0;
 }
 
@@ -351,6 +366,8 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
 static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n, void *stream,
                        bool defer_flush = false) {
     cudaStream_t st = (cudaStream_t)stream;
+    // promotions happen on the device (scg_agent_manage); the host learns of them from the mirror, without waiting
+    if (ctx->h_ctl) ag->n_active = std::max(ag->n_active, std::min((int)ctx->h_ctl->n_active, ag->K - 1));
     StepArgs args;
     args.ag = *ag;
     args.map_blob = map->d_blob;
@@ -359,6 +376,7 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1);
     args.w_bytes = args.k_stage * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
+    args.ev = ag->win_ev + (size_t)ag->win_len * ag->B;
     args.n_steps = n;
     // weights go to shared memory when two CTAs per SM still fit next to the map, or one big CTA
     static int big = -1;

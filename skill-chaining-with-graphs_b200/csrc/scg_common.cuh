@@ -19,6 +19,11 @@
 // meta bits: action (bits 0-2), option (bits 8-15), ZERO_AFTER (trace reset after the update), ACTIVE
 #define SCG_META_ACTIVE (1u << 31)
 #define SCG_META_ZERO_AFTER (1u << 16)
+// window records also carry, in floats [6], [7], the position where the executing option started (the example an option
+// termination appends to that option's ring); the event byte of a step (win_ev) says whether it terminated:
+#define SCG_EV_TERM 0x80u   // the option terminated at this step
+#define SCG_EV_HIT 0x40u    // ... by reaching one of its targets (label 1), else label 0
+#define SCG_EV_OPT 0x0Fu    // option id
 
 extern uint64_t g_scg_launches;  // host-side launch counter (scg_api.cu)
 
@@ -109,6 +114,11 @@ struct scg_ctx {
     int rec_capacity;
     int win_grid;        // CTAs of the window kernel (0 = not configured yet)
     cudaEvent_t host_ev; // "results copied" marker of scg_agent_step_host
+    // controller (scg_ctl.cu)
+    scg_ctl_t *h_ctl;          // host-mapped mirror of the device controller state (scg_agent_poll), allocated on first use
+    scg_ctl_t *d_hctl;         // its device alias
+    unsigned int *d_ring;      // scratch of the example-ring pass: per-CTA option counts, barrier and "done" tickets
+    unsigned int ring_gen;     // launches of the ring pass so far (generation of its grid barrier)
     // optional per-kernel timing of the agent pipeline (scg_profile_begin / scg_profile_end)
     cudaEvent_t *prof_ev;  // [prof_cap][2] start/stop pairs
     int *prof_kind;        // [prof_cap]

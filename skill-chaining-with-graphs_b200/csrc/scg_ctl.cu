@@ -1,0 +1,372 @@
+// scg_ctl.cu - the option-creation controller on the device (sm_100a): deterministic example rings and the
+// promote-and-fit kernel.
+//
+// Mirrors oracle/agent.py SkillChainAgent.step item 6 (example ring append) and SkillChainAgent.manage (the reference
+// has no code: /root/reference/README.md:1-2).
+//
+// k_ring   The step kernel leaves one event byte per env-step (option terminated? hit? which option) and the option's
+//          start position in the step record.  k_ring turns the events of the steps not yet processed into ring
+//          appends in exactly the oracle's order - steps in order, envs in order within a step - so the ring contents
+//          (including which examples survive once a ring wraps) do not depend on launch geometry or atomic timing:
+//          per-CTA per-option counts -> grid barrier -> exclusive prefix -> slot = (ex_count + rank) % capacity, and
+//          only the last `capacity` new examples of an option are written (no two writers per slot).
+// k_manage One CTA.  Reads the gestating option's success count, and if it qualifies fits its logistic initiation
+//          classifier on its ring by batch gradient descent from theta = 0, flips the option to active and wires the
+//          next gestating slot's parents - all in device memory, so the agent loop never waits for the host.  Across
+//          ranks the per-step gradient sums and example counts travel through NVLink peer memory (one flag round per
+//          gradient step) and are added in rank order: every rank ends with the bit-identical theta of one fit on the
+//          union of all ranks' examples.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "scg_common.cuh"
+#include "scg_xchg.cuh"
+
+#define RING_CTAS 32
+#define RING_NT 256
+
+// scratch layout (unsigned int): [RING_CTAS][16] per-CTA option counts | barrier counter | done ticket
+#define RING_BAR (RING_CTAS * SCG_MAX_OPTIONS)
+#define RING_DONE (RING_BAR + 1)
+#define RING_WORDS (RING_DONE + 1)
+
+__global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *__restrict__ ev, const float4 *__restrict__ rec,
+                                                  float *ex_xy, uint8_t *ex_label, long long *ex_count, uint32_t cap,
+                                                  unsigned int *scratch, unsigned int target) {
+    __shared__ uint32_t cnt_s[SCG_MAX_OPTIONS][RING_NT];   // [option][thread]: private column per thread, no conflicts
+    __shared__ uint32_t base_s[SCG_MAX_OPTIONS], tot_s[SCG_MAX_OPTIONS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = gridDim.x * RING_NT;
+    // contiguous chunk of the flat [step][env] byte array per thread; indices are taken relative to the 16-byte
+    // aligned address below `ev` so that whole chunks can be skipped 16 bytes at a time
+    const int mis = (int)(reinterpret_cast<uintptr_t>(ev) & 15);
+    const uint8_t *evv = ev - mis;
+    const long long nv = (long long)n + mis;
+    const int L = (int)((((nv + nthreads - 1) / nthreads) + 15) & ~15ll);
+    const long long lo = (long long)(blockIdx.x * RING_NT + tid) * L;
+    const int vbeg = (int)(lo < mis ? mis : (lo < nv ? lo : nv)), vend = (int)(lo + L < nv ? lo + L : nv);
+    auto walk = [&](auto &&fn) {            // fn(flat index, event byte) for every termination event of this thread's chunk
+        int v = vbeg;
+        while (v < vend) {
+            if ((v & 15) == 0 && v + 16 <= vend) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(evv + v);
+                if (!(q.x | q.y | q.z | q.w)) { v += 16; continue; }
+            }
+            const int e1 = min((v | 15) + 1, vend);
+            for (; v < e1; ++v) {
+                const uint32_t e = evv[v];
+                if (e & SCG_EV_TERM) fn(v - mis, e);
+            }
+        }
+    };
+    for (int o = 0; o < SCG_MAX_OPTIONS; ++o) cnt_s[o][tid] = 0;
+    // pass 1: count this thread's events per option
+    walk([&](int, uint32_t e) { cnt_s[e & SCG_EV_OPT][tid] += 1; });
+    __syncthreads();
+    // per option: exclusive prefix over the CTA's threads (warp w takes options w, w + 8), CTA total to scratch
+    for (int o = warp; o < SCG_MAX_OPTIONS; o += RING_NT / 32) {
+        uint32_t v[RING_NT / 32], s = 0;
+#pragma unroll
+        for (int i = 0; i < RING_NT / 32; ++i) { v[i] = cnt_s[o][lane * (RING_NT / 32) + i]; s += v[i]; }
+        uint32_t inc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        uint32_t run = inc - s;
+#pragma unroll
+        for (int i = 0; i < RING_NT / 32; ++i) { cnt_s[o][lane * (RING_NT / 32) + i] = run; run += v[i]; }
+        if (lane == 31) scratch[blockIdx.x * SCG_MAX_OPTIONS + o] = inc;
+    }
+    // grid barrier (all CTAs are co-resident: gridDim.x <= RING_CTAS): generation-counted arrivals
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(scratch + RING_BAR, 1u);
+        while ((int)(*reinterpret_cast<volatile unsigned int *>(scratch + RING_BAR) - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid < SCG_MAX_OPTIONS) {
+        uint32_t b = 0, t = 0;
+        for (int c = 0; c < (int)gridDim.x; ++c) {
+            const uint32_t v = __ldcg(scratch + c * SCG_MAX_OPTIONS + tid);
+            if (c < (int)blockIdx.x) b += v;
+            t += v;
+        }
+        base_s[tid] = b;
+        tot_s[tid] = t;
+    }
+    __syncthreads();
+    // pass 2: place the events.  rank = position of the event among this pass's events of its option, in (step, env)
+    // order; only the last `cap` of them are written, so every slot has at most one writer
+    walk([&](int i, uint32_t e) {
+        const uint32_t o = e & SCG_EV_OPT;
+        const uint32_t rank = base_s[o] + cnt_s[o][tid]++;
+        if ((int)o >= K || (unsigned long long)rank + cap < tot_s[o]) return;
+        const uint32_t slot = (uint32_t)(((unsigned long long)ex_count[o] + rank) % cap);
+        const float4 r1 = __ldg(rec + (size_t)i * 2 + 1);
+        const size_t ei = (size_t)o * cap + slot;
+        *reinterpret_cast<float2 *>(ex_xy + 2 * ei) = make_float2(r1.z, r1.w);
+        ex_label[ei] = (e & SCG_EV_HIT) ? 1 : 0;
+    });
+    // the last CTA to finish advances the counts (every CTA has read them by then)
+    __syncthreads();
+    __shared__ bool last;
+    if (tid == 0) {
+        __threadfence();
+        last = atomicInc(scratch + RING_DONE, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && tid < K) ex_count[tid] += (long long)tot_s[tid];
+}
+
+extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
+    if (!ctx || !ag) return SCG_EINVAL;
+    if (ag->ring_len < 0 || ag->ring_len > ag->win_len) return SCG_EINVAL;
+    const int T = ag->win_len - ag->ring_len;
+    if (T == 0 || ag->B <= 0) { ag->ring_len = ag->win_len; return 0; }
+    if (!ag->win_ev || !ag->win_rec || !ag->ex_xy || !ag->ex_label || !ag->ex_count || ag->example_capacity == 0)
+        return SCG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->d_ring) {
+        SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_ring, RING_WORDS * sizeof(unsigned int)));
+        SCG_CUDA_OK(cudaMemsetAsync(ctx->d_ring, 0, RING_WORDS * sizeof(unsigned int), st));
+        ctx->ring_gen = 0;
+    }
+    const long long n = (long long)T * ag->B;
+    if (n > 0x7fffffffll) return SCG_ELIMIT;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(RING_CTAS, (n + RING_NT * 64 - 1) / (RING_NT * 64)));
+    // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
+    ctx->ring_gen += (unsigned int)grid;
+    const size_t off = (size_t)ag->ring_len * ag->B;
+    k_ring<<<grid, RING_NT, 0, st>>>((int)n, ag->K, ag->win_ev + off, reinterpret_cast<const float4 *>(ag->win_rec) + off * 2,
+                                     ag->ex_xy, ag->ex_label, reinterpret_cast<long long *>(ag->ex_count),
+                                     ag->example_capacity, ctx->d_ring, ctx->ring_gen);
+    SCG_LAUNCH_CHECK();
+    ag->ring_len = ag->win_len;
+    return 0;
+}
+
+// ---- the promote-and-fit kernel ---------------------------------------------------------------------------------
+#define MANAGE_NT 1024
+#define MANAGE_CACHE 8     // examples per thread kept in registers (rings up to 8192 examples never re-read memory)
+
+struct ManageArgs {
+    scg_agent_t ag;
+    scg_ctl_t *mirror;               // host-mapped copy of ctl, written last
+    int world, rank;
+    unsigned char *peer[XCHG_MAX_WORLD];
+    size_t m_off;
+    uint32_t *status;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ void manage_accum(float px, float py, float lab, const float th[SCG_N_PSI], float g[SCG_N_PSI]) {
+    const float psi[SCG_N_PSI] = {1.f, px, py, px * px, px * py, py * py};
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < SCG_N_PSI; ++j) z = fmaf(th[j], psi[j], z);
+    const float d = 1.0f / (1.0f + expf(-z)) - lab;
+#pragma unroll
+    for (int j = 0; j < SCG_N_PSI; ++j) g[j] = fmaf(d, psi[j], g[j]);
+}
+
+__global__ void __launch_bounds__(MANAGE_NT) k_manage(const __grid_constant__ ManageArgs a) {
+    __shared__ float sm[33 * 8];
+    __shared__ int s_go, s_abort;
+    const scg_agent_t &g = a.ag;
+    scg_ctl_t *ctl = g.ctl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = g.K;
+    if (tid == 0) {
+        const int gi = ctl->n_active;
+        int go = 0;
+        if (gi < K - 1) {
+            // one rank: the live counter; several: the sum over ranks the last exchange left on every GPU
+            const long long ns = a.world > 1 ? (long long)g.n_success_global[gi] : (long long)(unsigned int)g.n_success[gi];
+            go = ns >= (long long)g.gestation_successes;
+        }
+        s_go = go;
+        s_abort = 0;
+    }
+    __syncthreads();
+    if (s_go) {
+        const int gi = ctl->n_active;
+        const long long have = g.ex_count[gi];
+        const int N = (int)(have < (long long)g.example_capacity ? have : (long long)g.example_capacity);
+        const float *X = g.ex_xy + (size_t)gi * g.example_capacity * 2;
+        const uint8_t *Y = g.ex_label + (size_t)gi * g.example_capacity;
+        float cx[MANAGE_CACHE], cy[MANAGE_CACHE], cl[MANAGE_CACHE];
+#pragma unroll
+        for (int k = 0; k < MANAGE_CACHE; ++k) {
+            const int i = tid + k * MANAGE_NT;
+            const bool in = i < N;
+            cx[k] = in ? X[2 * i] : 0.f;
+            cy[k] = in ? X[2 * i + 1] : 0.f;
+            cl[k] = in ? (float)Y[i] : 0.f;
+        }
+        float th[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned char *mine = a.world > 1 ? a.peer[a.rank] + a.m_off : nullptr;
+        uint32_t seq = (a.world > 1) ? *reinterpret_cast<uint32_t *>(mine + XCHG_M_SEQ) : 0u;
+        // does any rank have examples?  (one exchange round when there are several ranks; also the first fit round)
+        for (int it = 0; it < g.clf_steps && !s_abort; ++it) {
+            float gs[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < MANAGE_CACHE; ++k)
+                if (tid + k * MANAGE_NT < N) manage_accum(cx[k], cy[k], cl[k], th, gs);
+            for (int i = tid + MANAGE_CACHE * MANAGE_NT; i < N; i += MANAGE_NT)
+                manage_accum(X[2 * i], X[2 * i + 1], (float)Y[i], th, gs);
+#pragma unroll
+            for (int j = 0; j < SCG_N_PSI; ++j) {
+                const float v = scg_warp_sum(gs[j]);
+                if (lane == 0) sm[warp * 8 + j] = v;
+            }
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int j = 0; j < SCG_N_PSI; ++j) {
+                    float v = sm[lane * 8 + j];          // 32 warps
+                    v = scg_warp_sum(v);
+                    if (lane == 0) sm[32 * 8 + j] = v;
+                }
+                if (lane == 0) sm[32 * 8 + 6] = (float)N;
+            }
+            __syncthreads();
+            if (a.world > 1) {
+                // exchange round: publish (6 sums, N), signal every peer, wait for every peer, add in rank order
+                seq += 1;
+                float *mb = reinterpret_cast<float *>(mine + XCHG_M_BUF) + (seq & 1u) * 8;
+                if (tid < 8) mb[tid] = tid < 7 ? sm[32 * 8 + tid] : 0.f;
+                __syncthreads();
+                if (tid < a.world && tid != a.rank) {
+                    __threadfence_system();
+                    st_release_sys(reinterpret_cast<uint32_t *>(a.peer[tid] + a.m_off + XCHG_M_FLAG) + a.rank, seq);
+                    const uint32_t *lf = reinterpret_cast<const uint32_t *>(mine + XCHG_M_FLAG) + tid;
+                    const long long t0 = clock64();
+                    while ((int32_t)(ld_acquire_sys(lf) - seq) < 0) {
+                        if (clock64() - t0 > a.timeout_cycles) {
+                            *reinterpret_cast<volatile uint32_t *>(a.status) = 1u;
+                            __threadfence_system();
+                            s_abort = 1;
+                            break;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid < 7 && !s_abort) {
+                    float v = 0.f;
+                    for (int r = 0; r < a.world; ++r) {
+                        const float *pb = reinterpret_cast<const float *>(a.peer[r] + a.m_off + XCHG_M_BUF) + (seq & 1u) * 8;
+                        v += (r == a.rank) ? mb[tid] : ld_sys_f32(pb + tid);
+                    }
+                    sm[32 * 8 + tid] = v;
+                }
+                __syncthreads();
+            }
+            const float ntot = sm[32 * 8 + 6];
+            if (ntot > 0.f) {      // no examples anywhere: theta stays 0 (initiation set = everywhere), as in the oracle
+#pragma unroll
+                for (int j = 0; j < SCG_N_PSI; ++j)
+                    th[j] = __fsub_rn(th[j], __fmul_rn(g.clf_lr, __fdiv_rn(sm[32 * 8 + j], ntot)));
+            }
+            __syncthreads();
+        }
+        if (a.world > 1 && tid == 0) *reinterpret_cast<uint32_t *>(mine + XCHG_M_SEQ) = seq;
+        if (!s_abort) {
+            if (tid < SCG_N_PSI) g.theta[gi * SCG_N_PSI + tid] = th[tid];
+            if (tid == 0) {
+                const int n = gi + 1;
+                ctl->parents[n] = g.graph ? (((1u << n) - 1u) | SCG_GOAL_BIT) : (1u << (n - 1));
+                ctl->active_mask |= (1u << gi);
+                ctl->n_promotions += 1;
+                ctl->last_promotion_step = g.step;
+                __threadfence();
+                ctl->n_active = n;
+            }
+        }
+    }
+    __syncthreads();
+    // host mirror: everything but the sequence word, fence, then the sequence word
+    if (tid == 0) ctl->manage_calls += 1;
+    __syncthreads();
+    constexpr int NW = (int)(sizeof(scg_ctl_t) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ctl);
+    volatile uint32_t *dst = reinterpret_cast<volatile uint32_t *>(a.mirror);
+    if (tid < NW && tid != 4) dst[tid] = src[tid];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) dst[4] = src[4];
+}
+
+static int ensure_mirror(scg_ctx *ctx) {
+    if (ctx->h_ctl) return 0;
+    SCG_CUDA_OK(cudaHostAlloc((void **)&ctx->h_ctl, sizeof(scg_ctl_t), cudaHostAllocMapped));
+    memset(ctx->h_ctl, 0, sizeof(scg_ctl_t));
+    SCG_CUDA_OK(cudaHostGetDevicePointer((void **)&ctx->d_hctl, (void *)ctx->h_ctl, 0));
+    return 0;
+}
+
+extern "C" int scg_agent_manage(scg_ctx_t *ctx, scg_agent_t *ag, scg_xchg_t *xchg, void *stream) {
+    if (!ctx || !ag || !ag->ctl || !ag->theta || !ag->n_success) return SCG_EINVAL;
+    if (ag->K != ctx->K || ag->K < 1 || ag->K > SCG_MAX_OPTIONS || ag->clf_steps < 0) return SCG_EINVAL;
+    if (xchg && (!ag->n_success_global || xchg->K != ag->K)) return SCG_EINVAL;
+    if (xchg && *xchg->h_status) return SCG_EPEER;
+    int rc;
+    if ((rc = ensure_mirror(ctx))) return rc;
+    if ((rc = scg_agent_ring(ctx, ag, stream))) return rc;    // the rings must hold every example up to this step
+    ManageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ag = *ag;
+    a.mirror = ctx->d_hctl;
+    a.world = xchg ? xchg->world : 1;
+    a.rank = xchg ? xchg->rank : 0;
+    if (xchg) {
+        for (int r = 0; r < xchg->world; ++r) {
+            if (!xchg->d_peer[r]) return SCG_EINVAL;
+            a.peer[r] = xchg->d_peer[r];
+        }
+        a.m_off = xchg->m_off;
+        a.status = xchg->d_status;
+        a.timeout_cycles = xchg->timeout_cycles;
+    }
+    k_manage<<<1, MANAGE_NT, 0, (cudaStream_t)stream>>>(a);
+    SCG_LAUNCH_CHECK();
+    if (ctx->deterministic) {   // reproducible runs: the host sizes the next launches with exact knowledge
+        SCG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+        ag->n_active = std::max(ag->n_active, (int)ctx->h_ctl->n_active);
+    }
+    return 0;
+}
+
+extern "C" int scg_agent_poll(scg_ctx_t *ctx, scg_ctl_t *out) {
+    if (!ctx || !out) return SCG_EINVAL;
+    int rc = ensure_mirror(ctx);
+    if (rc) return rc;
+    const volatile uint32_t *src = reinterpret_cast<const volatile uint32_t *>(ctx->h_ctl);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out);
+    // the kernel writes the sequence word last: re-read until it is stable around the copy
+    for (int tries = 0; tries < 4; ++tries) {
+        const uint32_t s0 = src[4];
+        for (size_t i = 0; i < sizeof(scg_ctl_t) / 4; ++i) dst[i] = src[i];
+        if (src[4] == s0) break;
+    }
+    return 0;
+}
+
+extern "C" int scg_agent_set_ctl(scg_ctx_t *ctx, scg_agent_t *ag, const scg_ctl_t *in, void *stream) {
+    if (!ctx || !ag || !ag->ctl || !in) return SCG_EINVAL;
+    if (in->n_active < 0 || in->n_active > ag->K - 1 || (in->active_mask >> ag->K) != 0) return SCG_EINVAL;
+    int rc = ensure_mirror(ctx);
+    if (rc) return rc;
+    // staged through the mirror (pinned): the copy is asynchronous and ordered on the stream
+    SCG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));   // a manage kernel in flight may still write the mirror
+    memcpy(ctx->h_ctl, in, sizeof(scg_ctl_t));
+    SCG_CUDA_OK(cudaMemcpyAsync(ag->ctl, ctx->h_ctl, sizeof(scg_ctl_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    SCG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    ag->n_active = in->n_active;
+    return 0;
+}

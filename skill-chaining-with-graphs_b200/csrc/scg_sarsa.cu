@@ -194,7 +194,7 @@ struct WinCtl {
 
 template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
-                                               float *__restrict__ partial, float gl) {
+                                               float *__restrict__ partial, float gl, float *dW, int K_all) {
     using V = typename VecT<VEC>::type;
     constexpr int F = N1 * N1 * N1 * N1;
     constexpr int AF = SCG_A * F;
@@ -357,6 +357,29 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         }
     };
     auto flush_d = [&]() {
+        if (o_cur >= (uint32_t)K) {
+            // an option promoted after the host sized this launch (the accumulator covers options 0 .. K-1 only): its
+            // contribution goes straight to dW with atomics (rare and transient; ids beyond K_all are ignored)
+            if (o_cur < (uint32_t)K_all) {
+                float *gp = dW + (size_t)o_cur * AF;
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (own[j]) {
+#pragma unroll
+                        for (int r = 0; r < SCG_A; ++r) {
+                            float *q = gp + (size_t)(r * NCHR + tid + j * NT) * VEC;
+                            if constexpr (VEC == 4) {
+                                atomicAdd(q, d[j][r].x); atomicAdd(q + 1, d[j][r].y);
+                                atomicAdd(q + 2, d[j][r].z); atomicAdd(q + 3, d[j][r].w);
+                            } else {
+                                atomicAdd(q, d[j][r]);
+                            }
+                        }
+                    }
+                }
+            }
+            return;
+        }
         V *ap = reinterpret_cast<V *>(acc + (size_t)o_cur * AF);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -670,7 +693,7 @@ static size_t window_smem(const scg_ctx *ctx, int k_used) {
 // the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
 template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
-                            cudaStream_t st) {
+                            float *dW, cudaStream_t st) {
     const size_t smem = window_smem<N1>(ctx, k_used);
     auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL>;
     constexpr int NTT = NT + (CTRL ? 32 : 0);
@@ -685,16 +708,16 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4
     int grid = std::max(1, std::min(B, SCG_NUM_SMS * occ));
     int rc = ensure_partials(ctx, grid);
     if (rc) return rc;
-    kern<<<grid, NTT, smem, st>>>(B, k_used, T, rec, trace, ctx->d_partial, gl);
+    kern<<<grid, NTT, smem, st>>>(B, k_used, T, rec, trace, ctx->d_partial, gl, dW, ctx->K);
     SCG_LAUNCH_CHECK();
     return grid;
 }
 
 template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false>
 static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
-                           cudaStream_t st) {
-    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, st);
-    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, st);
+                           float *dW, cudaStream_t st) {
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
@@ -719,23 +742,23 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
         // <N1, floats per chunk, threads, chunks per thread>.  Measured on B200 (order 3, B = 65,536): two warps per
         // env with one chunk per thread 0.155 ms; one warp per env with two chunks per thread (SCG_WIN_CH3=2) has 18 %
         // fewer instructions but only 8 warps/SM to hide the shared-memory latency: 0.159 ms.  Order 5: 2.27 vs 2.38 ms.
-        case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
-        case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
+        case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
+        case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 3:
             if (win_ch3 == 1 && win_9cta3 && 9 * (window_smem<4>(ctx, k_used) + 1024) <= 227 * 1024)   // nine CTAs per SM (<= 112 registers)
-                grid = launch_window_t<4, 4, 64, 1, 9>(ctx, B, T, k_used, r4, trace, gl, st);
-            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, st);
-            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+                grid = launch_window_t<4, 4, 64, 1, 9>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             break;
-        case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, st); break;
+        case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 5:
             if (win_ch5 == 2 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two 6-warp CTAs, two chunks per thread
-                grid = launch_window_t<6, 4, 192, 2, 2>(ctx, B, T, k_used, r4, trace, gl, st);
-            else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, st);
+                grid = launch_window_t<6, 4, 192, 2, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
-                grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, st);
-            else if (win_ctrl5) grid = launch_window_t<6, 4, 352, 1, 1, true>(ctx, B, T, k_used, r4, trace, gl, st);
-            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, st);
+                grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (win_ctrl5) grid = launch_window_t<6, 4, 352, 1, 1, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             break;
         default: return SCG_ELIMIT;
     }
@@ -774,6 +797,8 @@ extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
     if (c->d_red) cudaFree(c->d_red);
     if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->host_ev) cudaEventDestroy(c->host_ev);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    if (c->d_ring) cudaFree(c->d_ring);
     for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);
     free(c->prof_ev);
     free(c->prof_kind);

@@ -26,23 +26,7 @@
 
 #include "scg_common.cuh"
 
-#define XCHG_SLICE 256                 // elements per CTA
-#define XCHG_HDR 32                    // per-slice header: update counts [0..15] and success counters [16..31] of the K options (int bits)
-#define XCHG_ROW (XCHG_SLICE + XCHG_HDR)
-#define XCHG_MAX_WORLD 16
-
-struct scg_xchg {
-    int rank, world, n, K, slices;
-    uint32_t seq;
-    size_t bytes, flag_bytes;
-    unsigned char *d_local;                      // [flags: world*slices u32 | status u32 x 16 | xbuf: 2*slices*XCHG_ROW f32]
-    unsigned char *d_peer[XCHG_MAX_WORLD];       // mapped bases of every rank's block (own entry = d_local)
-    bool ipc_opened[XCHG_MAX_WORLD];
-    unsigned int *d_ticket;                      // last-CTA-done counter
-    volatile uint32_t *h_status;                 // host-mapped sticky "a peer timed out" flag (written by the kernel)
-    uint32_t *d_status;                          // its device alias
-    long long timeout_cycles;                    // peer wait limit in SM clock cycles
-};
+#include "scg_xchg.cuh"
 
 struct SyncArgs {
     int n, K, slices, rank, world;
@@ -58,20 +42,6 @@ struct SyncArgs {
     size_t flag_bytes;
     unsigned char *peer[XCHG_MAX_WORLD];
 };
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_sys_f32(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
 
 template <int N1>
 __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ SyncArgs a) {
@@ -167,7 +137,8 @@ extern "C" int scg_xchg_create(scg_ctx_t *ctx, int rank, int world, scg_xchg_t *
     x->n = ctx->K * SCG_A * ctx->F;
     x->slices = (x->n + XCHG_SLICE - 1) / XCHG_SLICE;
     x->flag_bytes = (((size_t)world * x->slices + 16) * sizeof(uint32_t) + 255) & ~(size_t)255;
-    x->bytes = x->flag_bytes + (size_t)2 * x->slices * XCHG_ROW * sizeof(float);
+    x->m_off = x->flag_bytes + (size_t)2 * x->slices * XCHG_ROW * sizeof(float);
+    x->bytes = x->m_off + ((XCHG_M_BYTES + 255) & ~255);
     cudaError_t e = cudaMalloc((void **)&x->d_local, x->bytes);
     if (e == cudaSuccess) e = cudaMemset(x->d_local, 0, x->bytes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&x->d_ticket, sizeof(unsigned int));

@@ -40,3 +40,25 @@ def allreduce_scalar_sum(t, group=None):
     if world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def fit_union(grad_sum, n_local, theta0, steps, lr, group=None):
+    """Batch gradient descent of a logistic initiation classifier on the UNION of every rank's examples, without moving
+    the examples: at each step every rank computes its own gradient SUM `grad_sum(theta)` (6 values) over its `n_local`
+    examples, the sums and counts are added over ranks (one 7-value all-reduce), and every rank takes the same step
+        theta <- theta - lr * (sum over ranks of grad_sum) / (sum over ranks of n_local)
+    so all ranks end with the same theta, equal to one fit on the concatenated example sets (oracle/option.py
+    fit_initiation on the union).  Works on CUDA tensors over NCCL and CPU tensors over gloo."""
+    import torch
+    import torch.distributed as dist
+    theta = theta0.clone()
+    multi = world_size(group) > 1
+    for _ in range(int(steps)):
+        v = torch.cat([grad_sum(theta).to(torch.float32).reshape(6),
+                       torch.tensor([float(n_local)], dtype=torch.float32, device=theta.device)])
+        if multi:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        n = float(v[6])
+        if n > 0:
+            theta = theta - float(lr) * (v[:6] / n)
+    return theta

@@ -77,6 +77,73 @@ def test_two_rank_shards_equal_the_unsharded_run():
     assert (action == full.action)[same].mean() > 0.9
 
 
+def _fit_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from skill_chaining_with_graphs_b200.sync import fit_union
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, y = _examples(rank)
+    o = oracle.OptionSet(2, 1, 1)
+
+    def grad_sum(theta):                     # this rank's gradient SUM, from the oracle's mean gradient
+        if len(X) == 0:
+            return torch.zeros(6)
+        o.theta[1] = theta.numpy()
+        return torch.from_numpy(o.clf_grad(1, X, y) * np.float32(len(X)))
+
+    theta = fit_union(grad_sum, len(X), torch.zeros(6), 60, 2.0)
+    q.put((rank, theta.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _examples(rank):
+    """Rank-dependent example sets of different sizes (rank 2 of a 3-rank world has none)."""
+    n = (300, 130, 0)[rank]
+    rng = np.random.default_rng(50 + rank)
+    X = rng.random((n, 2)).astype(np.float32)
+    y = ((X[:, 0] - 0.6) ** 2 + (X[:, 1] - 0.4) ** 2 < 0.1).astype(np.uint8)
+    return X, y
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_union_fit_over_ranks_equals_the_oracle_fit_on_the_concatenated_examples(world):
+    """The multi-rank classifier fit of the controller (sync.fit_union: per-step gradient sums and counts added over
+    ranks) gives every rank the same theta, equal to oracle fit_initiation on the union of the ranks' examples - not
+    the average of per-rank fits."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_fit_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in ps), key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(1, world):
+        assert np.array_equal(res[r][1], res[0][1])                         # identical on every rank
+    X = np.concatenate([_examples(r)[0] for r in range(world)])
+    y = np.concatenate([_examples(r)[1] for r in range(world)])
+    ora = oracle.OptionSet(2, 1, 1)
+    ora.fit_initiation(1, X, y, steps=60, lr=2.0)
+    from oracle.compare import assert_close
+    assert_close(res[0][1], ora.theta[1], what="theta of the union fit")
+    avg = np.zeros(6)
+    for r in range(world):                                                   # what averaging per-rank fits would give
+        Xr, yr = _examples(r)
+        if len(Xr):
+            o = oracle.OptionSet(2, 1, 1)
+            avg += o.fit_initiation(1, Xr, yr, steps=60, lr=2.0) / world
+    assert np.abs(avg - ora.theta[1]).max() > 1e-2                           # ... is a different (wrong) answer
+
+
 def test_single_rank_is_a_no_op():
     import torch
     from skill_chaining_with_graphs_b200.sync import allreduce_deltas, world_size

@@ -349,12 +349,10 @@ def test_agent_step_matches_oracle_one_step(scg, torch, cull):
     assert_close(gag.options.dW.cpu().numpy(), oag.options.dW)
     assert_close(gag.options.trace.cpu().numpy(), oag.options.trace)
     assert out["term"].sum() > 100 and out["hit"].sum() > 10
-    for k in range(K):                                # same example multiset per option
+    for k in range(K):                                # same examples in the same ring slots (the oracle's append order)
         n = int(oag.ex_count[k])
-        ox = np.concatenate([oag.ex_xy[k, :n], oag.ex_label[k, :n, None].astype(np.float32)], axis=1)
-        gx = np.concatenate([gag.ex_xy[k, :n].cpu().numpy(),
-                             gag.ex_label[k, :n, None].cpu().numpy().astype(np.float32)], axis=1)
-        assert np.array_equal(ox[np.lexsort(ox.T)], gx[np.lexsort(gx.T)])
+        assert np.array_equal(gag.ex_xy[k, :n].cpu().numpy(), oag.ex_xy[k, :n])
+        assert np.array_equal(gag.ex_label[k, :n].cpu().numpy(), oag.ex_label[k, :n])
 
 
 def _set_gpu_options(gag, torch, theta, n_active, graph=False):
@@ -477,12 +475,216 @@ def test_agent_run_and_manage_promotes_option(scg, torch):
         ag.step()
     c = ag.counters()
     assert c["n_success"][0] >= 8 and c["goals"] >= 8
-    assert ag.manage() is True
+    assert ag.manage(wait=True) is True
     assert ag.n_active == 1 and ag.active_mask == 1 and int(ag.parents_host[1]) == 1
     for _ in range(8):
         ag.step()
     torch.cuda.synchronize()
     assert int((ag.option == 1).sum()) > 0                 # the new gestating option is being executed
+
+
+# ---- controller on the device: example rings and promote-and-fit -------------------------------------------
+@pytest.mark.parametrize("B,cap,launch", [(3000, 64, "window"), (3000, 64, "step"), (777, 4096, "window"), (40000, 1000, "window")])
+def test_example_rings_match_oracle_past_capacity(scg, torch, B, cap, launch):
+    """The rings hold the oracle's examples in the oracle's slots - steps in order, envs in order within a step - also
+    when a ring wraps several times inside one launch (cap 64, thousands of terminations per window)."""
+    from oracle_replay import activate, default_theta
+    K, n_active = 4, 2
+    kw = dict(sync_interval=1000, option_timeout=2, epsilon=0.3, alpha=0.0, max_episode_steps=7, example_capacity=cap)
+    oag, gag = _paired_agents(scg, torch, B, 2, K, "easy", 31, window=4, **kw)
+    theta = default_theta(K)
+    activate(oag, theta, n_active)
+    _set_gpu_options(gag, torch, theta, n_active)
+    for w in range(3):
+        if launch == "window":
+            pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 4)
+        else:
+            parts = [_gpu_run_window(gag, torch, 1) for _ in range(4)]
+            acts = np.concatenate([p[2][:1] for p in parts] + [parts[-1][2][1:]])
+            opts = np.concatenate([p[3][:1] for p in parts] + [parts[-1][3][1:]])
+        for t in range(4):
+            oag.step(follow=dict(action=acts[t + 1], option=opts[t + 1]))
+        assert np.array_equal(gag.ex_count.cpu().numpy(), oag.ex_count), f"window {w}"
+        assert np.array_equal(gag.ex_xy.cpu().numpy().view(np.uint32), oag.ex_xy.view(np.uint32)), f"window {w}"
+        assert np.array_equal(gag.ex_label.cpu().numpy(), oag.ex_label), f"window {w}"
+    assert oag.ex_count.max() > (3 * cap if cap < 1000 else 1000)
+    # one more step, read mid-window: the property appends the open window's events first
+    pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 1)
+    oag.step(follow=dict(action=acts[1], option=opts[1]))
+    assert np.array_equal(gag.ex_count.cpu().numpy(), oag.ex_count)
+    assert np.array_equal(gag.ex_xy.cpu().numpy().view(np.uint32), oag.ex_xy.view(np.uint32))
+    gag.run(3)                                              # and the rest of that window is appended exactly once
+    for t in range(3):
+        oag.step()
+    assert int(gag.ex_count.sum()) == int(gag.n_success.sum() + gag.n_fail.sum())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_manage_on_device_matches_oracle(scg, torch, graph):
+    """scg_agent_manage (decision + classifier fit + promotion in ONE kernel, no host round trip) against
+    oracle.manage(): same decision at the same call, theta within 1e-4, same parents / masks; below the threshold and at
+    the last slot nothing happens."""
+    from oracle_replay import activate, default_theta
+    B, K = 4096, 4
+    kw = dict(sync_interval=4, option_timeout=6, epsilon=0.3, alpha=1e-3, gestation_successes=40, clf_steps=120, clf_lr=2.0,
+              graph=graph)
+    oag, gag = _paired_agents(scg, torch, B, 2, K, "easy", 19, **kw)
+    tx, ty, tr = oag.map.target
+    rng = np.random.default_rng(0)
+    S = np.zeros((B, 4), dtype=np.float32)                 # start next to the goal so option 0 collects successes
+    S[:, 0] = tx + rng.uniform(-0.15, 0.03, B)
+    S[:, 1] = ty + rng.uniform(-0.12, 0.12, B)
+    oag.env.reset(states=S)
+    oag.start_xy = oag.env.state[:, :2].copy()
+    gag.s.copy_(torch.as_tensor(S.T.copy()))
+    gag.start_xy.copy_(torch.as_tensor(S[:, :2].copy()))
+    gag.invalidate()
+    promoted = []
+    for w in range(6):
+        pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 4)
+        for t in range(4):
+            out = oag.step(follow=dict(action=acts[t + 1], option=opts[t + 1]))
+            assert np.array_equal(out["state"].view(np.uint32), (pre[t + 1] if t < 3 else gag.state.cpu().numpy()).view(np.uint32))
+        op = oag.manage()
+        gp = gag.manage(wait=True)
+        assert op == gp, f"window {w}: oracle promoted={op}, device promoted={gp} (n_success {oag.n_success})"
+        if op:
+            promoted.append(w)
+            g = oag.n_active - 1
+            assert_close(gag.options.theta[g].cpu().numpy(), oag.options.theta[g], what=f"theta of option {g}")
+        c = gag.controller_state()
+        assert c["n_active"] == oag.n_active and c["active_mask"] == int(sum(1 << k for k in range(K) if oag.active[k]))
+        assert c["parents"] == [int(v) for v in oag.parents]
+        assert c["n_promotions"] == len(promoted)
+    assert len(promoted) >= 1, promoted
+    assert np.array_equal(gag.option.cpu().numpy(), oag.option) and np.array_equal(gag.n_success.cpu().numpy(), oag.n_success)
+    # the last slot is never promoted
+    full = scg.SkillChainAgent(scg.AgentConfig(map="easy", batch=64, order=1, max_options=2, gestation_successes=0))
+    full.n_active, full.active_mask = 1, 1
+    assert full.manage(wait=True) is False and full.controller_state()["n_active"] == 1
+
+
+def test_promotion_the_host_has_not_seen_yet_is_still_correct(scg, torch):
+    """The host sizes the on-chip weight staging and the sweep's accumulator with its LOWER BOUND of n_active; options
+    the device promoted since are handled by the kernels' global-memory paths.  A twin launched with a stale bound
+    (n_active = 0 in the struct, a context without mirror) must reproduce the run that knows: states, actions, rings
+    bit for bit; dW / W to rounding (different summation order)."""
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check, current_stream
+    from oracle_replay import default_theta
+    lib = scg.load_library()
+    for order, K, n_active in ((3, 4, 2), (5, 8, 3)):
+        B = 1500 if order == 3 else 400
+        kw = dict(sync_interval=4, option_timeout=4, epsilon=0.2, alpha=5e-3, max_episode_steps=9)
+        (_, a), (_, b) = (_paired_agents(scg, torch, B, order, K, "hard", 23, **kw) for _ in range(2))
+        theta = default_theta(K)
+        for g in (a, b):
+            _set_gpu_options(g, torch, theta, n_active)
+        a.run(12)
+        blind = scg.OptionSet(K, order, 1)                   # a second context: no mirror to learn from
+        st = b._struct
+        st.n_active = 0                                     # stale lower bound: only option 0 is staged / accumulated
+        check(lib.scg_agent_run(b.map.handle, blind.ctx, C.byref(st), 12, 4, None, current_stream()))
+        torch.cuda.synchronize()
+        assert int(st.n_active) == 0
+        assert torch.equal(a.s, b.s) and torch.equal(a.action, b.action) and torch.equal(a.option, b.option)
+        assert torch.equal(a.n_success, b.n_success) and torch.equal(a.t_opt, b.t_opt)
+        assert_close(b.options.W.cpu().numpy(), a.options.W.cpu().numpy(), rtol=1e-5, what=f"order {order}: W")
+        assert_close(b.options._trace.cpu().numpy(), a.options._trace.cpu().numpy(), rtol=1e-5, what=f"order {order}: traces")
+
+
+def _two_rank_agents_one_device(scg, torch, Bh, streams, **kw):
+    """Two half-batch agents on cuda:0 whose exchange contexts are connected through plain device pointers: the code
+    path of one process per GPU (k_sync, k_manage's peer exchange) on a single GPU, one stream per rank."""
+    import ctypes as C
+    from skill_chaining_with_graphs_b200._lib import check
+    lib = scg.load_library()
+    global FULL_B
+    saved, FULL_B = FULL_B, 2 * Bh
+    try:
+        halves, xs = [], []
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                h = _full_agent(scg, torch, Bh, r * Bh, **kw)
+            x = C.c_void_p()
+            check(lib.scg_xchg_create(h.options.ctx, r, 2, C.byref(x)))
+            halves.append(h); xs.append(x)
+        torch.cuda.synchronize()
+        _connect_ranks_one_process(lib, xs)
+        for r in range(2):
+            halves[r]._xchg = xs[r]
+        with torch.cuda.stream(streams[0]):
+            whole = _full_agent(scg, torch, 2 * Bh, 0, **kw)
+        torch.cuda.synchronize()
+        return whole, halves, xs
+    finally:
+        FULL_B = saved
+
+
+def test_two_rank_agents_on_one_device_equal_single_agent_and_union_fit(scg, torch):
+    """Row (e) and the multi-rank controller on the driver's single GPU: two ranks (streams) exchange weight deltas
+    through k_sync every sync interval and reproduce the unsharded agent; then both promote the gestating option at the
+    same manage() call with a classifier fit on the UNION of their example rings (gradient sums over peer memory):
+    theta bit-identical on both ranks and within 1e-4 of the oracle's fit on the concatenated examples."""
+    lib = scg.load_library()
+    Bh = 4096
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    kw = dict(window=0, order=3, K=4, name="hard", gestation_successes=50, clf_steps=80, clf_lr=2.0)
+    whole, halves, xs = _two_rank_agents_one_device(scg, torch, Bh, streams, **kw)
+    try:
+        for h in halves + [whole]:
+            h.cfg.sync_interval = 8
+        for it in range(3):                      # three sync intervals queued back to back on both streams
+            for r in range(2):
+                with torch.cuda.stream(streams[r]):
+                    halves[r].run(8)
+        with torch.cuda.stream(streams[0]):
+            whole.run(24)
+        torch.cuda.synchronize()
+        st = torch.cat([halves[0].s, halves[1].s], dim=1)
+        assert torch.equal(st, whole.s)
+        assert torch.equal(halves[0].options.W, halves[1].options.W) and torch.equal(halves[0].options.Wt, halves[1].options.Wt)
+        assert not halves[0].peer_sync_timed_out() and not halves[1].peer_sync_timed_out()
+        assert_close(halves[0].options.W.cpu().numpy(), whole.options.W.cpu().numpy(), rtol=1e-5, what="W: 2 ranks vs 1")
+        assert torch.equal(halves[0].n_success_global, halves[1].n_success_global)
+        assert torch.equal(halves[0].n_success_global, halves[0].n_success + halves[1].n_success)
+        # the controller: gestating option 2 (options 0, 1 are active in _full_agent) qualifies on the summed count
+        g = 2
+        assert int(halves[0].n_success_global[g]) >= 50 > 0
+        ex = [h.examples(g) for h in halves]
+        assert min(len(e[0]) for e in ex) > 0
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                halves[r].manage()
+        with torch.cuda.stream(streams[0]):
+            whole.manage()
+        torch.cuda.synchronize()
+        c0, c1, cw = (h.controller_state() for h in (halves[0], halves[1], whole))
+        assert c0 == c1 and c0["n_active"] == 3 and c0["parents"][3] == 1 << 2
+        assert cw["n_active"] == 3
+        th0, th1 = halves[0].options.theta[g].cpu().numpy(), halves[1].options.theta[g].cpu().numpy()
+        assert np.array_equal(th0.view(np.uint32), th1.view(np.uint32))          # bit-identical replicas
+        X = np.concatenate([e[0].cpu().numpy() for e in ex])
+        y = np.concatenate([e[1].cpu().numpy() for e in ex])
+        ora = oracle.OptionSet(4, 1, 1)
+        ora.fit_initiation(g, X, y, steps=80, lr=2.0)
+        assert_close(th0, ora.theta[g], what="theta: union fit over two ranks vs the oracle on the concatenated examples")
+        # (the unsharded agent has the same examples in one ring, in a different order: same fit to rounding)
+        assert_close(whole.options.theta[g].cpu().numpy(), ora.theta[g], what="theta: single agent")
+        # and the ranks keep running in step after the promotion (the new option is staged on both)
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                halves[r].run(16)
+        with torch.cuda.stream(streams[0]):
+            whole.run(16)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([halves[0].s, halves[1].s], dim=1), whole.s)
+        assert torch.equal(halves[0].options.W, halves[1].options.W)
+    finally:
+        for h in halves:
+            h._xchg = None
+        for x in xs:
+            lib.scg_xchg_destroy(x)
 
 
 # ---- windowed pipeline -------------------------------------------------------------------------------
