@@ -629,7 +629,9 @@ def test_two_rank_agents_on_one_device_equal_single_agent_and_union_fit(scg, tor
     lib = scg.load_library()
     Bh = 4096
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    kw = dict(window=0, order=3, K=4, name="hard", gestation_successes=50, clf_steps=80, clf_lr=2.0)
+    # (rings large enough not to wrap: the unsharded agent's one ring then holds the same example set as the two
+    # ranks' rings together, and more than the 8192 examples the fit kernel keeps in registers)
+    kw = dict(window=0, order=3, K=4, name="hard", gestation_successes=50, clf_steps=80, clf_lr=2.0, example_capacity=32768)
     whole, halves, xs = _two_rank_agents_one_device(scg, torch, Bh, streams, **kw)
     try:
         for h in halves + [whole]:
@@ -652,7 +654,7 @@ def test_two_rank_agents_on_one_device_equal_single_agent_and_union_fit(scg, tor
         g = 2
         assert int(halves[0].n_success_global[g]) >= 50 > 0
         ex = [h.examples(g) for h in halves]
-        assert min(len(e[0]) for e in ex) > 0
+        assert min(len(e[0]) for e in ex) > 0 and sum(len(e[0]) for e in ex) == len(whole.examples(g)[0]) < 32768
         for r in range(2):
             with torch.cuda.stream(streams[r]):
                 halves[r].manage()
