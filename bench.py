@@ -50,21 +50,35 @@ def gpu_only(args):
     return dict(sync_backend=args.sync_backend, window=args.window)
 
 
+def configs_label(args):
+    """Which BASELINE.json config this workload is (built from the arguments, not assumed)."""
+    graph = bool(getattr(args, "graph", False))
+    if args.map == "easy" and args.order == 3 and args.options == 4 and args.batch == 65536 and not graph:
+        return "configs[1]"
+    if args.map == "hard" and args.order == 5 and args.options == 8 and args.batch == 131072:
+        return "configs[4] (option-graph variant of configs[2])" if graph else "configs[2] per-GPU shape"
+    return "custom" + (" (option-graph variant)" if graph else "")
+
+
 def config_json(args, n_gpus):
     F = (args.order + 1) ** 4
+    T = args.window or min(args.sync_interval, 8)
     return {
-        "workload": f"configs[{4 if getattr(args, 'graph', False) else 1}]{' option-graph variant' if getattr(args, 'graph', False) else ''}: "
-                    f"Pinball '{args.map}', {args.batch} envs per GPU, order-{args.order} Fourier "
-                    f"(F={F}), {args.options} option slots (2 active initiation classifiers), "
-                    f"sync every {args.sync_interval} steps",
-        "controller": f"SkillChainAgent.manage() every {MANAGE_EVERY} steps inside the timed region",
+        "workload": f"{configs_label(args)}: Pinball '{args.map}', {args.batch} envs per GPU, order-{args.order} Fourier "
+                    f"(F={F}), {args.options} option slots ({N_PRESET_ACTIVE} preset active initiation classifiers, the "
+                    f"controller promotes further ones), sync every {args.sync_interval} steps",
+        "controller": f"SkillChainAgent.manage() every {MANAGE_EVERY} steps inside the timed region (one kernel on the "
+                      "stream: decision, classifier fit and promotion on the device)",
         "envs_per_gpu": args.batch, "global_envs": args.batch * n_gpus, "order": args.order,
         "options": args.options, "sync_interval": args.sync_interval, "map": args.map,
         "parallelism": f"env-sharded x{n_gpus}, sum of (dW, cnt) over ranks every sync interval "
                        f"({'one NVLink peer-memory exchange+apply kernel' if getattr(args, 'sync_backend', 'p2p') == 'p2p' else 'NCCL all-reduce'})",
-        "l2": f"traces {args.batch * 5 * F * 4 / 2**20:.0f} MiB per GPU > 126 MiB L2, swept once per window between 8 "
-              "step kernels (inputs larger than L2; no explicit flush)",
+        "l2": f"traces {args.batch * 5 * F * 4 / 2**20:.0f} MiB per GPU > 126 MiB L2, swept once per {T}-step window "
+              "(inputs larger than L2; no explicit flush)",
     }
+
+
+N_PRESET_ACTIVE = 2
 
 
 def setup_classifiers(theta):
@@ -127,8 +141,8 @@ def _cpu_worker(wl, batch, steps, seed, q, warmup=1):
     ag.env.reset(states=ag.map.sample_free_states(rng, batch))
     ag.options.W[:] = (rng.standard_normal(ag.options.W.shape) * 0.1).astype(np.float32)
     setup_classifiers(ag.options.theta)
-    ag.active[:2] = True
-    ag.n_active = 2
+    ag.active[:N_PRESET_ACTIVE] = True
+    ag.n_active = N_PRESET_ACTIVE
     ag.parents[1], ag.parents[2] = (np.uint32(1 | (1 << 31)), np.uint32(3 | (1 << 31))) if wl.get("graph") else (1, 2)
     for _ in range(max(warmup, 1)):             # untimed warm-up
         ag.step()
@@ -190,6 +204,75 @@ def run_reference(args):
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------
+def k3_traffic(order, batch, T):
+    """ncu dram bytes per k_window launch for this (order, envs, window) if a capture of it is committed, else None."""
+    path = os.path.join(ROOT, "profiles", "k3_traffic.json")
+    try:
+        tj = json.load(open(path))
+    except Exception:
+        return None
+    for e in (tj if isinstance(tj, list) else [tj]):
+        if e.get("kernel") == "k_window" and e.get("order", 3) == order and e.get("envs", 65536) == batch and \
+                e.get("window_steps", 8) == T:
+            return e.get("dram_bytes_per_launch")
+    return None
+
+
+def make_agent(scg, torch, args, rank, world):
+    """The bench agent: random free-space start states, random-init weights (the same on every rank), two preset
+    active initiation classifiers, the third option gestating."""
+    B = args.batch
+    gmap = scg.PinballMap.from_name(args.map)
+    rng = np.random.default_rng(1234 + rank)
+    S = gmap.sample_free_states(rng, B)
+    cfg = scg.AgentConfig(**workload(args), env_offset=rank * B, **gpu_only(args))
+    ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
+    wrng = np.random.default_rng(7)
+    ag.options.set_weights((wrng.standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32))
+    theta = np.zeros((args.options, 6), dtype=np.float32)
+    setup_classifiers(theta)
+    ag.options.theta.copy_(torch.as_tensor(theta))
+    ag.active_mask, ag.n_active = (1 << N_PRESET_ACTIVE) - 1, N_PRESET_ACTIVE
+    GOAL = 1 << 31
+    ag.parents_host[1], ag.parents_host[2] = (1 | GOAL, 3 | GOAL) if args.graph else (1, 2)
+    ag._push_parents()
+    return ag
+
+
+def timed_blocks(torch, ag, steps, n_blocks, barrier, t_done):
+    """`n_blocks` consecutive blocks of exactly `steps` agent steps each, device-resident, CUDA events at the block
+    boundaries (windows, syncs and the controller's cadence run on across blocks: a block is a slice of the steady
+    state, whatever `steps` is).  Returns per-block milliseconds and the global step counter."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_blocks + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(n_blocks):
+        left = steps
+        while left > 0:                                         # full skill chaining: steps + the controller
+            k = min(left, MANAGE_EVERY - t_done % MANAGE_EVERY)
+            ag.run(k)
+            t_done += k
+            left -= k
+            if t_done % MANAGE_EVERY == 0:
+                ag.manage()
+        if i == n_blocks - 1:
+            ag.flush()                                          # a partial last window is swept inside the timed region
+        ev[i + 1].record()
+    barrier()
+    return [ev[i].elapsed_time(ev[i + 1]) for i in range(n_blocks)], t_done
+
+
+def stage_pass(torch, ag, T, n_windows=8):
+    """Untimed-by-the-headline side pass: CUDA events around every launch kind (costs ~5 us per step, so it is not done
+    in the timed region): -> (ms per launch, launches) for [fused step, sweep, dW reduction, apply / exchange]."""
+    n_side = n_windows * T
+    ag.profile_begin(6 * n_side + 16, kinds=(0, 1, 2, 3))
+    ag.run(n_side)
+    torch.cuda.synchronize()
+    ms, n = ag.profile_end()
+    return [ms[k] / n[k] if n[k] else 0.0 for k in range(4)], n, n_side
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -206,152 +289,197 @@ def run_ours(args):
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = scg.load_library()
-    wl = workload(args)
-    B = args.batch
-    gmap = scg.PinballMap.from_name(args.map)
-    rng = np.random.default_rng(1234 + rank)
-    S = gmap.sample_free_states(rng, B)
-    cfg = scg.AgentConfig(**wl, env_offset=rank * B, **gpu_only(args))
-    ag = scg.SkillChainAgent(cfg, gmap, initial_states=S)
-    if world > 1 and args.sync_backend == "p2p" and ag._xchg is None:
-        args.sync_backend = "nccl"                      # the agent fell back (it said why on stderr): report what ran
-    wrng = np.random.default_rng(7)                     # same weights on every rank
-    ag.options.set_weights((wrng.standard_normal(tuple(ag.options.W.shape)) * 0.1).astype(np.float32))
-    theta = np.zeros((args.options, 6), dtype=np.float32)
-    setup_classifiers(theta)
-    ag.options.theta.copy_(torch.as_tensor(theta))
-    ag.active_mask, ag.n_active = 3, 2
-    GOAL = 1 << 31
-    ag.parents_host[1], ag.parents_host[2] = (1 | GOAL, 3 | GOAL) if args.graph else (1, 2)
-    ag._push_parents()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_warm = max(args.warmup, 16)            # at least two windows, so the gestating option has qualified by the end
-    ag.run(n_warm)
-    ag.warm_up_controller()
-    ag.manage()              # with these classifiers the gestating option qualifies within the warm-up: promote it here
-    barrier()
+    def reduce_max(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def measure(a, steps, n_blocks, n_warm, live_kind=True):
+        """Warm up, then time n_blocks blocks of `steps` steps -> dict of per-rank-max block times and kernel timings."""
+        ag = make_agent(scg, torch, a, rank, world)
+        backend = a.sync_backend
+        if world > 1 and a.sync_backend == "p2p" and ag._xchg is None:
+            backend = "nccl"                                   # the agent fell back (it said why on stderr): report what ran
+        B, T = a.batch, ag.win_cap
+        ag.warm_up_controller()
+        t_done = 0
+        for lo in range(0, n_warm, MANAGE_EVERY):
+            k = min(MANAGE_EVERY, n_warm - lo)
+            ag.run(k)
+            t_done += k
+        t_done = 0                                              # the controller's cadence counts from the timed region
+        ag.manage()                                             # the preset gestating option qualifies within the warm-up
+        barrier()
+        launches0 = lib.scg_launch_count()
+        if live_kind:
+            ag.profile_begin(n_blocks * steps + 64, kinds=(1,))    # events around the dominant kernel only, live
+        blocks, t_done = timed_blocks(torch, ag, steps, n_blocks, barrier, t_done)
+        live_ms, live_n = ag.profile_end() if live_kind else ([0.0] * 4, [0] * 4)
+        launches = lib.scg_launch_count() - launches0
+        blocks = reduce_max(blocks)                             # per block: the slowest rank
+        side_ms, side_n, n_side = stage_pass(torch, ag, T)
+        if ag.peer_sync_timed_out():
+            raise scg.ScgError("a cross-GPU weight exchange timed out during the bench: no valid number")
+        med = float(np.median(blocks))
+        k3_ms = live_ms[1] / live_n[1] if live_n[1] else side_ms[1]
+        return dict(ag=ag, backend=backend, blocks=blocks, ms_block=med, ms_per_step=med / steps, k3_ms=k3_ms,
+                    k3_launches=live_n[1], side_ms=side_ms, side_n=side_n, n_side=n_side, launches=launches,
+                    ctl=ag.controller_state(sync=True))
+
+    n_warm = max(args.warmup, 16)          # at least two windows, so the preset gestating option has qualified by the end
+    n_blocks = args.blocks or max(3, -(-1024 // max(args.steps, 1)))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region: exactly K steps, device-resident ----
-    launches0 = lib.scg_launch_count()
-    # CUDA events around the dominant kernel (the window sweep), live in the timed region.  Events around every launch
-    # would cost ~5 us per step here (each record is a stream operation between back-to-back kernels): the other
-    # stages are timed in a short separate pass below.
-    ag.profile_begin(args.steps + 16, kinds=(1,))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for lo in range(0, args.steps, MANAGE_EVERY):               # full skill chaining: steps + the controller
-        ag.run(min(MANAGE_EVERY, args.steps - lo))
-        ag.manage()
-    ag.flush()                                                  # a partial last window is swept inside the timed region too
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    kind_ms, kind_n = ag.profile_end()
-    launches = lib.scg_launch_count() - launches0
-    n_side = 8 * max(args.sync_interval, ag.win_cap)
-    ag.profile_begin(4 * n_side + 16, kinds=(0, 2, 3))          # untimed side pass: step kernel, reduction, apply / exchange
-    ag.run(n_side)
-    torch.cuda.synchronize()
-    side_ms, side_n = ag.profile_end()
-    for k in (0, 2, 3):
-        kind_ms[k], kind_n[k] = side_ms[k] * args.steps / n_side, side_n[k] * args.steps // n_side
-    # ---- e2e: same K steps through the host-buffer API ----
+    m = measure(args, args.steps, n_blocks, n_warm)
+    ag, B, T = m["ag"], args.batch, m["ag"].win_cap
+    args.sync_backend = m["backend"]
+    # ---- e2e: the same K-step blocks through the host-buffer API ----
+    def e2e_blocks(step_fn, n_b):
+        out = []
+        for _ in range(n_b):
+            barrier()
+            t0 = time.perf_counter()
+            step_fn()
+            torch.cuda.synchronize()
+            out.append((time.perf_counter() - t0) * 1e3)
+        return reduce_max(out)
+
     hs = ag.s.cpu().numpy().copy()
     ha = ag.action.cpu().numpy().copy()
+    host = dict(s=hs, a=ha, i=0)
+
+    def host_steps():
+        for _ in range(args.steps):
+            s2, r, f, a2, d = ag.step_host(host["s"], host["a"])
+            host["s"], host["a"] = s2, a2                       # views of the pinned result buffers, fed straight back
+            host["i"] += 1
+            if host["i"] % MANAGE_EVERY == 0:
+                ag.manage()
+
     for _ in range(3):
-        s2, r, f, a2, d = ag.step_host(hs, ha)
-        hs, ha = s2, a2
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        s2, r, f, a2, d = ag.step_host(hs, ha)
-        hs, ha = s2, a2                              # views of the pinned result buffers, fed straight back
-        if (i + 1) % MANAGE_EVERY == 0:
-            ag.manage()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+        host["s"], r, f, host["a"], d = ag.step_host(host["s"], host["a"])
+    n_e2e = max(3, min(n_blocks, -(-256 // max(args.steps, 1))))
+    e2e = e2e_blocks(host_steps, n_e2e)
+    e2e_ms = float(np.median(e2e))
     # informational: the same loop for a caller that needs the state only once per sync interval (run_host)
-    T = args.sync_interval
-    hs, ha = ag.s.cpu().numpy().copy(), ag.action.cpu().numpy().copy()
-    for _ in range(2):
-        hs, ha, r, f, d = ag.run_host(hs, ha, T)
-    barrier()
-    t0 = time.perf_counter()
-    n_calls = max(args.steps // T, 1)
-    for _ in range(n_calls):
-        hs, ha, r, f, d = ag.run_host(hs, ha, T)
-    torch.cuda.synchronize()
-    e2e_win_ms = (time.perf_counter() - t0) * 1e3
+    Ts = args.sync_interval
+    hw = dict(s=ag.s.cpu().numpy().copy(), a=ag.action.cpu().numpy().copy())
+    n_calls = max(args.steps // Ts, 1)
+
+    def host_windows():
+        for _ in range(n_calls):
+            hw["s"], hw["a"], r, f, d = ag.run_host(hw["s"], hw["a"], Ts)
+
+    host_windows()
+    e2e_win_ms = float(np.median(e2e_blocks(host_windows, 3)))
     clocks = sampler.stop() if rank == 0 else None
+    # ---- cross-GPU sync: the peer-memory kernel against two NCCL all-reduces + apply on the same payload ----
+    sync_cmp = None
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, e2e_win_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, e2e_win_ms = float(t[0]), float(t[1]), float(t[2])
+        from skill_chaining_with_graphs_b200.sync import allreduce_deltas
+        o = ag.options
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 50
+        for i in range(reps + 5):
+            if i == 5:
+                barrier()
+                ev[0].record()
+            allreduce_deltas(o._dW, o.cnt, ag.pg)
+            o.apply()
+        ev[1].record()
+        torch.cuda.synchronize()
+        nccl_us = reduce_max([ev[0].elapsed_time(ev[1]) / reps * 1e3])[0]
+        sync_cmp = {"p2p_kernel_us": reduce_max([m["side_ms"][3] * 1e3])[0] if m["backend"] == "p2p" else None,
+                    "nccl_allreduce_x2_plus_apply_us": nccl_us, "payload_bytes": int(o._dW.numel() * 4 + o.cnt.numel() * 4),
+                    "note": "per sync, max over ranks; the p2p figure includes the wait for the slowest rank to arrive"}
+    # ---- the north-star configuration, in the same process, at every N ----
+    north = None
+    if not args.no_north_star and configs_label(args) == "configs[1]":
+        del ag, m["ag"]
+        torch.cuda.empty_cache()
+        na = argparse.Namespace(**vars(args))
+        na.map, na.order, na.options, na.batch, na.window = "hard", 5, 8, 131072, 0
+        nm = measure(na, 64, 5, 16)
+        F5 = 6 ** 4
+        nb = 8 * 5 * F5 + 32 * nm["ag"].win_cap
+        north = {"workload": config_json(na, world)["workload"], "value": na.batch * world * 64 / (nm["ms_block"] * 1e-3),
+                 "unit": UNIT, "ms_per_step": nm["ms_per_step"], "steps_per_block": 64, "blocks_ms": nm["blocks"],
+                 "n_active_end": nm["ctl"]["n_active"],
+                 "k_window": {"avg_launch_ms": nm["k3_ms"], "achieved_gbs": na.batch * nb / (nm["k3_ms"] * 1e-3) / 1e9 if nm["k3_ms"] else None,
+                              "algorithmic_bytes_per_launch": na.batch * nb},
+                 "stages_ms_per_launch": {"fused_step": nm["side_ms"][0], "k3_window_sweep": nm["side_ms"][1],
+                                          "dw_reduce": nm["side_ms"][2], "apply_or_exchange": nm["side_ms"][3]}}
+        del nm
     if rank == 0:
         F = (args.order + 1) ** 4
         total_env_steps = B * world * args.steps
-        value = total_env_steps / (ms * 1e-3)
+        value = total_env_steps / (m["ms_block"] * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-        T = ag.win_cap
         bytes_per_env = 8 * 5 * F + 32 * T              # trace read + write once per window, T 32-byte records
-        avg = lambda k: kind_ms[k] / kind_n[k] if kind_n[k] else 0.0
-        k3_ms = avg(1)
+        k3_ms = m["k3_ms"]
         achieved = B * bytes_per_env / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-        tot_ms = sum(kind_ms)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                traffic = tj.get("dram_bytes_per_launch") if tj.get("kernel") == "k_window" else None
-            except Exception:
-                traffic = None
+        side, side_n, n_side = m["side_ms"], m["side_n"], m["n_side"]
+        per_step = [side[k] * side_n[k] / n_side for k in range(4)]     # ms per agent step of each stage (side pass)
+        per_step[1] = k3_ms * (side_n[1] / n_side)                      # the sweep: its live timing
+        tot = sum(per_step)
+        if north is not None:
+            north["k_window"]["frac_of_hbm_peak"] = (north["k_window"]["achieved_gbs"] or 0.0) / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_json(args, world),
+            "timed_region": {"blocks": len(m["blocks"]), "steps_per_block": args.steps, "block_ms_median": m["ms_block"],
+                             "block_ms_min": min(m["blocks"]), "block_ms_max": max(m["blocks"]),
+                             "warmup_steps_run": n_warm,
+                             "note": "value = steps of one block / median block time; blocks are consecutive slices of the "
+                                     "steady state (windows, syncs and the controller cadence run on across them), each "
+                                     "bracketed by CUDA events, max over ranks per block"},
             "roofline": {"kernel": "k_window (K3 Sarsa(lambda) trace sweep, forward-view window form)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": k3_traffic(args.order, B, T),
                          "peak_source": which, "algorithmic_bytes_per_launch": B * bytes_per_env,
                          "bytes_per_env_step": bytes_per_env / T, "window_steps": T,
-                         "avg_launch_ms": k3_ms, "launches": kind_n[1],
-                         "share_of_step": (kind_ms[1] / tot_ms) if tot_ms else None},
-            "stages_ms_per_step": {"fused_step_k1_k2_k4": kind_ms[0] / args.steps, "k3_window_sweep": kind_ms[1] / args.steps,
-                                   "dw_reduce": kind_ms[2] / args.steps, "apply": kind_ms[3] / args.steps,
-                                   "fused_step_avg_launch_ms": avg(0), "steps_per_fused_launch": args.sync_interval,
+                         "avg_launch_ms": k3_ms, "launches": m["k3_launches"],
+                         "share_of_step": (per_step[1] / tot) if tot else None},
+            "stages_ms_per_step": {"fused_step_k1_k2_k4": per_step[0], "k3_window_sweep": per_step[1],
+                                   "dw_reduce": per_step[2], "apply": per_step[3],
+                                   "fused_step_avg_launch_ms": side[0], "steps_per_fused_launch": n_side / max(side_n[0], 1),
                                    "note": "k3_window_sweep timed live in the timed region; the other stages in a separate "
                                            f"{n_side}-step pass (events around every launch cost ~5 us per step)"},
             # north_star also asks for the FP32 view of the feature + Q part (K2): 18 F flop per env-step, counted
             # against the nominal FP32 FMA rate at the maximum SM clock (148 SMs x 128 lanes x 2 flop)
             "k2_fp32": {"kernel": "k_agent_step (K1+K2+K4; only K2's 18*F flop per env-step are counted)",
-                        "flop_per_env_step": 18 * F, "achieved_tflops": B * 18 * F / (kind_ms[0] / args.steps * 1e-3) / 1e12
-                        if kind_ms[0] > 0 else None, "peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12},
+                        "flop_per_env_step": 18 * F, "achieved_tflops": B * 18 * F / (per_step[0] * 1e-3) / 1e12
+                        if per_step[0] > 0 else None, "peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12},
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": B * ag.HOST_H2D_BYTES_PER_ENV,
-                    "d2h_bytes_per_step": B * ag.HOST_D2H_BYTES_PER_ENV,
+                    "h2d_bytes_per_step": B * scg.SkillChainAgent.HOST_H2D_BYTES_PER_ENV,
+                    "d2h_bytes_per_step": B * scg.SkillChainAgent.HOST_D2H_BYTES_PER_ENV,
+                    "blocks_ms": e2e,
                     "api": "SkillChainAgent.step_host -> scg_agent_step_host (pinned host buffers)"},
-            "e2e_per_sync_interval": {"value": B * world * n_calls * T / (e2e_win_ms * 1e-3), "unit": UNIT,
-                                      "h2d_bytes_per_call": B * 20, "d2h_bytes_per_call": B * 32, "steps_per_call": T,
+            "e2e_per_sync_interval": {"value": B * world * n_calls * Ts / (e2e_win_ms * 1e-3), "unit": UNIT,
+                                      "h2d_bytes_per_call": B * 20, "d2h_bytes_per_call": B * 32, "steps_per_call": Ts,
                                       "api": "SkillChainAgent.run_host: host state in / out once per sync interval "
                                              "(informational; `e2e` above copies every step)"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "controller_state_end": m["ctl"], "sync": sync_cmp, "north_star_config": north,
+            "gpu_launches": int(m["launches"]), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
             cores = max(1, len(os.sched_getaffinity(0)))
-            rate, wall = cpu_oracle_rate(wl, args.cpu_batch, args.cpu_steps, cores)
+            rate, wall = cpu_oracle_rate(workload(args), args.cpu_batch, args.cpu_steps, cores)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"NumPy oracle SkillChainAgent.step, {args.cpu_batch} envs x {args.cpu_steps} steps of the "
@@ -378,6 +506,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--window", type=int, default=0, help="steps per trace sweep (0 = min(sync interval, 8))")
+    ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps (0 = enough for ~1024 steps, at least 3)")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the extra configs[2]-shape measurement")
     ap.add_argument("--graph", action="store_true", help="option-graph variant (configs[4]): an option's targets are the "
                     "initiation sets of ALL earlier options and the goal, so chains merge")
     args = ap.parse_args()
