@@ -266,11 +266,12 @@ def stage_pass(torch, ag, T, n_windows=8):
     """Untimed-by-the-headline side pass: CUDA events around every launch kind (costs ~5 us per step, so it is not done
     in the timed region): -> (ms per launch, launches) for [fused step, sweep, dW reduction, apply / exchange]."""
     n_side = n_windows * T
-    ag.profile_begin(6 * n_side + 16, kinds=(0, 1, 2, 3))
+    ag.profile_begin(8 * n_side + 16, kinds=(0, 1, 2, 3, 4, 5))
     ag.run(n_side)
+    ag.manage()
     torch.cuda.synchronize()
     ms, n = ag.profile_end()
-    return [ms[k] / n[k] if n[k] else 0.0 for k in range(4)], n, n_side
+    return [ms[k] / n[k] if n[k] else 0.0 for k in range(len(ms))], n, n_side
 
 
 def run_ours(args):
@@ -322,7 +323,7 @@ def run_ours(args):
         if live_kind:
             ag.profile_begin(n_blocks * steps + 64, kinds=(1,))    # events around the dominant kernel only, live
         blocks, t_done = timed_blocks(torch, ag, steps, n_blocks, barrier, t_done)
-        live_ms, live_n = ag.profile_end() if live_kind else ([0.0] * 4, [0] * 4)
+        live_ms, live_n = ag.profile_end() if live_kind else ([0.0] * 6, [0] * 6)
         launches = lib.scg_launch_count() - launches0
         blocks = reduce_max(blocks)                             # per block: the slowest rank
         side_ms, side_n, n_side = stage_pass(torch, ag, T)
@@ -417,7 +418,8 @@ def run_ours(args):
                  "k_window": {"avg_launch_ms": nm["k3_ms"], "achieved_gbs": na.batch * nb / (nm["k3_ms"] * 1e-3) / 1e9 if nm["k3_ms"] else None,
                               "algorithmic_bytes_per_launch": na.batch * nb},
                  "stages_ms_per_launch": {"fused_step": nm["side_ms"][0], "k3_window_sweep": nm["side_ms"][1],
-                                          "dw_reduce": nm["side_ms"][2], "apply_or_exchange": nm["side_ms"][3]}}
+                                          "dw_reduce": nm["side_ms"][2], "apply_or_exchange": nm["side_ms"][3],
+                                          "example_ring_pass": nm["side_ms"][4], "controller": nm["side_ms"][5]}}
         del nm
     if rank == 0:
         F = (args.order + 1) ** 4
@@ -457,6 +459,8 @@ def run_ours(args):
                          "share_of_step": (per_step[1] / tot) if tot else None},
             "stages_ms_per_step": {"fused_step_k1_k2_k4": per_step[0], "k3_window_sweep": per_step[1],
                                    "dw_reduce": per_step[2], "apply": per_step[3],
+                                   "example_ring_pass": side[4] * side_n[4] / n_side,
+                                   "controller_kernel_ms_per_launch": side[5],
                                    "fused_step_avg_launch_ms": side[0], "steps_per_fused_launch": n_side / max(side_n[0], 1),
                                    "note": "k3_window_sweep timed live in the timed region; the other stages in a separate "
                                            f"{n_side}-step pass (events around every launch cost ~5 us per step)"},

@@ -43,6 +43,7 @@ extern "C" {
 #define SCG_STREAM_ACTION 0
 #define SCG_STREAM_RESET 1
 #define SCG_STREAM_RESELECT 2
+#define SCG_STREAM_TOP 3
 
 #define SCG_EINVAL (-1)   /* bad argument */
 #define SCG_ENOMEM (-2)   /* host allocation failed */
@@ -115,6 +116,10 @@ int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const float *y, cons
                      float *trace, float *dW, int *cnt, void *stream);
 int scg_apply(int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
               int window_steps, void *stream);
+/* same with the top-level learner's slots (oracle/option.py OptionSet(top_slots=...)): slots K_opt .. K-1 are stepped
+ * with alpha_top and the mean over the window's events (cnt[k] = event count) instead of alpha * steps / cnt[k] */
+int scg_apply_top(int order, int K, int K_opt, float *W, float *Wt, float *dW, int *cnt, float alpha,
+                  float alpha_top, int window_steps, void *stream);
 
 /* ---- K4: initiation classifiers --------------------------------------------------------------
  * mirrors oracle/option.py OptionSet.initiation_prob / clf_grad / fit_initiation. */
@@ -159,11 +164,16 @@ typedef struct scg_agent {
     float alpha; int32_t window_steps, win_cap, win_len;
     int32_t ring_len;                /* slabs of the open window whose option terminations are already in the example rings */
     int32_t gestation_successes, clf_steps; float clf_lr;   /* controller: promotion threshold, classifier fit */
+    int32_t top_slots;               /* 0: options are chosen "first active initiation set"; n = ceil(K / 5): by the top-level
+                                        SMDP learner whose weights are slots K .. K+n-1 of W / Wt / dW / cnt (K + n <= 16) */
+    float alpha_top, epsilon_top; int32_t reserved0;
     /* per-env state (device) */
     float *x, *y, *vx, *vy;          /* current state s */
     float *x2, *y2, *vx2, *vy2;      /* the other state buffer: a step writes s' here, then the two swap */
     int32_t *action, *option, *t_opt, *ep_steps;
     float *start_xy;                 /* [B][2] position where the current option execution began */
+    float *start_vxy;                /* [B][2] velocity there; opt_ret [B] discounted task reward since, opt_disc [B] gamma^steps */
+    float *opt_ret, *opt_disc;       /*   (top-level learner only; may be NULL when top_slots == 0) */
     float *ep_return;                /* [B] running task return */
     int32_t *ep_count;               /* [B] finished episodes of each env */
     float *last_return;              /* [B] task return of each env's last finished episode */
@@ -172,6 +182,8 @@ typedef struct scg_agent {
     float *q_carry;                  /* [B] Q_o(s, a) of the pending (state, action), valid iff carry_valid */
     float *win_rec;                  /* [win_cap][B][8] step records of the open window */
     uint8_t *win_ev;                 /* [win_cap][B] option-termination events of the open window (0 = none) */
+    float *win_top;                  /* [win_cap][B][8] top-level SMDP updates of the open window, valid where win_ev says
+                                        "terminated": s0 (4), delta_top, option bits (top_slots > 0 only) */
     float *trace;                    /* [B][A][F], as of the last flush */
     /* per-option state (device) */
     float *W, *Wt, *theta, *dW;      /* [K][A][F], [F][K][8], [K][6], [K][A][F] */
@@ -242,6 +254,10 @@ int scg_xchg_set_timeout(scg_xchg_t *x, double seconds);
  * Every rank must call it the same number of times. */
 int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
                   int window_steps, const int *nsucc_local, int *nsucc_global, void *stream);
+/* same with top-level learner slots K_opt .. K-1 (see scg_apply_top) */
+int scg_xchg_sync_top(scg_xchg_t *x, int order, int K, int K_opt, float *W, float *Wt, float *dW, int *cnt,
+                      float alpha, float alpha_top, int window_steps, const int *nsucc_local, int *nsucc_global,
+                      void *stream);
 
 /* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
  * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]
@@ -256,8 +272,9 @@ int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag,
  * scg_profile_end waits for the recorded events and returns, per kind, the summed milliseconds and the
  * launch count: kind 0 fused step kernel, 1 window trace sweep, 2 dW reduction, 3 weight apply / exchange.
  * (Events around the step kernels - bit 0 - keep consecutive step kernels from overlapping their prologues.) */
+#define SCG_PROF_KINDS 6   /* 0 fused step, 1 window sweep, 2 dW reduction, 3 apply / exchange, 4 example-ring pass, 5 controller */
 int scg_profile_begin(scg_ctx_t *ctx, int max_events, int kind_mask);
-int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [4] */, int *count /* HOST [4] */);
+int scg_profile_end(scg_ctx_t *ctx, float *ms /* HOST [SCG_PROF_KINDS] */, int *count /* HOST [SCG_PROF_KINDS] */);
 
 /* kernel launch counter (this library's launches since load), for bench.py's gpu_launches */
 uint64_t scg_launch_count(void);

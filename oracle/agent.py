@@ -31,6 +31,19 @@ One agent step t, for every env (this is the definition the fused GPU pipeline m
                  a' = eps-greedy(Q_o'(s_next, .); Philox(seed; env, t, STREAM_RESELECT))
      else:       o' = o, a' = a2
   9. every sync_interval steps: OptionSet.apply()
+Top-level SMDP learner (AgentConfig.top_level=True; SURVEY.md section 8 f-3 - the paper's agent learns which option to
+run): Q_top(s, j) over the option slots j, linear in the same Fourier features, stored in extra slots of the OptionSet's
+weight tables (oracle/option.py).  The admissible set at s is A(s) = {active k with I_k(s)} + {the gestating slot g}
+(g's initiation set is everywhere: it is the flat learner through which the primitive actions stay reachable).
+  * per env, since its option o started at s0:  R += disc * r_env;  disc *= gamma   (task reward, no option bonus)
+  * at step 8 (option terminated), BEFORE re-selection, with s2 the state the step reached (before any reset):
+        target    = R + (0 if the episode ended or timed out else disc * max_{j in A(s2)} Q_top(s2, j))
+        delta_top = target - Q_top(s0, o)
+        dW[top slot of o] += delta_top * phi(s0);   cnt[top slots] += 1        (applied with alpha_top, mean over events)
+  * re-selection: o' = eps_top-greedy over A(s_next) of Q_top(s_next, .): with (u0, u1) = Philox(seed; env, t, STREAM_TOP),
+        explore iff u0 < epsilon_top: the min(int(u1 * |A|), |A| - 1)-th admissible slot in ascending order; otherwise the
+        first admissible slot with the maximal value.  With zero top-level weights this is the "first active" rule above.
+
 manage() is the low-rate controller: when the gestating option has collected enough successes its
 classifier is fit on its examples, it becomes active and the next slot starts gestating.
 """
@@ -39,7 +52,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .option import OptionSet, epsilon_greedy
-from .philox import STREAM_ACTION
+from .philox import STREAM_ACTION, STREAM_TOP, draws, uniform01
 from .pinball import PinballEnv, PinballMap
 
 f32 = np.float32
@@ -69,6 +82,9 @@ class AgentConfig:
     clf_lr: float = 1.0
     graph: bool = False
     windowed: bool = False      # Sarsa(lambda) in the forward-view window form (OptionSet.flush) instead of the dense sweep
+    top_level: bool = False     # option choice by the learned SMDP value function Q_top instead of "first active"
+    alpha_top: float = 1e-3
+    epsilon_top: float = 0.05
 
 
 class SkillChainAgent:
@@ -78,7 +94,8 @@ class SkillChainAgent:
         B, K = cfg.batch, cfg.max_options
         self.env = PinballEnv(self.map, B, seed=cfg.seed, env_offset=cfg.env_offset)
         self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon,
-                                 cfg.seed, cfg.env_offset, windowed=cfg.windowed)
+                                 cfg.seed, cfg.env_offset, windowed=cfg.windowed,
+                                 top_slots=(-(-K // 5) if cfg.top_level else 0), alpha_top=cfg.alpha_top)
         self.active = np.zeros(K, dtype=bool)
         self.parents = np.zeros(K, dtype=np.uint32)
         self.parents[0] = GOAL_BIT
@@ -88,6 +105,10 @@ class SkillChainAgent:
         self.t_opt = np.zeros(B, dtype=np.int32)
         self.ep_steps = np.zeros(B, dtype=np.int32)
         self.start_xy = self.env.state[:, :2].copy()
+        self.opt_s0 = self.env.state.copy()              # top-level learner: state where the current option started,
+        self.opt_R = np.zeros(B, dtype=np.float32)       # discounted task reward since then,
+        self.opt_disc = np.ones(B, dtype=np.float32)     # and gamma^(steps since then)
+        self.last_delta_top = np.zeros(B, dtype=np.float32)
         self.ex_xy = np.zeros((K, cfg.example_capacity, 2), dtype=np.float32)
         self.ex_label = np.zeros((K, cfg.example_capacity), dtype=np.uint8)
         self.ex_count = np.zeros(K, dtype=np.int64)
@@ -106,6 +127,23 @@ class SkillChainAgent:
         I = self.options.initiation(state) & self.active[None, :]
         w = (np.uint32(1) << np.arange(self.options.K, dtype=np.uint32))[None, :]
         return (I * w).sum(axis=1).astype(np.uint32)
+
+    def choose_option_top(self, bits, state, t):
+        """eps_top-greedy over the admissible slots of Q_top(state, .) (module docstring).  -> (choice, Q_top rows)"""
+        K = self.options.K
+        g = min(self.n_active, K - 1)
+        adm = ((bits[:, None] >> np.arange(K, dtype=np.uint32)[None, :]) & np.uint32(1)).astype(bool)
+        adm[:, g] = True
+        Qt = self.options.q_top(state)
+        masked = np.where(adm, Qt, -np.inf)
+        greedy = np.argmax(masked, axis=1).astype(np.int32)                # first admissible maximum
+        r = draws(self.cfg.seed, self.options.env_ids, t, STREAM_TOP)
+        u0, u1 = uniform01(r[:, 0]), uniform01(r[:, 1])
+        n_adm = adm.sum(axis=1).astype(np.int32)
+        pick = np.minimum((u1 * n_adm.astype(np.float32)).astype(np.int32), n_adm - 1)
+        rank = np.cumsum(adm, axis=1) - 1                                  # rank of each admissible slot
+        rand = np.argmax(adm & (rank == pick[:, None]), axis=1).astype(np.int32)
+        return np.where(u0 < f32(self.cfg.epsilon_top), rand, greedy).astype(np.int32), Qt, adm
 
     def choose_option(self, bits):
         """First active option whose initiation set holds, else the gestating slot."""
@@ -148,6 +186,21 @@ class SkillChainAgent:
         delta = opts.update(s, a, r, s2, a2, term, o)
         self.last_delta = delta
         self.ep_return += r_env
+        if cfg.top_level:       # SMDP return of the running option (fp32, this operation order)
+            self.opt_R = (self.opt_R + (self.opt_disc * r_env).astype(np.float32)).astype(np.float32)
+            self.opt_disc = (self.opt_disc * f32(cfg.gamma)).astype(np.float32)
+            if term.any():
+                K = opts.K
+                g = min(self.n_active, K - 1)
+                adm2 = ((bits[:, None] >> np.arange(K, dtype=np.uint32)[None, :]) & np.uint32(1)).astype(bool)
+                adm2[:, g] = True
+                m2 = np.where(adm2, opts.q_top(s2), -np.inf).max(axis=1).astype(np.float32)
+                ended = env_done | ep_timeout
+                boot = np.where(ended, f32(0.0), (self.opt_disc * m2).astype(np.float32)).astype(np.float32)
+                q0 = opts.q_top(self.opt_s0)[idx, o]
+                d_top = ((self.opt_R + boot).astype(np.float32) - q0).astype(np.float32)
+                self.last_delta_top = np.where(term, d_top, f32(0.0)).astype(np.float32)
+                opts.top_update(self.opt_s0, o, d_top, term)
         for b in np.nonzero(term)[0]:
             k = o[b]
             slot = self.ex_count[k] % cfg.example_capacity
@@ -171,7 +224,11 @@ class SkillChainAgent:
         own_action, own_o, Qsel = own_a2.copy(), o.copy(), Q2
         if term.any():
             bits_next = self.initiation_bits(s_next)
-            o_sel = self.choose_option(bits_next)
+            if cfg.top_level:
+                o_sel, Qtop, adm = self.choose_option_top(bits_next, s_next, t)
+                self._last_Qtop = np.where(adm, Qtop, -np.inf)
+            else:
+                o_sel = self.choose_option(bits_next)
             o_next = np.where(term, o_sel, o).astype(np.int32)
             if follow is not None:  # evaluate the first action under the followed option
                 own_o = o_next
@@ -183,11 +240,17 @@ class SkillChainAgent:
             Qsel = np.where(term[:, None], Qn, Q2)
             self.t_opt[term] = 0
             self.start_xy[term] = s_next[term, :2]
+            self.opt_s0[term] = s_next[term]
+            self.opt_R[term] = 0
+            self.opt_disc[term] = 1
         extra = {}
         if follow is not None:
             # own_action / own_option: what the oracle would have chosen itself; Qsel: the Q row each own_action was
             # the eps-greedy choice from (under the followed option where the option was re-selected)
             extra = dict(own_action=own_action, own_option=own_o, Qsel=Qsel)
+            if cfg.top_level:       # the top-level values the option choice was made from (-inf: not admissible)
+                extra["Qtop"] = self._last_Qtop if term.any() else None
+                extra["delta_top"] = self.last_delta_top
             a_next = np.asarray(follow["action"], dtype=np.int32).copy()
         self.option, self.action = o_next, a_next
         opts.tick()

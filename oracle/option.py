@@ -29,6 +29,12 @@ option) per step and, at the end of the window, for each env over its recorded s
   which is algebraically the same sum (tests/test_oracle_option.py checks the two forms equal).
   It assumes what the agent guarantees: an env changes option only after a step with done = True.
 
+Top-level value function (OptionSet(..., top_slots=n), used by oracle/agent.py with top_level=True; SURVEY.md
+section 8 f-3): the SMDP learner over options shares the basis and the weight tables.  Q_top(s, j), j = 0..K-1, is row
+j % 5 of the extra slot K + j // 5 of W (n = ceil(K / 5) slots), so the same q() evaluates it; its window delta lives
+in dW[K:], and apply() steps those slots with alpha_top and the MEAN over the window's termination events
+(cnt[K:] all hold the event count):  W[k] += alpha_top * alpha_scale (.) dW[k] / cnt[k]  for k >= K.
+
 Initiation classifier of option k: p = sigmoid(theta_k . psi(x, y)), psi = (1, x, y, x^2, xy, y^2);
 I_k(s) = p >= 0.5.  fit: theta -= lr * mean_i (p_i - y_i) psi_i, a fixed number of steps.
 """
@@ -70,8 +76,11 @@ class OptionSet:
     per-env traces (B, A, F), window accumulators dW (K, A, F) / cnt (K,)."""
 
     def __init__(self, n_options, order, batch, gamma=0.99, lam=0.9, alpha=1e-3, epsilon=0.05,
-                 seed=0, env_offset=0, windowed=False):
+                 seed=0, env_offset=0, windowed=False, top_slots=0, alpha_top=1e-3):
         self.K = int(n_options)
+        self.top_slots = int(top_slots)
+        self.K_all = self.K + self.top_slots
+        self.alpha_top = f32(alpha_top)
         self.windowed = bool(windowed)
         self._win = []
         self.basis = FourierBasis(order)
@@ -83,11 +92,11 @@ class OptionSet:
         self.epsilon = f32(epsilon)
         self.seed = int(seed)
         self.env_ids = np.arange(self.B, dtype=np.uint32) + np.uint32(env_offset)
-        self.W = np.zeros((self.K, N_ACTIONS, self.F), dtype=np.float32)
+        self.W = np.zeros((self.K_all, N_ACTIONS, self.F), dtype=np.float32)
         self.theta = np.zeros((self.K, N_PSI), dtype=np.float32)
         self.trace = np.zeros((self.B, N_ACTIONS, self.F), dtype=np.float32)
-        self.dW = np.zeros((self.K, N_ACTIONS, self.F), dtype=np.float64)
-        self.cnt = np.zeros(self.K, dtype=np.int64)
+        self.dW = np.zeros((self.K_all, N_ACTIONS, self.F), dtype=np.float64)
+        self.cnt = np.zeros(self.K_all, dtype=np.int64)
         self.window_steps = 0
 
     # -- value function -----------------------------------------------------------------------
@@ -101,6 +110,30 @@ class OptionSet:
             mk = option_ids == k
             Q[mk] = (phi[mk].astype(np.float64) @ self.W[k].T.astype(np.float64)).astype(np.float32)
         return Q
+
+    def q_top(self, state, phi=None):
+        """Q_top(s, j) for every option slot j: (B, K) float32 (rows of the top-level slots of W)."""
+        if phi is None:
+            phi = self.basis.features(state)
+        Q = np.zeros((phi.shape[0], self.K), dtype=np.float32)
+        for j in range(self.K):
+            w = self.W[self.K + j // N_ACTIONS, j % N_ACTIONS].astype(np.float64)
+            Q[:, j] = (phi.astype(np.float64) @ w).astype(np.float32)
+        return Q
+
+    def top_update(self, s0, option_ids, delta_top, mask):
+        """SMDP update of the top-level learner for the envs in `mask` (their option just terminated): dW of row
+        `option` of the top-level slots += delta_top * phi(s0); every top-level slot's cnt += number of events."""
+        sel = np.nonzero(mask)[0]
+        if len(sel) == 0 or self.top_slots == 0:
+            return
+        phi = self.basis.features(np.asarray(s0, dtype=np.float32)[sel]).astype(np.float64)
+        d = np.asarray(delta_top, dtype=np.float64)[sel]
+        o = np.asarray(option_ids)[sel]
+        for j in np.unique(o):
+            mj = o == j
+            self.dW[self.K + j // N_ACTIONS, j % N_ACTIONS] += d[mj] @ phi[mj]
+        self.cnt[self.K:] += len(sel)
 
     def act(self, state, option_ids, step, stream=STREAM_ACTION, env_ids=None):
         Q = self.q(state, option_ids)
@@ -129,7 +162,7 @@ class OptionSet:
         if self.windowed:
             self._win.append((np.array(s, dtype=np.float32).reshape(B, 4), a.astype(np.int32).copy(), delta.copy(),
                               done.copy(), option_ids.astype(np.int32).copy(), np.asarray(mask, dtype=bool).copy()))
-            self.cnt += np.bincount(option_ids[mask], minlength=self.K)[: self.K]
+            self.cnt[: self.K] += np.bincount(option_ids[mask], minlength=self.K)[: self.K]
             return delta
         phi = self.basis.features(s)
         gl = f32(self.gamma * self.lam)
@@ -205,10 +238,12 @@ class OptionSet:
         dW = self.dW if dW is None else dW
         cnt = self.cnt if cnt is None else cnt
         steps = max(self.window_steps, 1)
-        for k in range(self.K):
+        for k in range(self.K_all):
             if cnt[k] > 0:
-                scale = f32(f32(steps) / f32(cnt[k]))
-                step = (self.alpha * self.basis.alpha_scale)[None, :] * (dW[k].astype(np.float32) * scale)
+                top = k >= self.K        # top-level slots: mean over the window's termination events, own step size
+                scale = f32(f32(1 if top else steps) / f32(cnt[k]))
+                alpha = self.alpha_top if top else self.alpha
+                step = (alpha * self.basis.alpha_scale)[None, :] * (dW[k].astype(np.float32) * scale)
                 self.W[k] += step.astype(np.float32)
         self.dW[:] = 0
         self.cnt[:] = 0

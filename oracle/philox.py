@@ -43,6 +43,8 @@ def uniform01(u32):
 # Stream ids: which decision a draw is for.  Counter = (env id, step, stream, 0).
 STREAM_ACTION = 0
 STREAM_RESET = 1
+# (2 = STREAM_RESELECT, oracle/agent.py: first action under a newly selected option)
+STREAM_TOP = 3         # the top-level learner's choice of the next option
 
 
 def draws(seed, env_ids, step, stream):

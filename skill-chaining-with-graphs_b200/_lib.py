@@ -12,7 +12,7 @@ MAX_OPTIONS = 16
 MAX_ORDER = 5
 WIN_MAX = 32
 GOAL_BIT = 0x80000000
-STREAM_ACTION, STREAM_RESET, STREAM_RESELECT = 0, 1, 2
+STREAM_ACTION, STREAM_RESET, STREAM_RESELECT, STREAM_TOP = 0, 1, 2, 3
 
 
 class ScgError(RuntimeError):
@@ -40,12 +40,14 @@ class AgentStruct(C.Structure):
         ("carry_valid", C.c_int32),
         ("alpha", C.c_float), ("window_steps", C.c_int32), ("win_cap", C.c_int32), ("win_len", C.c_int32),
         ("ring_len", C.c_int32), ("gestation_successes", C.c_int32), ("clf_steps", C.c_int32), ("clf_lr", C.c_float),
+        ("top_slots", C.c_int32), ("alpha_top", C.c_float), ("epsilon_top", C.c_float), ("reserved0", C.c_int32),
         ("x", C.c_void_p), ("y", C.c_void_p), ("vx", C.c_void_p), ("vy", C.c_void_p),
         ("x2", C.c_void_p), ("y2", C.c_void_p), ("vx2", C.c_void_p), ("vy2", C.c_void_p),
         ("action", C.c_void_p), ("option", C.c_void_p), ("t_opt", C.c_void_p), ("ep_steps", C.c_void_p),
-        ("start_xy", C.c_void_p), ("ep_return", C.c_void_p), ("ep_count", C.c_void_p), ("last_return", C.c_void_p),
+        ("start_xy", C.c_void_p), ("start_vxy", C.c_void_p), ("opt_ret", C.c_void_p), ("opt_disc", C.c_void_p),
+        ("ep_return", C.c_void_p), ("ep_count", C.c_void_p), ("last_return", C.c_void_p),
         ("reward", C.c_void_p), ("flags", C.c_void_p), ("delta", C.c_void_p), ("q_carry", C.c_void_p),
-        ("win_rec", C.c_void_p), ("win_ev", C.c_void_p), ("trace", C.c_void_p),
+        ("win_rec", C.c_void_p), ("win_ev", C.c_void_p), ("win_top", C.c_void_p), ("trace", C.c_void_p),
         ("W", C.c_void_p), ("Wt", C.c_void_p), ("theta", C.c_void_p), ("dW", C.c_void_p),
         ("cnt", C.c_void_p), ("ctl", C.c_void_p),
         ("ex_xy", C.c_void_p), ("ex_label", C.c_void_p),
@@ -80,6 +82,7 @@ _SIGS = {
     "scg_ctx_set_deterministic": (C.c_int, [_P, C.c_int]),
     "scg_sarsa_update": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_float, _P, _P, _P, _P]),
     "scg_apply": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P]),
+    "scg_apply_top": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int, _P]),
     "scg_clf_eval": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, _P, _P]),
     "scg_clf_grad": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "scg_clf_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_float, _P]),
@@ -100,6 +103,7 @@ _SIGS = {
     "scg_xchg_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "scg_xchg_set_timeout": (C.c_int, [_P, C.c_double]),
     "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
+    "scg_xchg_sync_top": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
     "scg_profile_begin": (C.c_int, [_P, C.c_int, C.c_int]),
     "scg_profile_end": (C.c_int, [_P, _P, _P]),

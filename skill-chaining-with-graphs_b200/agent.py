@@ -54,6 +54,9 @@ class AgentConfig:
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
     deterministic: bool = False   # fixed-order reduction of the weight deltas: runs reproduce bit for bit (slightly slower)
     sync_backend: str = "p2p"   # multi-rank weight-delta exchange: "p2p" (one kernel over NVLink peer memory) or "nccl"
+    top_level: bool = False     # option choice by the learned SMDP value function Q_top (oracle/agent.py) instead of "first active"
+    alpha_top: float = 1e-3
+    epsilon_top: float = 0.05
     sync_timeout_s: float = 30.0   # how long a peer-memory exchange waits for the other ranks before failing (ScgError)
 
 
@@ -70,8 +73,10 @@ class SkillChainAgent:
         B, K = cfg.batch, cfg.max_options
         dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self.top_slots = -(-K // N_ACTIONS) if cfg.top_level else 0
         self.options = OptionSet(K, cfg.order, B, cfg.gamma, cfg.lam, cfg.alpha, cfg.epsilon, cfg.seed,
-                                 cfg.env_offset, dev, deterministic=cfg.deterministic)
+                                 cfg.env_offset, dev, deterministic=cfg.deterministic, top_slots=self.top_slots,
+                                 alpha_top=cfg.alpha_top)
         self.options._pre_read = self.flush        # dW / trace reads see the open window folded in
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -93,6 +98,12 @@ class SkillChainAgent:
         self.q_carry = torch.zeros(B, **f32)
         self.win_rec = torch.zeros((self.win_cap, B, 8), **f32)
         self.win_ev = torch.zeros((self.win_cap, max(B, 1)), dtype=torch.uint8, device=dev)
+        # top-level learner: s0 = (start_xy, start_vxy), discounted return and discount of the running option, and the
+        # SMDP update records of the open window
+        self.start_vxy = torch.zeros((B, 2), **f32)
+        self.opt_ret = torch.zeros(B, **f32)
+        self.opt_disc = torch.ones(B, **f32)
+        self.win_top = torch.zeros((self.win_cap if cfg.top_level else 0, max(B, 1), 8), **f32)
         # controller state: a device block (struct scg_ctl) the kernels read and scg_agent_manage updates in place
         self.ctl = torch.zeros(32, **i32)
         self._ctl = CtlStruct()
@@ -101,9 +112,11 @@ class SkillChainAgent:
         self._ex_xy = torch.zeros((K, cfg.example_capacity, 2), **f32)
         self._ex_label = torch.zeros((K, cfg.example_capacity), dtype=torch.uint8, device=dev)
         self._ex_count = torch.zeros(K, dtype=torch.int64, device=dev)
-        self.n_success = torch.zeros(K, **i32)
-        self.n_fail = torch.zeros(K, **i32)
-        self.n_success_global = torch.zeros(K, **i32)
+        # (sized for every weight slot: the cross-GPU exchange carries one success counter per slot)
+        self._n_success = torch.zeros(_lib.MAX_OPTIONS, **i32)
+        self._n_fail = torch.zeros(_lib.MAX_OPTIONS, **i32)
+        self._n_success_global = torch.zeros(_lib.MAX_OPTIONS, **i32)
+        self.n_success, self.n_fail, self.n_success_global = self._n_success[:K], self._n_fail[:K], self._n_success_global[:K]
         self.stats = torch.zeros(4, dtype=torch.int64, device=dev)
         # initial state, option and action (oracle/agent.py __init__)
         s = self._sbuf[0]
@@ -114,6 +127,7 @@ class SkillChainAgent:
             check(self.lib.scg_reset(self.map.handle, B, None, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), cfg.seed, 0,
                                      cfg.env_offset, _lib.current_stream()))
         self.start_xy.copy_(s[:2].t())
+        self.start_vxy.copy_(s[2:].t())
         self.options.pack()
         self.action.copy_(self.options.act(None, self.option, step=0xFFFFFFFF, stream=_lib.STREAM_RESELECT, soa=s))
         self._struct = self._make_struct()
@@ -253,14 +267,16 @@ class SkillChainAgent:
         g.step = g.window_steps = g.win_len = g.carry_valid = g.ring_len = g.n_active = 0
         g.graph, g.gestation_successes = int(bool(cfg.graph)), int(cfg.gestation_successes)
         g.clf_steps, g.clf_lr = int(cfg.clf_steps), float(cfg.clf_lr)
+        g.top_slots, g.alpha_top, g.epsilon_top = self.top_slots, float(cfg.alpha_top), float(cfg.epsilon_top)
         s, s2 = self._sbuf
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
         for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
                      "q_carry", "win_rec", "win_ev", "ctl", "n_success", "n_fail", "n_success_global", "stats",
-                     "ep_count", "last_return"):
+                     "ep_count", "last_return", "start_vxy", "opt_ret", "opt_disc"):
             setattr(g, name, getattr(self, name).data_ptr())
         g.ex_xy, g.ex_label, g.ex_count = self._ex_xy.data_ptr(), self._ex_label.data_ptr(), self._ex_count.data_ptr()
+        g.win_top = self.win_top.data_ptr() if cfg.top_level else None
         g.trace, g.W, g.Wt, g.theta = o._trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
         g.dW, g.cnt = o._dW.data_ptr(), o.cnt.data_ptr()
         return g
@@ -405,14 +421,17 @@ class SkillChainAgent:
     HOST_H2D_BYTES_PER_ENV = 20      # state 16 + action 4
     HOST_D2H_BYTES_PER_ENV = 32      # next state 16 + reward 4 + flags 4 + next action 4 + TD error 4
 
-    def profile_begin(self, max_events, kinds=(0, 1, 2, 3)):
-        """Record CUDA events around the launches of the given kinds (0 step, 1 window sweep, 2 reduce, 3 apply)."""
+    PROF_KINDS = 6
+
+    def profile_begin(self, max_events, kinds=(0, 1, 2, 3, 4, 5)):
+        """Record CUDA events around the launches of the given kinds (0 step, 1 window sweep, 2 reduce, 3 apply /
+        exchange, 4 example-ring pass, 5 controller kernel)."""
         check(self.lib.scg_profile_begin(self.options.ctx, int(max_events), sum(1 << k for k in kinds)))
 
     def profile_end(self):
-        """-> (ms per kind, launches per kind) for [fused step, window sweep, dW reduction, apply]."""
-        ms = (C.c_float * 4)()
-        n = (C.c_int * 4)()
+        """-> (ms per kind, launches per kind) for [fused step, window sweep, dW reduction, apply, ring pass, controller]."""
+        ms = (C.c_float * self.PROF_KINDS)()
+        n = (C.c_int * self.PROF_KINDS)()
         check(self.lib.scg_profile_end(self.options.ctx, ms, n))
         return [float(v) for v in ms], [int(v) for v in n]
 
@@ -421,9 +440,9 @@ class SkillChainAgent:
         o, g = self.options, self._struct
         self.flush()
         if self._xchg is not None:
-            check(self.lib.scg_xchg_sync(self._xchg, o.order, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt),
-                                         self.cfg.alpha, max(int(g.window_steps), 1), ptr(self.n_success),
-                                         ptr(self.n_success_global), _lib.current_stream()))
+            check(self.lib.scg_xchg_sync_top(self._xchg, o.order, o.K_all, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt),
+                                             self.cfg.alpha, self.cfg.alpha_top, max(int(g.window_steps), 1),
+                                             ptr(self.n_success), ptr(self.n_success_global), _lib.current_stream()))
             o.window_steps = 0
         else:
             allreduce_deltas(o._dW, o.cnt, self.pg)
@@ -514,7 +533,8 @@ class SkillChainAgent:
 
     # -- checkpoint / resume ----------------------------------------------------
     _CKPT_TENSORS = ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "_ex_xy", "_ex_label", "_ex_count",
-                     "n_success", "n_fail", "n_success_global", "stats", "q_carry", "ep_count", "last_return")
+                     "n_success", "n_fail", "n_success_global", "stats", "q_carry", "ep_count", "last_return", "start_vxy",
+                     "opt_ret", "opt_disc")
 
     def save(self, path):
         """Write everything needed to resume this rank (option weights, classifiers, option graph, per-env state and

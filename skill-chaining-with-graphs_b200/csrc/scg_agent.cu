@@ -28,6 +28,7 @@
 int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, float *trace, float gl, float *dW,
                       cudaStream_t st);
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
+int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st);
 
 struct StepArgs {
     scg_agent_t ag;
@@ -38,6 +39,7 @@ struct StepArgs {
     int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
     float4 *rec;  // this step's slab of the window: [B][2]
     uint8_t *ev;  // this step's slab of the event bytes: [B]
+    float *top;   // this step's slab of the top-level update records: [B][8] (top_slots > 0)
 };
 
 // bulk-TMA staging of up to two global blocks into shared memory behind one mbarrier
@@ -74,7 +76,57 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
     }
 }
 
-template <int N1, bool SMEMW, bool PAIR, int NTH>
+// Q_slot(z, .) for the lanes of `mask` (a warp-uniform ballot), compacted: N1 lanes share one of those envs, one leading
+// multi-index digit c0 each, and the partial sums are folded back to the env's own lane.  `z` and `slot` are the env's
+// phasors and weight-table slot (valid on the lanes of mask); q receives the 5 values on those lanes.
+template <int N1, bool SMEMW>
+__device__ __forceinline__ void warp_compact_q(unsigned mask, bool in_mask, int lane, const float2 z[4], int slot_id,
+                                               const float *Wt_staged, int Kw, int k_opt, int K, const float *Wt_global,
+                                               int Kall, float q[SCG_A]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PER = 32 / N1;                                 // envs served per pass
+    const int my_rank = __popc(mask & ((1u << lane) - 1u));      // rank of this lane among the lanes of mask
+    const int grp = lane / N1, c0 = lane - grp * N1;
+    for (int base = 0; base < __popc(mask); base += PER) {
+        const unsigned src = __fns(mask, 0, base + grp + 1);     // lane of the (base+grp)-th env of mask
+        const bool have = grp < PER && src < 32u;
+        const int sl = have ? (int)src : 0;
+        float2 zs[4];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+            zs[dd].x = __shfl_sync(FULL, z[dd].x, sl);
+            zs[dd].y = __shfl_sync(FULL, z[dd].y, sl);
+        }
+        const int os = __shfl_sync(FULL, slot_id, sl);
+        float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        // staged table: option slots 0 .. k_opt-1, then the top-level slots K .. Kall-1; anything else (an option
+        // promoted after the host sized this launch) is read through the global path
+        const bool staged = os < k_opt || os >= K;
+        if (SMEMW && __any_sync(FULL, have && !staged)) {
+            if (have) scg_q_c0<N1, false>(c0, zs, WCur<false>(Wt_global, Kall, os), qp);
+        } else {
+            if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(SMEMW ? Wt_staged : Wt_global, Kw, SMEMW && os >= K ? os - K + k_opt : os), qp);
+        }
+#pragma unroll
+        for (int dd = 1; dd < N1; ++dd) {                        // group head (c0 == 0) gathers the partial sums
+#pragma unroll
+            for (int i = 0; i < SCG_A; ++i) {
+                const float v = __shfl_down_sync(FULL, qp[i], dd);
+                if (c0 == 0) qp[i] += v;
+            }
+        }
+        const int rel = my_rank - base;
+        const bool mine = in_mask && rel >= 0 && rel < PER;
+        const int head = mine ? rel * N1 : 0;
+#pragma unroll
+        for (int i = 0; i < SCG_A; ++i) {
+            const float v = __shfl_sync(FULL, qp[i], head);
+            if (mine) q[i] = v;
+        }
+    }
+}
+
+template <int N1, bool SMEMW, bool PAIR, int NTH, bool TOP>
 __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_constant__ StepArgs args) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
@@ -87,7 +139,9 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     if (args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
     // the map always moves with one bulk-TMA copy; so do the weights when every option is staged (contiguous table);
     // when only the options in use are staged, their slots are gathered feature by feature with plain 16-byte copies
-    const bool bulk_w = SMEMW && args.k_stage == g.K;
+    // staged slots: the option slots in use (0 .. k_opt-1) followed by the top-level learner's slots (K .. Kall-1)
+    const int Kall = g.K + g.top_slots, k_opt = args.k_stage - g.top_slots;
+    const bool bulk_w = SMEMW && k_opt == g.K;
     stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, bulk_w ? args.w_bytes : 0, &bar);
     if (SMEMW && !bulk_w) {
         const int per_f = 2 * args.k_stage, total = (args.w_bytes >> 4);
@@ -95,7 +149,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
         float4 *dst = reinterpret_cast<float4 *>(w_smem);
         for (int c = threadIdx.x; c < total; c += blockDim.x) {
             const int f = c / per_f, j = c - f * per_f;
-            dst[c] = __ldg(src + (size_t)f * 2 * g.K + j);
+            const int sl = j >> 1, src_slot = sl < k_opt ? sl : sl - k_opt + g.K;
+            dst[c] = __ldg(src + (size_t)f * 2 * Kall + 2 * src_slot + (j & 1));
         }
         __syncthreads();
     }
@@ -104,7 +159,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
     const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
     const int K = g.K;
-    const int Kw = SMEMW ? args.k_stage : K;          // options per feature in the weight table being read
+    const int Kw = SMEMW ? args.k_stage : Kall;       // slots per feature in the weight table being read
     // controller state lives on the device (scg_agent_manage promotes options in place): the launch was sized with the
     // host's lower bound of n_active (k_stage), the truth is read here
     const int n_act = g.ctl->n_active;
@@ -127,6 +182,9 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
         int t_opt = g.t_opt[b], ep = g.ep_steps[b];
         float ret = g.ep_return[b], qc = PAIR ? 0.f : g.q_carry[b];
         float stx = g.start_xy[2 * b], sty = g.start_xy[2 * b + 1];
+        // top-level learner: velocity at the option's start, discounted task reward since, gamma^steps
+        float stvx = 0.f, stvy = 0.f, oret = 0.f, odisc = 1.f;
+        if (TOP) { stvx = g.start_vxy[2 * b]; stvy = g.start_vxy[2 * b + 1]; oret = g.opt_ret[b]; odisc = g.opt_disc[b]; }
         float r_env = 0.f, delta = 0.f;
         int fl = 0;
         for (int s = 0; s < args.n_steps; ++s) {
@@ -142,18 +200,18 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
             float qb[SCG_A], qsa = qc;
             // an option promoted after the host sized this launch (o >= k_stage) is not in the staged table: the warp
             // then reads the weights through the global path for this step (rare and transient)
-            const bool unstaged = SMEMW && __any_sync(FULL, o >= args.k_stage);
+            const bool unstaged = SMEMW && __any_sync(FULL, o >= k_opt);
             if (PAIR && s == 0) {
                 float2 za[4];
                 scg_phasors(sx, sy, svx, svy, za);
                 float qa[SCG_A];
-                if (unstaged) scg_q_pair<N1, false>(za, zb, WCur<false>(g.Wt, K, o), qa, qb);
+                if (unstaged) scg_q_pair<N1, false>(za, zb, WCur<false>(g.Wt, Kall, o), qa, qb);
                 else scg_q_pair<N1, SMEMW>(za, zb, WCur<SMEMW>(Wt, Kw, o), qa, qb);
                 qsa = 0.f;
 #pragma unroll
                 for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
             } else {
-                if (unstaged) scg_q_one<N1, false>(zb, WCur<false>(g.Wt, K, o), qb);
+                if (unstaged) scg_q_one<N1, false>(zb, WCur<false>(g.Wt, Kall, o), qb);
                 else scg_q_one<N1, SMEMW>(zb, WCur<SMEMW>(Wt, Kw, o), qb);
             }
             // 2-3: initiation bits of s2, termination, option reward
@@ -173,6 +231,10 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
             for (int i = 0; i < SCG_A; ++i) qs2 = (i == a2) ? qb[i] : qs2;
             delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g.gamma, term ? 0.f : 1.f), qs2)), qsa);
             ret += r_env;
+            if (TOP) {   // SMDP return of the running option (oracle/agent.py: this operation order)
+                oret = __fadd_rn(oret, __fmul_rn(odisc, r_env));
+                odisc = __fmul_rn(odisc, g.gamma);
+            }
             const bool reset = env_done || ep_timeout;
             {   // cnt[o] += 1, one atomic per (warp, option)
                 const uint32_t peers = __match_any_sync(FULL, valid ? o : -1);
@@ -204,57 +266,75 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     ep = 0;
                 }
             }
-            // 8: option re-selection.  Terminations are rare, so the Q evaluation under the new option is
-            // compacted inside the warp: N1 lanes share one terminated env, one leading digit c0 each.
+            // 8: option re-selection.  Terminations are rare, so every Q evaluation they need is compacted inside the
+            // warp (warp_compact_q): N1 lanes share one terminated env, one leading digit c0 each.
             int o_next = o, a_next = a2;
             float q_next = qs2;
             const bool tv = term && valid;
             const unsigned tmask = __ballot_sync(FULL, tv);
             if (tmask) {
                 float2 zn[4] = {zb[0], zb[1], zb[2], zb[3]};
+                uint32_t bn = bits;
                 if (tv) {
-                    const uint32_t bn = reset ? scg_init_bits(g.theta, K, amask, nx, ny) : bits;
+                    if (reset) {
+                        bn = scg_init_bits(g.theta, K, amask, nx, ny);
+                        scg_phasors(nx, ny, nvx, nvy, zn);
+                    }
                     o_next = bn ? (__ffs(bn) - 1) : gest;
-                    if (reset) scg_phasors(nx, ny, nvx, nvy, zn);
                 }
-                constexpr int PER = 32 / N1;                         // envs served per pass
-                const int my_slot = __popc(tmask & ((1u << lane) - 1u));   // rank of this lane among the terminated
-                const int slot = lane / N1, c0 = lane - slot * N1;
-                float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int base = 0; base < __popc(tmask); base += PER) {
-                    const unsigned src = __fns(tmask, 0, base + slot + 1);   // lane of the (base+slot)-th terminated env
-                    const bool have = slot < PER && src < 32u;
-                    const int sl = have ? (int)src : 0;
-                    float2 zs[4];
-#pragma unroll
-                    for (int dd = 0; dd < 4; ++dd) {
-                        zs[dd].x = __shfl_sync(FULL, zn[dd].x, sl);
-                        zs[dd].y = __shfl_sync(FULL, zn[dd].y, sl);
-                    }
-                    const int os = __shfl_sync(FULL, o_next, sl);
-                    float qp[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (SMEMW && __any_sync(FULL, have && os >= args.k_stage)) {
-                        if (have) scg_q_c0<N1, false>(c0, zs, WCur<false>(g.Wt, K, os), qp);
-                    } else {
-                        if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(Wt, Kw, os), qp);
-                    }
-#pragma unroll
-                    for (int dd = 1; dd < N1; ++dd) {                // slot head (c0 == 0) gathers the partial sums
+                if (TOP) {
+                    // The top-level SMDP learner (oracle/agent.py module docstring).  Q_top(s, j) is row j % 5 of slot
+                    // K + j / 5.  (i) max over the admissible slots at s2 for the bootstrap, and - the same pass when the
+                    // env was not reset - the greedy choice at s_next; (ii) Q_top(s0, o); (iii) delta_top -> win_top.
+                    const uint32_t adm2 = bits | (1u << gest), admn = bn | (1u << gest);
+                    float m2 = -INFINITY, mn = -INFINITY;
+                    int best = gest;
+                    const unsigned rmask = __ballot_sync(FULL, tv && reset);
+                    for (int sl = 0; sl < g.top_slots; ++sl) {
+                        float qt[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                        warp_compact_q<N1, SMEMW>(tmask, tv, lane, zb, K + sl, Wt, Kw, k_opt, K, g.Wt, Kall, qt);
 #pragma unroll
                         for (int i = 0; i < SCG_A; ++i) {
-                            const float v = __shfl_down_sync(FULL, qp[i], dd);
-                            if (c0 == 0) qp[i] += v;
+                            const int j = sl * SCG_A + i;
+                            if (j < K && ((adm2 >> j) & 1u)) {
+                                m2 = fmaxf(m2, qt[i]);
+                                if (!reset && qt[i] > mn) { mn = qt[i]; best = j; }     // first admissible maximum
+                            }
+                        }
+                        if (rmask) {          // envs that were reset choose at the start state instead
+                            float qr[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                            warp_compact_q<N1, SMEMW>(rmask, tv && reset, lane, zn, K + sl, Wt, Kw, k_opt, K, g.Wt, Kall, qr);
+#pragma unroll
+                            for (int i = 0; i < SCG_A; ++i) {
+                                const int j = sl * SCG_A + i;
+                                if (reset && j < K && ((admn >> j) & 1u) && qr[i] > mn) { mn = qr[i]; best = j; }
+                            }
                         }
                     }
-                    const int rel = my_slot - base;
-                    const bool mine = tv && rel >= 0 && rel < PER;
-                    const int head = mine ? rel * N1 : 0;
+                    float2 z0[4];
+                    scg_phasors(stx, sty, stvx, stvy, z0);
+                    float q0v[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                    warp_compact_q<N1, SMEMW>(tmask, tv, lane, z0, K + o / SCG_A, Wt, Kw, k_opt, K, g.Wt, Kall, q0v);
+                    if (tv) {
+                        float q0 = 0.f;
+                        const int row = o - (o / SCG_A) * SCG_A;
 #pragma unroll
-                    for (int i = 0; i < SCG_A; ++i) {
-                        const float v = __shfl_sync(FULL, qp[i], head);
-                        if (mine) qn[i] = v;
+                        for (int i = 0; i < SCG_A; ++i) q0 = (i == row) ? q0v[i] : q0;
+                        const float boot = reset ? 0.f : __fmul_rn(odisc, m2);
+                        const float dtop = __fsub_rn(__fadd_rn(oret, boot), q0);
+                        float4 *tr = reinterpret_cast<float4 *>(args.top) + ((size_t)s * g.B + b) * 2;
+                        tr[0] = make_float4(stx, sty, stvx, stvy);
+                        tr[1] = make_float4(dtop, __int_as_float(o), 0.f, 0.f);
+                        // eps_top-greedy over the admissible slots at s_next
+                        const uint4 rt = scg_draw(g.seed, env, step, SCG_STREAM_TOP);
+                        const int n_adm = __popc(admn);
+                        const int pick = min((int)__fmul_rn(scg_u01(rt.y), (float)n_adm), n_adm - 1);
+                        const int rnd_o = (int)__fns(admn, 0, pick + 1);
+                        o_next = (scg_u01(rt.x) < g.epsilon_top) ? rnd_o : best;
                     }
                 }
+                float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                warp_compact_q<N1, SMEMW>(tmask, tv, lane, zn, o_next, Wt, Kw, k_opt, K, g.Wt, Kall, qn);
                 if (tv) {
                     a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, step, SCG_STREAM_RESELECT));
 #pragma unroll
@@ -262,6 +342,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     t_opt = 0;
                     stx = nx;
                     sty = ny;
+                    if (TOP) { stvx = nvx; stvy = nvy; oret = 0.f; odisc = 1.f; }
                 }
             }
             // the next step starts from here
@@ -278,6 +359,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
             g.q_carry[b] = qc;
             g.start_xy[2 * b] = stx;
             g.start_xy[2 * b + 1] = sty;
+            if (TOP) { g.start_vxy[2 * b] = stvx; g.start_vxy[2 * b + 1] = stvy; g.opt_ret[b] = oret; g.opt_disc[b] = odisc; }
             g.reward[b] = r_env;
             g.flags[b] = fl;
             g.delta[b] = delta;
@@ -286,9 +368,9 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
 }
 
 // ---- launch plumbing --------------------------------------------------------------------------------
-template <int N1, bool SMEMW, bool PAIR, int NTH>
-static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
-    auto kern = k_agent_step<N1, SMEMW, PAIR, NTH>;
+template <int N1, bool SMEMW, bool PAIR, int NTH, bool TOP>
+static int launch_step_tt(const StepArgs &args, size_t smem, cudaStream_t st) {
+    auto kern = k_agent_step<N1, SMEMW, PAIR, NTH, TOP>;
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
     int rcc = scg_configure(cfgc, kern, NTH, smem, &per_sm);
@@ -318,6 +400,12 @@ static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
     return 0;
 }
 
+template <int N1, bool SMEMW, bool PAIR, int NTH>
+static int launch_step_t(const StepArgs &args, size_t smem, cudaStream_t st) {
+    if (args.ag.top_slots > 0) return launch_step_tt<N1, SMEMW, PAIR, NTH, true>(args, smem, st);
+    return launch_step_tt<N1, SMEMW, PAIR, NTH, false>(args, smem, st);
+}
+
 // mode 0: weights through the read-only global path; 1: staged to shared memory, two 256-thread CTAs per SM;
 // 2: staged, one 512-thread CTA per SM (order 5: the options in use take up to ~200 KB)
 template <int N1>
@@ -336,8 +424,10 @@ static int launch_step_n(const StepArgs &args, int mode, bool pair, cudaStream_t
 
 static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_agent_t *ag) {
     if (!map || !ctx || !ag) return SCG_EINVAL;
-    if (ag->K != ctx->K || ag->order != ctx->order) return SCG_EINVAL;
-    if (ag->K < 1 || ag->K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
+    if (ag->top_slots < 0 || ag->K + ag->top_slots != ctx->K || ag->order != ctx->order) return SCG_EINVAL;
+    if (ag->K < 1 || ag->K + ag->top_slots > SCG_MAX_OPTIONS) return SCG_ELIMIT;
+    if (ag->top_slots > 0 && (ag->top_slots * SCG_A < ag->K || !ag->win_top || !ag->start_vxy || !ag->opt_ret || !ag->opt_disc))
+        return SCG_EINVAL;
     if (ag->B < 0 || ag->win_cap < 1 || ag->win_cap > SCG_WIN_MAX || ag->win_len < 0 || ag->win_len >= ag->win_cap)
         return SCG_EINVAL;
     if (ag->n_active < 0 || ag->n_active > ag->K - 1 || !ag->ctl || !ag->win_ev) return SCG_EINVAL;
@@ -353,6 +443,7 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     // option ids in the records are 0 .. n_active (the gestating slot); n_active is the host's lower bound of the
     // device's value: records of an option promoted since then are folded through the sweep's global-memory path
     const int k_used = std::min(ag->K, std::max(ag->n_active, 0) + 1);
+    if ((rc = scg_launch_top(ctx, ag, (cudaStream_t)stream))) return rc;     // the top-level learner's SMDP updates
     rc = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
                                (cudaStream_t)stream);
     if (rc) return rc;
@@ -373,10 +464,11 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.map_blob = map->d_blob;
     args.blob_bytes = map->hdr.blob_bytes;
     // only the options that can be executed (ids 0 .. n_active) need their weights on chip
-    args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1);
+    args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1) + ag->top_slots;   // + the top-level learner's slots
     args.w_bytes = args.k_stage * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
     args.ev = ag->win_ev + (size_t)ag->win_len * ag->B;
+    args.top = ag->win_top ? ag->win_top + (size_t)ag->win_len * ag->B * 8 : nullptr;
     args.n_steps = n;
     // weights go to shared memory when two CTAs per SM still fit next to the map, or one big CTA
     static int big = -1;
@@ -426,8 +518,9 @@ extern "C" int scg_agent_run(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *
         if (sync_interval > 0 && ag->window_steps >= sync_interval) {
             if ((rc = scg_agent_flush(ctx, ag, stream))) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, false))) return rc;
-            if (xchg) rc = scg_xchg_sync(xchg, ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, ag->n_success, ag->n_success_global, stream);
-            else rc = scg_apply(ag->order, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->window_steps, stream);
+            const int Kall = ag->K + ag->top_slots;
+            if (xchg) rc = scg_xchg_sync_top(xchg, ag->order, Kall, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->alpha_top, ag->window_steps, ag->n_success, ag->n_success_global, stream);
+            else rc = scg_apply_top(ag->order, Kall, ag->K, ag->W, ag->Wt, ag->dW, ag->cnt, ag->alpha, ag->alpha_top, ag->window_steps, stream);
             if (rc) return rc;
             if ((rc = scg_prof_push(ctx, 3, (cudaStream_t)stream, true))) return rc;
             ag->window_steps = 0;
@@ -506,7 +599,7 @@ int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end) {
 
 extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_events, int kind_mask) {
     if (!ctx || max_events <= 0) return SCG_EINVAL;
-    ctx->prof_mask = kind_mask & 15;
+    ctx->prof_mask = kind_mask & ((1 << SCG_PROF_KINDS) - 1);
     if (max_events > ctx->prof_cap) {
         for (int i = 0; i < 2 * ctx->prof_cap; ++i) cudaEventDestroy(ctx->prof_ev[i]);
         free(ctx->prof_ev);
@@ -527,12 +620,12 @@ extern "C" int scg_profile_begin(scg_ctx_t *ctx, int max_events, int kind_mask) 
 extern "C" int scg_profile_end(scg_ctx_t *ctx, float *ms, int *count) {
     if (!ctx || !ms || !count) return SCG_EINVAL;
     ctx->prof_on = 0;
-    for (int k = 0; k < 4; ++k) { ms[k] = 0.f; count[k] = 0; }
+    for (int k = 0; k < SCG_PROF_KINDS; ++k) { ms[k] = 0.f; count[k] = 0; }
     for (int i = 0; i < ctx->prof_n; ++i) {
         float t = 0.f;
         SCG_CUDA_OK(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
         SCG_CUDA_OK(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
-        int k = ctx->prof_kind[i] & 3;
+        int k = ctx->prof_kind[i] % SCG_PROF_KINDS;
         ms[k] += t;
         count[k] += 1;
     }

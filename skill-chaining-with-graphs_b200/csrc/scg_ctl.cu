@@ -24,6 +24,8 @@
 #include "scg_common.cuh"
 #include "scg_xchg.cuh"
 
+int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
+
 #define RING_CTAS 32
 #define RING_NT 256
 
@@ -143,11 +145,136 @@ extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
     ctx->ring_gen += (unsigned int)grid;
     const size_t off = (size_t)ag->ring_len * ag->B;
+    int rcp;
+    if ((rcp = scg_prof_push(ctx, 4, st, false))) return rcp;
     k_ring<<<grid, RING_NT, 0, st>>>((int)n, ag->K, ag->win_ev + off, reinterpret_cast<const float4 *>(ag->win_rec) + off * 2,
                                      ag->ex_xy, ag->ex_label, reinterpret_cast<long long *>(ag->ex_count),
                                      ag->example_capacity, ctx->d_ring, ctx->ring_gen);
     SCG_LAUNCH_CHECK();
+    if ((rcp = scg_prof_push(ctx, 4, st, true))) return rcp;
     ag->ring_len = ag->win_len;
+    return 0;
+}
+
+// ---- the top-level learner's window update --------------------------------------------------------------------------
+// Mirrors oracle/option.py OptionSet.top_update.  The step kernel left, for every env-step at which an option terminated
+// (event byte), a record (s0, delta_top, option) in win_top.  k_top folds them into the top-level slots of dW:
+//     dW[K + o / 5][o % 5][f] += delta_top * phi_f(s0)          and  cnt[K ..] += number of events.
+// A CTA scans a contiguous chunk of the event bytes, then processes its events TOP_EB at a time: a few threads build the
+// phasor powers exp(i pi c s0_j) of the batch (one sincospi each), then every thread forms its features as products of
+// four table entries and accumulates into the CTA's shared-memory copy of the top-level rows; one atomicAdd per touched
+// element at the end.
+#define TOP_NT 256
+#define TOP_EB 8
+#define TOP_CTAS 148
+
+template <int N1>
+__global__ void __launch_bounds__(TOP_NT) k_top(int n, int K, int top_slots, const uint8_t *__restrict__ ev,
+                                                const float4 *__restrict__ top, float *dW, int *cnt) {
+    constexpr int F = N1 * N1 * N1 * N1;
+    constexpr int FPT = (F + TOP_NT - 1) / TOP_NT;              // features per thread
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *acc = reinterpret_cast<float *>(smem_raw);           // [K][F]: row j = option j (slot K + j / 5, row j % 5)
+    float2 *tab = reinterpret_cast<float2 *>(acc + (size_t)K * F);          // [TOP_EB][4][N1]
+    float *dl = reinterpret_cast<float *>(tab + TOP_EB * 4 * N1);           // [TOP_EB] delta_top
+    int *oo = reinterpret_cast<int *>(dl + TOP_EB);                         // [TOP_EB] option
+    int *list = oo + TOP_EB;                                                 // [chunk] flat indices of this CTA's events
+    __shared__ int n_ev;
+    const int tid = threadIdx.x;
+    const int chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int beg = min(n, (int)blockIdx.x * chunk), end = min(n, beg + chunk);
+    for (int i = tid; i < K * F; i += TOP_NT) acc[i] = 0.f;
+    if (tid == 0) n_ev = 0;
+    __syncthreads();
+    for (int i = beg + tid; i < end; i += TOP_NT)
+        if (ev[i] & SCG_EV_TERM) list[atomicAdd(&n_ev, 1)] = i;
+    __syncthreads();
+    const int ne = n_ev;
+    if (ne == 0) return;
+    // per-thread constants: digits of the owned features, packed 4 x 4 bits
+    uint32_t dig[FPT];
+#pragma unroll
+    for (int k = 0; k < FPT; ++k) {
+        int f = tid + k * TOP_NT;
+        if (f >= F) f = F - 1;
+        const int c3 = f % N1, c2 = (f / N1) % N1, c1 = (f / (N1 * N1)) % N1, c0 = f / (N1 * N1 * N1);
+        dig[k] = (uint32_t)c0 | ((uint32_t)c1 << 4) | ((uint32_t)c2 << 8) | ((uint32_t)c3 << 12);
+    }
+    for (int e0 = 0; e0 < ne; e0 += TOP_EB) {
+        const int nb = min(TOP_EB, ne - e0);
+        if (tid < nb * 4 * N1) {                                 // table entry (event, dimension j, power c)
+            const int e = tid / (4 * N1), r = tid - e * 4 * N1, j = r / N1, c = r - j * N1;
+            const float4 s0 = __ldg(top + (size_t)list[e0 + e] * 2);
+            const float raw = j == 0 ? s0.x : (j == 1 ? s0.y : (j == 2 ? s0.z : s0.w));
+            const float sh = j < 2 ? raw : __fmul_rn(__fadd_rn(raw, 2.0f), 0.25f);
+            float sn, cs;
+            sincospif((float)c * sh, &sn, &cs);
+            tab[tid] = make_float2(cs, sn);
+        }
+        if (tid < nb) {
+            const float4 r1 = __ldg(top + (size_t)list[e0 + tid] * 2 + 1);
+            dl[tid] = r1.x;
+            oo[tid] = min(max(__float_as_int(r1.y), 0), K - 1);
+        }
+        __syncthreads();
+        for (int e = 0; e < nb; ++e) {
+            const float2 *t = tab + e * 4 * N1;
+            const float d = dl[e];
+            float *row = acc + (size_t)oo[e] * F;
+#pragma unroll
+            for (int k = 0; k < FPT; ++k) {
+                const int f = tid + k * TOP_NT;
+                if (f < F) {
+                    const float2 p = scg_cmul(scg_cmul(t[dig[k] & 15], t[N1 + ((dig[k] >> 4) & 15)]),
+                                              scg_cmul(t[2 * N1 + ((dig[k] >> 8) & 15)], t[3 * N1 + (dig[k] >> 12)]));
+                    row[f] = fmaf(d, p.x, row[f]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < K * F; i += TOP_NT) {
+        const float v = acc[i];
+        if (v != 0.f) {
+            const int j = i / F, f = i - j * F;
+            atomicAdd(dW + ((size_t)(K + j / SCG_A) * SCG_A + (j % SCG_A)) * F + f, v);
+        }
+    }
+    if (tid < top_slots) atomicAdd(cnt + K + tid, ne);
+}
+
+// fold the open window's top-level update records (slabs 0 .. win_len-1) into dW / cnt
+int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st) {
+    if (ag->top_slots <= 0 || ag->win_len <= 0 || ag->B <= 0) return 0;
+    if (!ag->win_top || !ag->win_ev) return SCG_EINVAL;
+    const long long n = (long long)ag->win_len * ag->B;
+    if (n > 0x7fffffffll) return SCG_ELIMIT;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(TOP_CTAS, (n + 4095) / 4096));
+    const int chunk = (int)((n + grid - 1) / grid);
+    const int N1 = ctx->order + 1;
+    const size_t smem = (size_t)ag->K * ctx->F * sizeof(float) + (size_t)TOP_EB * 4 * N1 * sizeof(float2) +
+                        TOP_EB * (sizeof(float) + sizeof(int)) + (size_t)chunk * sizeof(int);
+    if (smem > 200 * 1024) return SCG_ELIMIT;
+    const float4 *top = reinterpret_cast<const float4 *>(ag->win_top);
+    int rc = 0;
+#define LAUNCH_TOP(N)                                                                                              \
+    {                                                                                                               \
+        static ScgKernelCfg cfgc = {};                                                                              \
+        int per_sm = 0;                                                                                             \
+        rc = scg_configure(cfgc, k_top<N>, TOP_NT, smem, &per_sm);                                                  \
+        if (!rc) k_top<N><<<grid, TOP_NT, smem, st>>>((int)n, ag->K, ag->top_slots, ag->win_ev, top, ag->dW, ag->cnt); \
+    }
+    switch (ctx->order) {
+        case 1: LAUNCH_TOP(2); break;
+        case 2: LAUNCH_TOP(3); break;
+        case 3: LAUNCH_TOP(4); break;
+        case 4: LAUNCH_TOP(5); break;
+        case 5: LAUNCH_TOP(6); break;
+        default: return SCG_ELIMIT;
+    }
+#undef LAUNCH_TOP
+    if (rc) return rc;
+    SCG_LAUNCH_CHECK();
     return 0;
 }
 
@@ -312,8 +439,8 @@ static int ensure_mirror(scg_ctx *ctx) {
 
 extern "C" int scg_agent_manage(scg_ctx_t *ctx, scg_agent_t *ag, scg_xchg_t *xchg, void *stream) {
     if (!ctx || !ag || !ag->ctl || !ag->theta || !ag->n_success) return SCG_EINVAL;
-    if (ag->K != ctx->K || ag->K < 1 || ag->K > SCG_MAX_OPTIONS || ag->clf_steps < 0) return SCG_EINVAL;
-    if (xchg && (!ag->n_success_global || xchg->K != ag->K)) return SCG_EINVAL;
+    if (ag->K + ag->top_slots != ctx->K || ag->K < 1 || ctx->K > SCG_MAX_OPTIONS || ag->clf_steps < 0) return SCG_EINVAL;
+    if (xchg && (!ag->n_success_global || xchg->K != ctx->K)) return SCG_EINVAL;
     if (xchg && *xchg->h_status) return SCG_EPEER;
     int rc;
     if ((rc = ensure_mirror(ctx))) return rc;
@@ -333,8 +460,10 @@ extern "C" int scg_agent_manage(scg_ctx_t *ctx, scg_agent_t *ag, scg_xchg_t *xch
         a.status = xchg->d_status;
         a.timeout_cycles = xchg->timeout_cycles;
     }
+    if ((rc = scg_prof_push(ctx, 5, (cudaStream_t)stream, false))) return rc;
     k_manage<<<1, MANAGE_NT, 0, (cudaStream_t)stream>>>(a);
     SCG_LAUNCH_CHECK();
+    if ((rc = scg_prof_push(ctx, 5, (cudaStream_t)stream, true))) return rc;
     if (ctx->deterministic) {   // reproducible runs: the host sizes the next launches with exact knowledge
         SCG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
         ag->n_active = std::max(ag->n_active, (int)ctx->h_ctl->n_active);

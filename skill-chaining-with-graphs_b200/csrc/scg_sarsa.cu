@@ -598,9 +598,10 @@ __global__ void k_make_rec(int B, const float *__restrict__ x, const float *__re
 }
 
 // W += (alpha * alpha_scale_f) * (dW * (steps / cnt_k));  refresh the packed copy;  dW <- 0
+// Slots k >= K_opt hold the top-level learner (oracle/option.py): step size alpha_top, mean over the window's events.
 template <int N1>
-__global__ void k_apply(int K, float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ dW,
-                        const int *__restrict__ cnt, float alpha, float steps) {
+__global__ void k_apply(int K, int K_opt, float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ dW,
+                        const int *__restrict__ cnt, float alpha, float alpha_top, float steps) {
     constexpr int F = N1 * N1 * N1 * N1;
     int n = K * SCG_A * F;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -612,8 +613,9 @@ __global__ void k_apply(int K, float *__restrict__ W, float *__restrict__ Wt, fl
 #pragma unroll
             for (int j = 0; j < 4; ++j) { int q = d % N1; ss += q * q; d /= N1; }
             float as = (ss == 0) ? 1.0f : (float)(1.0 / sqrt((double)ss));
-            float scale = __fdiv_rn(steps, (float)c);
-            w = __fadd_rn(w, __fmul_rn(__fmul_rn(alpha, as), __fmul_rn(dW[i], scale)));
+            const bool top = k >= K_opt;
+            float scale = __fdiv_rn(top ? 1.0f : steps, (float)c);
+            w = __fadd_rn(w, __fmul_rn(__fmul_rn(top ? alpha_top : alpha, as), __fmul_rn(dW[i], scale)));
             W[i] = w;
         }
         Wt[((size_t)f * K + k) * SCG_WT_STRIDE + a] = w;
@@ -829,13 +831,18 @@ extern "C" int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const flo
 
 extern "C" int scg_apply(int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha, int window_steps,
                          void *stream) {
+    return scg_apply_top(order, K, K, W, Wt, dW, cnt, alpha, 0.f, window_steps, stream);
+}
+
+extern "C" int scg_apply_top(int order, int K, int K_opt, float *W, float *Wt, float *dW, int *cnt, float alpha,
+                             float alpha_top, int window_steps, void *stream) {
     if (K < 1 || K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
-    if (!W || !Wt || !dW || !cnt) return SCG_EINVAL;
+    if (!W || !Wt || !dW || !cnt || K_opt < 0 || K_opt > K) return SCG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     float steps = (float)std::max(window_steps, 1);
     int F = scg_pow4(order + 1);
     int grid = std::max(1, std::min((K * SCG_A * F + 255) / 256, SCG_NUM_SMS * 8));
-    DISPATCH_ORDER(order, k_apply<N1><<<grid, 256, 0, st>>>(K, W, Wt, dW, cnt, alpha, steps));
+    DISPATCH_ORDER(order, k_apply<N1><<<grid, 256, 0, st>>>(K, K_opt, W, Wt, dW, cnt, alpha, alpha_top, steps));
     SCG_LAUNCH_CHECK();
     k_zero_int<<<1, 32, 0, st>>>(K, cnt);
     SCG_LAUNCH_CHECK();

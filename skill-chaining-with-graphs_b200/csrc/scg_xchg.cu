@@ -29,9 +29,9 @@
 #include "scg_xchg.cuh"
 
 struct SyncArgs {
-    int n, K, slices, rank, world;
+    int n, K, K_opt, slices, rank, world;
     uint32_t seq;
-    float alpha, steps;
+    float alpha, alpha_top, steps;
     float *W, *Wt, *dW;
     int *cnt;
     const int *nsucc_local;   // [K] this rank's option success counters (may be NULL)
@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
 #pragma unroll
             for (int q = 0; q < 4; ++q) { int dg = d % N1; ss += dg * dg; d /= N1; }
             const float as = (ss == 0) ? 1.0f : (float)(1.0 / sqrt((double)ss));
-            const float scale = __fdiv_rn(a.steps, (float)cn);
-            w = __fadd_rn(w, __fmul_rn(__fmul_rn(a.alpha, as), __fmul_rn(v, scale)));
+            const bool top = k >= a.K_opt;       // top-level learner slots: alpha_top, mean over the window's events
+            const float scale = __fdiv_rn(top ? 1.0f : a.steps, (float)cn);
+            w = __fadd_rn(w, __fmul_rn(__fmul_rn(top ? a.alpha_top : a.alpha, as), __fmul_rn(v, scale)));
             a.W[j] = w;
         }
         a.Wt[((size_t)f * a.K + k) * SCG_WT_STRIDE + act] = w;
@@ -235,13 +236,19 @@ extern "C" int scg_xchg_status(scg_xchg_t *x, int *timed_out) {
 // dW (already reduced over this rank's slabs) and cnt -> summed over ranks -> applied; dW and cnt zeroed
 extern "C" int scg_xchg_sync(scg_xchg_t *x, int order, int K, float *W, float *Wt, float *dW, int *cnt, float alpha,
                              int window_steps, const int *nsucc_local, int *nsucc_global, void *stream) {
-    if (!x || !W || !Wt || !dW || !cnt) return SCG_EINVAL;
+    return scg_xchg_sync_top(x, order, K, K, W, Wt, dW, cnt, alpha, 0.f, window_steps, nsucc_local, nsucc_global, stream);
+}
+
+extern "C" int scg_xchg_sync_top(scg_xchg_t *x, int order, int K, int K_opt, float *W, float *Wt, float *dW, int *cnt,
+                                 float alpha, float alpha_top, int window_steps, const int *nsucc_local,
+                                 int *nsucc_global, void *stream) {
+    if (!x || !W || !Wt || !dW || !cnt || K_opt < 0 || K_opt > K) return SCG_EINVAL;
     if (K != x->K || K * SCG_A * scg_pow4(order + 1) != x->n) return SCG_EINVAL;
     for (int r = 0; r < x->world; ++r)
         if (!x->d_peer[r]) return SCG_EINVAL;   // not connected
     if (*x->h_status) return SCG_EPEER;         // an earlier exchange timed out: the replicas are no longer in step
     SyncArgs a;
-    a.n = x->n; a.K = K; a.slices = x->slices; a.rank = x->rank; a.world = x->world;
+    a.n = x->n; a.K = K; a.K_opt = K_opt; a.alpha_top = alpha_top; a.slices = x->slices; a.rank = x->rank; a.world = x->world;
     a.seq = ++x->seq;
     a.alpha = alpha; a.steps = (float)std::max(window_steps, 1);
     a.W = W; a.Wt = Wt; a.dW = dW; a.cnt = cnt; a.ticket = x->d_ticket;

@@ -66,15 +66,19 @@ def _dev(t, dtype):
 
 class OptionSet:
     def __init__(self, n_options, order, batch, gamma=0.99, lam=0.9, alpha=1e-3, epsilon=0.05, seed=0,
-                 env_offset=0, device=None, deterministic=False):
+                 env_offset=0, device=None, deterministic=False, top_slots=0, alpha_top=1e-3):
         import torch
         if not torch.cuda.is_available():
             raise _lib.ScgError("OptionSet needs a CUDA device: there is no CPU fallback")
         self.torch = torch
         self.lib = _lib.load()
         self.K = int(n_options)
-        if not 1 <= self.K <= _lib.MAX_OPTIONS:
-            raise ValueError(f"n_options must be in 1..{_lib.MAX_OPTIONS}")
+        # top-level learner (oracle/option.py OptionSet(top_slots=...)): Q_top(s, j) is row j % 5 of slot K + j // 5
+        self.top_slots = int(top_slots)
+        self.K_all = self.K + self.top_slots
+        self.alpha_top = float(alpha_top)
+        if not 1 <= self.K or not self.K_all <= _lib.MAX_OPTIONS or self.top_slots < 0:
+            raise ValueError(f"n_options (+ top-level slots) must be in 1..{_lib.MAX_OPTIONS}")
         self.basis = FourierBasis(order)
         self.order = self.basis.order
         self.F = self.basis.n_features
@@ -84,17 +88,17 @@ class OptionSet:
         self.env_offset = int(env_offset)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         z = dict(dtype=torch.float32, device=self.device)
-        self.W = torch.zeros((self.K, N_ACTIONS, self.F), **z)
-        self.Wt = torch.zeros((self.F, self.K, 8), **z)
+        self.W = torch.zeros((self.K_all, N_ACTIONS, self.F), **z)
+        self.Wt = torch.zeros((self.F, self.K_all, 8), **z)
         self.theta = torch.zeros((self.K, N_PSI), **z)
         self._trace = torch.zeros((self.B, N_ACTIONS, self.F), **z)
-        self._dW = torch.zeros((self.K, N_ACTIONS, self.F), **z)
+        self._dW = torch.zeros((self.K_all, N_ACTIONS, self.F), **z)
         self._pre_read = None        # set by SkillChainAgent: folds its open window in before a read
         self._on_weights_changed = None   # set by SkillChainAgent: its carried Q_o(s, a) goes stale
-        self.cnt = torch.zeros(self.K, dtype=torch.int32, device=self.device)
+        self.cnt = torch.zeros(self.K_all, dtype=torch.int32, device=self.device)
         self.window_steps = 0
         self._ctx = C.c_void_p()
-        check(self.lib.scg_ctx_create(self.order, self.K, C.byref(self._ctx)))
+        check(self.lib.scg_ctx_create(self.order, self.K_all, C.byref(self._ctx)))
         if deterministic:       # fixed-order dW reduction: bit-reproducible runs, ~1 us per step slower at 65,536 envs
             check(self.lib.scg_ctx_set_deterministic(self._ctx, 1))
 
@@ -126,13 +130,13 @@ class OptionSet:
 
     # -- weights ---------------------------------------------------------------------------------
     def set_weights(self, W):
-        self.W.copy_(_dev(W, self.torch.float32).reshape(self.K, N_ACTIONS, self.F))
+        self.W.copy_(_dev(W, self.torch.float32).reshape(self.K_all, N_ACTIONS, self.F))
         self.pack()
         if self._on_weights_changed is not None:
             self._on_weights_changed()
 
     def pack(self):
-        check(self.lib.scg_pack_weights(self.order, self.K, ptr(self.W), ptr(self.Wt), _lib.current_stream()))
+        check(self.lib.scg_pack_weights(self.order, self.K_all, ptr(self.W), ptr(self.Wt), _lib.current_stream()))
 
     # -- K2 --------------------------------------------------------------------------------------
     def q(self, state, option_ids, soa=None):
@@ -141,9 +145,20 @@ class OptionSet:
         B = s.shape[1]
         o = _dev(option_ids, torch.int32)
         Q = torch.empty((B, N_ACTIONS), dtype=torch.float32, device=self.device)
-        check(self.lib.scg_q_eval(self.order, self.K, B, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), ptr(o),
+        check(self.lib.scg_q_eval(self.order, self.K_all, B, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), ptr(o),
                                   ptr(self.Wt), ptr(Q), _lib.current_stream()))
         return Q
+
+    def q_top(self, state, soa=None):
+        """Q_top(s, j) for every option slot j: (B, K) (rows of the top-level slots of W)."""
+        torch = self.torch
+        s = _as_soa(state) if soa is None else soa
+        B = s.shape[1]
+        cols = []
+        for sl in range(self.top_slots):
+            ids = torch.full((B,), self.K + sl, dtype=torch.int32, device=self.device)
+            cols.append(self.q(None, ids, soa=s))
+        return torch.cat(cols, dim=1)[:, :self.K] if cols else torch.zeros((B, 0), device=self.device)
 
     def select(self, Q, step, stream=_lib.STREAM_ACTION):
         torch = self.torch
@@ -164,7 +179,7 @@ class OptionSet:
         r = _dev(r, torch.float32)
         d = _dev(done, torch.uint8)
         delta = torch.empty(B, dtype=torch.float32, device=self.device)
-        check(self.lib.scg_td_error(self.order, self.K, B, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), ptr(a), ptr(r),
+        check(self.lib.scg_td_error(self.order, self.K_all, B, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]), ptr(a), ptr(r),
                                     ptr(s2[0]), ptr(s2[1]), ptr(s2[2]), ptr(s2[3]), ptr(a2), ptr(d), ptr(o),
                                     ptr(self.Wt), self.gamma, ptr(delta), _lib.current_stream()))
         return delta
@@ -193,8 +208,9 @@ class OptionSet:
         """Fold the window's dW into W (call after any cross-rank allreduce of dW / cnt)."""
         if self._pre_read is not None:
             self._pre_read()
-        check(self.lib.scg_apply(self.order, self.K, ptr(self.W), ptr(self.Wt), ptr(self._dW), ptr(self.cnt),
-                                 self.alpha, max(self.window_steps, 1), _lib.current_stream()))
+        check(self.lib.scg_apply_top(self.order, self.K_all, self.K, ptr(self.W), ptr(self.Wt), ptr(self._dW),
+                                     ptr(self.cnt), self.alpha, self.alpha_top, max(self.window_steps, 1),
+                                     _lib.current_stream()))
         self.window_steps = 0
         if self._on_weights_changed is not None:
             self._on_weights_changed(applied=True)

@@ -483,6 +483,86 @@ def test_agent_run_and_manage_promotes_option(scg, torch):
     assert int((ag.option == 1).sum()) > 0                 # the new gestating option is being executed
 
 
+# ---- top-level SMDP learner over the options ------------------------------------------
+@pytest.mark.parametrize("order,K,n_active,name,B,launch", [
+    (3, 4, 2, "easy", 3000, "window"),
+    (3, 4, 3, "hard", 3000, "step"),
+    (2, 7, 5, "easy", 2000, "window"),        # 7 option slots -> two top-level slots
+    (5, 8, 3, "hard", 500, "window"),
+    (5, 8, 6, "hard", 500, "step"),           # weights through the global path
+])
+def test_top_level_learner_matches_oracle(scg, torch, order, K, n_active, name, B, launch):
+    """Option choice by the learned SMDP value function Q_top (oracle/agent.py top_level=True): per step the TD errors
+    of the options AND of the top-level learner (delta_top at every option termination), the chosen options (equal to
+    the oracle's own eps_top-greedy choice except at Q_top near-ties), and after every apply all weight slots -
+    the options' and the top-level learner's - element-wise within 1e-4."""
+    from oracle_replay import activate, default_theta
+    manual = launch == "step"
+    kw = dict(sync_interval=1000 if manual else 4, option_timeout=4, epsilon=0.1, alpha=5e-3, max_episode_steps=9,
+              top_level=True, alpha_top=2e-5, epsilon_top=0.15)
+    oag, gag = _paired_agents(scg, torch, B, order, K, name, 29, window=4, **kw)
+    assert gag.options.K_all == oag.options.K_all == K + (K + 4) // 5
+    oag.opt_s0 = oag.env.state.copy()
+    theta = default_theta(K)
+    activate(oag, theta, n_active)
+    _set_gpu_options(gag, torch, theta, n_active)
+    opt0 = np.random.default_rng(3).integers(0, n_active + 1, B).astype(np.int32)
+    oag.option = opt0.copy()
+    gag.option.copy_(torch.as_tensor(opt0))
+    W0 = oag.options.W.copy()
+    n_term, n_dis_o = 0, 0
+    for w in range(4):
+        n = 4 if w < 3 else 1
+        wl0 = int(gag._struct.win_len)
+        if not manual:
+            pre, dl, acts, opts, term = _gpu_run_window(gag, torch, n)
+        else:
+            parts = [_gpu_run_window(gag, torch, 1) for _ in range(n)]
+            pre = np.concatenate([p[0] for p in parts]); dl = np.concatenate([p[1] for p in parts])
+            acts = np.concatenate([p[2][:1] for p in parts] + [parts[-1][2][1:]])
+            opts = np.concatenate([p[3][:1] for p in parts] + [parts[-1][3][1:]])
+            term = np.concatenate([p[4] for p in parts])
+        top = gag.win_top[wl0:wl0 + n].cpu().numpy()                    # (n, B, 8): s0, delta_top, option
+        for t in range(n):
+            what = f"window {w} step {t}"
+            assert np.array_equal(oag.env.state.view(np.uint32), pre[t].view(np.uint32)), f"{what}: pre-step state"
+            s0_before, o_before = oag.opt_s0.copy(), oag.option.copy()
+            out = oag.step(follow=dict(action=acts[t + 1], option=opts[t + 1]))
+            assert np.array_equal(out["term"], term[t]), f"{what}: termination flags"
+            assert_close(dl[t], out["delta"], what=f"{what}: TD error")
+            tm = out["term"]
+            if tm.any():
+                assert np.array_equal(top[t, tm, :4].view(np.uint32), s0_before[tm].view(np.uint32)), f"{what}: s0"
+                assert np.array_equal(top[t, tm, 5].copy().view(np.int32), o_before[tm])
+                assert_close(top[t, tm, 4], out["delta_top"][tm], what=f"{what}: top-level TD error")
+                dis = out["own_option"] != opts[t + 1]
+                if dis.any():                                          # only at a near-tie of the oracle's Q_top row
+                    Q = out["Qtop"][dis].astype(np.float64)
+                    gap = Q.max(axis=1) - Q[np.arange(len(Q)), opts[t + 1][dis]]
+                    fin = np.isfinite(out["Qtop"])
+                    assert gap.max() <= 1e-4 * max(1e-30, float(np.abs(out["Qtop"][fin]).mean())), f"{what}: option choice"
+                n_dis_o += int(dis.sum())
+            _check_choices(dict(out, own_option=opts[t + 1]), acts[t + 1], opts[t + 1], what)
+            n_term += int(tm.sum())
+        assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), oag.env.state.view(np.uint32))
+        if w < 3:
+            if manual:
+                assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+                assert_close(gag.options.dW.cpu().numpy()[K:], oag.options.dW[K:], what=f"top-level dW of window {w}")
+                assert_close(gag.options.dW.cpu().numpy()[:K], oag.options.dW[:K], what=f"dW of window {w}")
+                gag.sync()
+                oag.options.apply()
+            gW = gag.options.W.cpu().numpy()
+            assert_close(gW[:K], oag.options.W[:K], what=f"option weights after apply {w}")
+            assert_close(gW[K:] - W0[K:], oag.options.W[K:] - W0[K:], what=f"top-level weights after apply {w}")
+            assert np.abs(oag.options.W[K:] - W0[K:]).max() > 1e-4
+    assert n_term > B // 2 and n_dis_o <= B // 100
+    assert len(np.unique(oag.option)) >= min(3, n_active + 1)         # the learner really spreads over several options
+    assert np.array_equal(gag.options.cnt.cpu().numpy(), oag.options.cnt)
+    for got, want in ((gag.start_vxy, oag.opt_s0[:, 2:]), (gag.opt_ret, oag.opt_R), (gag.opt_disc, oag.opt_disc)):
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+
+
 # ---- controller on the device: example rings and promote-and-fit -------------------------------------------
 @pytest.mark.parametrize("B,cap,launch", [(3000, 64, "window"), (3000, 64, "step"), (777, 4096, "window"), (40000, 1000, "window")])
 def test_example_rings_match_oracle_past_capacity(scg, torch, B, cap, launch):
