@@ -394,13 +394,13 @@ def run_ours(args):
             if i == 5:
                 barrier()
                 ev[0].record()
-            allreduce_deltas(o._dW, o.cnt, ag.pg)
+            allreduce_deltas(o._dW, o._cnt, ag.pg)
             o.apply()
         ev[1].record()
         torch.cuda.synchronize()
         nccl_us = reduce_max([ev[0].elapsed_time(ev[1]) / reps * 1e3])[0]
         sync_cmp = {"p2p_kernel_us": reduce_max([m["side_ms"][3] * 1e3])[0] if m["backend"] == "p2p" else None,
-                    "nccl_allreduce_x2_plus_apply_us": nccl_us, "payload_bytes": int(o._dW.numel() * 4 + o.cnt.numel() * 4),
+                    "nccl_allreduce_x2_plus_apply_us": nccl_us, "payload_bytes": int(o._dW.numel() * 4 + o._cnt.numel() * 4),
                     "note": "per sync, max over ranks; the p2p figure includes the wait for the slowest rank to arrive"}
     # ---- the north-star configuration, in the same process, at every N ----
     north = None

@@ -278,7 +278,7 @@ class SkillChainAgent:
         g.ex_xy, g.ex_label, g.ex_count = self._ex_xy.data_ptr(), self._ex_label.data_ptr(), self._ex_count.data_ptr()
         g.win_top = self.win_top.data_ptr() if cfg.top_level else None
         g.trace, g.W, g.Wt, g.theta = o._trace.data_ptr(), o.W.data_ptr(), o.Wt.data_ptr(), o.theta.data_ptr()
-        g.dW, g.cnt = o._dW.data_ptr(), o.cnt.data_ptr()
+        g.dW, g.cnt = o._dW.data_ptr(), o._cnt.data_ptr()
         return g
 
     def _sync_struct(self):
@@ -440,12 +440,12 @@ class SkillChainAgent:
         o, g = self.options, self._struct
         self.flush()
         if self._xchg is not None:
-            check(self.lib.scg_xchg_sync_top(self._xchg, o.order, o.K_all, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o.cnt),
+            check(self.lib.scg_xchg_sync_top(self._xchg, o.order, o.K_all, o.K, ptr(o.W), ptr(o.Wt), ptr(o._dW), ptr(o._cnt),
                                              self.cfg.alpha, self.cfg.alpha_top, max(int(g.window_steps), 1),
                                              ptr(self.n_success), ptr(self.n_success_global), _lib.current_stream()))
             o.window_steps = 0
         else:
-            allreduce_deltas(o._dW, o.cnt, self.pg)
+            allreduce_deltas(o._dW, o._cnt, self.pg)
             o.window_steps = int(g.window_steps)
             o.apply()
         g.window_steps = 0
@@ -544,7 +544,7 @@ class SkillChainAgent:
         c = self.controller_state(sync=True)
         arrs = {k.lstrip("_"): getattr(self, k).cpu().numpy() for k in self._CKPT_TENSORS}
         arrs.update(W=o.W.cpu().numpy(), theta=o.theta.cpu().numpy(), trace=o._trace.cpu().numpy(),
-                    dW=o._dW.cpu().numpy(), cnt=o.cnt.cpu().numpy(), state=self.s.cpu().numpy(),
+                    dW=o._dW.cpu().numpy(), cnt=o._cnt.cpu().numpy(), state=self.s.cpu().numpy(),
                     parents=np.array(c["parents"], dtype=np.uint32),
                     meta=np.array([c["n_active"], c["active_mask"], int(g.step), int(g.window_steps), c["n_promotions"],
                                    c["last_promotion_step"]], dtype=np.int64))
@@ -564,7 +564,7 @@ class SkillChainAgent:
         o.theta.copy_(torch.as_tensor(z["theta"]))
         o._trace.copy_(torch.as_tensor(z["trace"]))
         o._dW.copy_(torch.as_tensor(z["dW"]))
-        o.cnt.copy_(torch.as_tensor(z["cnt"]))
+        o._cnt.copy_(torch.as_tensor(z["cnt"]))
         o.pack()
         self.s.copy_(torch.as_tensor(z["state"]))
         self.torch.cuda.current_stream().synchronize()

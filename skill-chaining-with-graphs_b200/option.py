@@ -95,7 +95,7 @@ class OptionSet:
         self._dW = torch.zeros((self.K_all, N_ACTIONS, self.F), **z)
         self._pre_read = None        # set by SkillChainAgent: folds its open window in before a read
         self._on_weights_changed = None   # set by SkillChainAgent: its carried Q_o(s, a) goes stale
-        self.cnt = torch.zeros(self.K_all, dtype=torch.int32, device=self.device)
+        self._cnt = torch.zeros(self.K_all, dtype=torch.int32, device=self.device)
         self.window_steps = 0
         self._ctx = C.c_void_p()
         check(self.lib.scg_ctx_create(self.order, self.K_all, C.byref(self._ctx)))
@@ -120,6 +120,13 @@ class OptionSet:
         if self._pre_read is not None:
             self._pre_read()
         return self._trace
+
+    @property
+    def cnt(self):
+        """Updates per weight slot accumulated since the last apply (K_all,)."""
+        if self._pre_read is not None:
+            self._pre_read()
+        return self._cnt
 
     @property
     def dW(self):
@@ -198,7 +205,7 @@ class OptionSet:
         gl = float(np.float32(self.gamma) * np.float32(self.lam))
         check(self.lib.scg_sarsa_update(self._ctx, self.B, ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(a),
                                         ptr(o), ptr(delta), ptr(d), ptr(m), gl, ptr(self._trace), ptr(self._dW),
-                                        ptr(self.cnt), _lib.current_stream()))
+                                        ptr(self._cnt), _lib.current_stream()))
         return delta
 
     def tick(self):
@@ -209,7 +216,7 @@ class OptionSet:
         if self._pre_read is not None:
             self._pre_read()
         check(self.lib.scg_apply_top(self.order, self.K_all, self.K, ptr(self.W), ptr(self.Wt), ptr(self._dW),
-                                     ptr(self.cnt), self.alpha, self.alpha_top, max(self.window_steps, 1),
+                                     ptr(self._cnt), self.alpha, self.alpha_top, max(self.window_steps, 1),
                                      _lib.current_stream()))
         self.window_steps = 0
         if self._on_weights_changed is not None:
