@@ -499,7 +499,7 @@ def test_top_level_learner_matches_oracle(scg, torch, order, K, n_active, name, 
     from oracle_replay import activate, default_theta
     manual = launch == "step"
     kw = dict(sync_interval=1000 if manual else 4, option_timeout=4, epsilon=0.1, alpha=5e-3, max_episode_steps=9,
-              top_level=True, alpha_top=2e-5, epsilon_top=0.15)
+              top_level=True, alpha_top=1e-3, epsilon_top=0.15)
     oag, gag = _paired_agents(scg, torch, B, order, K, name, 29, window=4, **kw)
     assert gag.options.K_all == oag.options.K_all == K + (K + 4) // 5
     oag.opt_s0 = oag.env.state.copy()
