@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top(int n, int K, int top_slots, con
     constexpr int FPT = (F + TOP_NT - 1) / TOP_NT;              // features per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);           // [K][F]: row j = option j (slot K + j / 5, row j % 5)
-    float2 *tab = reinterpret_cast<float2 *>(acc + (size_t)K * F);          // [TOP_EB][4][N1]
+    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * F + 3) & ~(size_t)3));   // [TOP_EB][4][N1], 16-byte aligned
     float *dl = reinterpret_cast<float *>(tab + TOP_EB * 4 * N1);           // [TOP_EB] delta_top
     int *oo = reinterpret_cast<int *>(dl + TOP_EB);                         // [TOP_EB] option
     int *list = oo + TOP_EB;                                                 // [chunk] flat indices of this CTA's events
@@ -252,7 +252,7 @@ int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st) {
     const int grid = (int)std::max<long long>(1, std::min<long long>(TOP_CTAS, (n + 4095) / 4096));
     const int chunk = (int)((n + grid - 1) / grid);
     const int N1 = ctx->order + 1;
-    const size_t smem = (size_t)ag->K * ctx->F * sizeof(float) + (size_t)TOP_EB * 4 * N1 * sizeof(float2) +
+    const size_t smem = ((((size_t)ag->K * ctx->F + 3) & ~(size_t)3)) * sizeof(float) + (size_t)TOP_EB * 4 * N1 * sizeof(float2) +
                         TOP_EB * (sizeof(float) + sizeof(int)) + (size_t)chunk * sizeof(int);
     if (smem > 200 * 1024) return SCG_ELIMIT;
     const float4 *top = reinterpret_cast<const float4 *>(ag->win_top);
