@@ -125,6 +125,10 @@ int scg_apply_top(int order, int K, int K_opt, float *W, float *Wt, float *dW, i
  * mirrors oracle/option.py OptionSet.initiation_prob / clf_grad / fit_initiation. */
 int scg_clf_eval(int B, const float *x, const float *y, const float *theta /* [K][6] */, int K,
                  float *p /* [B][K] */, void *stream);
+/* mirrors OptionSet.initiation: inside[b][k] = (theta_k . psi(x_b, y_b) >= 0), the logit formed in fp32 with one rounding
+ * per operation in the oracle's order (initiation_logit), so the decision is bit-identical to the oracle's */
+int scg_clf_decide(int B, const float *x, const float *y, const float *theta /* [K][6] */, int K,
+                   uint8_t *inside /* [B][K] */, void *stream);
 int scg_clf_grad(int N, const float *X /* [N][2] */, const uint8_t *y, const float *theta_k /* [6] */,
                  float *grad /* [6], overwritten */, void *stream);
 int scg_clf_fit(int N, const float *X, const uint8_t *y, float *theta_k /* [6] in/out */, int steps,

@@ -36,7 +36,8 @@ in dW[K:], and apply() steps those slots with alpha_top and the MEAN over the wi
 (cnt[K:] all hold the event count):  W[k] += alpha_top * alpha_scale (.) dW[k] / cnt[k]  for k >= K.
 
 Initiation classifier of option k: p = sigmoid(theta_k . psi(x, y)), psi = (1, x, y, x^2, xy, y^2);
-I_k(s) = p >= 0.5.  fit: theta -= lr * mean_i (p_i - y_i) psi_i, a fixed number of steps.
+I_k(s) = (p >= 0.5), decided on the fp32 logit z = theta_k . psi >= 0 (initiation_logit: fixed operation order, one
+rounding per operation, bit-reproducible).  fit: theta -= lr * mean_i (p_i - y_i) psi_i, a fixed number of steps.
 """
 import numpy as np
 
@@ -254,8 +255,27 @@ class OptionSet:
         psi = logistic_features(state).astype(np.float64)
         return sigmoid(psi @ self.theta.T.astype(np.float64))       # (B, K)
 
+    def initiation_logit(self, state):
+        """theta_k . psi(x, y) in fp32 with one rounding per operation, in this order (B, K):
+               z = ((((t0 + t1*x) + t2*y) + t3*(x*x)) + t4*(x*y)) + t5*(y*y)
+        The initiation DECISION is taken on this value, so that it is reproducible bit for bit (a decision taken on a
+        rounded probability would flip for states within an ulp of the boundary, e.g. a start position that lies
+        exactly on a classifier's edge)."""
+        s = np.asarray(state, dtype=np.float32)
+        s = s.reshape(-1, s.shape[-1])
+        x, y = s[:, 0:1], s[:, 1:2]
+        t = self.theta.astype(np.float32)[None, :, :]
+        xx, xy, yy = x * x, x * y, y * y                       # fp32 products
+        z = t[:, :, 0] + t[:, :, 1] * x
+        z = z + t[:, :, 2] * y
+        z = z + t[:, :, 3] * xx
+        z = z + t[:, :, 4] * xy
+        z = z + t[:, :, 5] * yy
+        return z.astype(np.float32)
+
     def initiation(self, state):
-        return self.initiation_prob(state) >= f32(0.5)
+        """I_k(s)  <=>  sigmoid(z) >= 0.5  <=>  z >= 0, with z = initiation_logit(s)."""
+        return self.initiation_logit(state) >= f32(0.0)
 
     def clf_grad(self, k, X, y):
         """mean_i (p_i - y_i) psi_i for option k: float32 (6,)."""

@@ -84,6 +84,7 @@ _SIGS = {
     "scg_apply": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P]),
     "scg_apply_top": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int, _P]),
     "scg_clf_eval": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "scg_clf_decide": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, _P, _P]),
     "scg_clf_grad": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "scg_clf_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_float, _P]),
     "scg_agent_step": (C.c_int, [_P, _P, C.POINTER(AgentStruct), _P]),

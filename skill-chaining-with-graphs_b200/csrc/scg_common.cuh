@@ -380,22 +380,24 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
     }
 }
 
-// initiation bits (oracle/agent.py initiation_bits): bit k iff active and theta_k . psi(x, y) >= 0
-// (sigmoid(z) >= 0.5  <=>  z >= 0).
+// initiation bits (oracle/agent.py initiation_bits): bit k iff active and z_k >= 0 (sigmoid(z) >= 0.5  <=>  z >= 0), with
+// z_k = theta_k . psi(x, y) formed exactly as oracle/option.py initiation_logit does - fp32, one rounding per operation,
+// the same order - so that the decision is bit-identical to the oracle's, also for states on a classifier's boundary.
+__device__ __forceinline__ float scg_init_logit(const float *__restrict__ t, float x, float y, float xx, float xy, float yy) {
+    float z = __fadd_rn(__ldg(t), __fmul_rn(__ldg(t + 1), x));
+    z = __fadd_rn(z, __fmul_rn(__ldg(t + 2), y));
+    z = __fadd_rn(z, __fmul_rn(__ldg(t + 3), xx));
+    z = __fadd_rn(z, __fmul_rn(__ldg(t + 4), xy));
+    z = __fadd_rn(z, __fmul_rn(__ldg(t + 5), yy));
+    return z;
+}
 __device__ __forceinline__ uint32_t scg_init_bits(const float *__restrict__ theta, int K, uint32_t active_mask,
                                                   float x, float y) {
     uint32_t bits = 0;
-    float xx = x * x, xy = x * y, yy = y * y;
+    const float xx = __fmul_rn(x, x), xy = __fmul_rn(x, y), yy = __fmul_rn(y, y);
     for (int k = 0; k < K; ++k) {
         if (!((active_mask >> k) & 1u)) continue;
-        const float *t = theta + k * SCG_N_PSI;
-        float zz = __ldg(t);
-        zz = fmaf(__ldg(t + 1), x, zz);
-        zz = fmaf(__ldg(t + 2), y, zz);
-        zz = fmaf(__ldg(t + 3), xx, zz);
-        zz = fmaf(__ldg(t + 4), xy, zz);
-        zz = fmaf(__ldg(t + 5), yy, zz);
-        if (zz >= 0.f) bits |= (1u << k);
+        if (scg_init_logit(theta + k * SCG_N_PSI, x, y, xx, xy, yy) >= 0.f) bits |= (1u << k);
     }
     return bits;
 }

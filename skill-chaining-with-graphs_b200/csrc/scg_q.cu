@@ -131,6 +131,15 @@ __global__ void k_clf_eval(int B, const float *__restrict__ x, const float *__re
     }
 }
 
+// initiation decisions I_k(s) = (theta_k . psi >= 0) on the fp32 logit of scg_init_logit: bit-identical to the oracle
+__global__ void k_clf_decide(int B, const float *__restrict__ x, const float *__restrict__ y,
+                             const float *__restrict__ theta, int K, uint8_t *__restrict__ out) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const uint32_t bits = scg_init_bits(theta, K, 0xffffffffu, x[b], y[b]);
+        for (int k = 0; k < K; ++k) out[(size_t)b * K + k] = (bits >> k) & 1u;
+    }
+}
+
 // mean_i (p_i - y_i) psi_i with a single CTA: per-thread partial sums, warp shuffles, smem.  Each thread keeps up to
 // CLF_CACHE of its examples in registers, so the gradient-descent loop of k_clf_fit touches global memory only for
 // the examples beyond 1024 * CLF_CACHE.
@@ -277,6 +286,15 @@ extern "C" int scg_clf_eval(int B, const float *x, const float *y, const float *
     if (B < 0 || (B > 0 && (!x || !y || !theta || !p))) return SCG_EINVAL;
     if (B == 0) return 0;
     k_clf_eval<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, x, y, theta, K, p);
+    SCG_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int scg_clf_decide(int B, const float *x, const float *y, const float *theta, int K, uint8_t *inside, void *stream) {
+    if (K < 1 || K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
+    if (B < 0 || (B > 0 && (!x || !y || !theta || !inside))) return SCG_EINVAL;
+    if (B == 0) return 0;
+    k_clf_decide<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, x, y, theta, K, inside);
     SCG_LAUNCH_CHECK();
     return 0;
 }

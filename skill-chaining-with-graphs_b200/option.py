@@ -232,7 +232,13 @@ class OptionSet:
         return p
 
     def initiation(self, state):
-        return self.initiation_prob(state) >= 0.5
+        """I_k(s) for every option: bool (B, K), decided on the fp32 logit exactly as the oracle does (bit-identical)."""
+        torch = self.torch
+        s = _as_soa(state)
+        B = s.shape[1]
+        out = torch.empty((B, self.K), dtype=torch.uint8, device=self.device)
+        check(self.lib.scg_clf_decide(B, ptr(s[0]), ptr(s[1]), ptr(self.theta), self.K, ptr(out), _lib.current_stream()))
+        return out.bool()
 
     def clf_grad(self, k, X, y):
         torch = self.torch

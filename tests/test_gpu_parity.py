@@ -280,6 +280,39 @@ def test_classifier_eval_grad_fit_match_oracle(scg, torch):
     assert_close(gp, op)
 
 
+def test_initiation_decisions_bit_identical_including_boundary_states(scg, torch):
+    """I_k(s) is decided on the fp32 logit with the oracle's operation order: identical decisions for random states,
+    for states exactly on a classifier's edge (x = 0.2 with theta = (2, -10, ...): the easy map's start position) and
+    for states one ulp either side of it."""
+    from oracle_replay import default_theta
+    K = 8
+    theta = default_theta(K)
+    rng = np.random.default_rng(12)
+    theta[6:] = rng.standard_normal((2, 6)).astype(np.float32) * 3
+    oset, gset = oracle.OptionSet(K, 1, 1), scg.OptionSet(K, 1, 1)
+    oset.theta[:] = theta
+    gset.theta.copy_(torch.as_tensor(theta))
+    S = rng.random((200000, 4)).astype(np.float32)
+    edge = np.float32(0.2)
+    S[:3000, 0] = np.nextafter(edge, np.float32(rng.choice([0, 1])), dtype=np.float32)
+    S[3000:6000, 0] = edge
+    S[6000:9000, 1] = np.float32(0.45)                       # theta[1] = (4.5, 0, -10): y <= 0.45
+    S[9000:12000, 0] = np.float32(0.6)                       # theta[0] = (-6, 10): x >= 0.6
+    # points on the disc's boundary (quadratic terms) by bisection of the oracle's own logit along rays
+    for i in range(12000, 13000):
+        lo, hi = np.float32(0.5), np.float32(1.0)
+        for _ in range(40):
+            mid = np.float32((lo + hi) / 2)
+            inside = oset.initiation_logit(np.array([[mid, 0.5, 0, 0]], dtype=np.float32))[0, 5] >= 0
+            lo, hi = (mid, hi) if inside else (lo, mid)
+        S[i, 0], S[i, 1] = (lo if i % 2 else hi), 0.5
+    want = oset.initiation(S)
+    got = gset.initiation(S).cpu().numpy()
+    assert np.array_equal(got, want)
+    z = oset.initiation_logit(S)
+    assert (np.abs(z) < 1e-6).sum() > 3000                   # the set really contains boundary cases
+
+
 # ---- fused agent step ------------------------------------------------------------------------------
 def _paired_agents(scg, torch, B, order, K, name, seed, **kw):
     omap = oracle.PinballMap.from_name(name)
