@@ -632,6 +632,7 @@ static int ensure_partials(scg_ctx *ctx, int n);
 template <int N1, int VEC, int CPT, int NT, int U>
 static int launch_trace_t(scg_ctx *ctx, int B, const float4 *rec, float *trace, float gl, cudaStream_t st) {
     size_t smem = (size_t)ctx->K * SCG_A * ctx->F * sizeof(float);
+    if (smem > 227 * 1024) return SCG_ELIMIT;   // the CTA accumulator must fit in shared memory
     auto kern = k_trace<N1, VEC, CPT, NT, U>;
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
@@ -777,11 +778,8 @@ extern "C" int scg_ctx_create(int order, int K, scg_ctx_t **out) {
     scg_ctx *c = (scg_ctx *)calloc(1, sizeof(scg_ctx));
     if (!c) return SCG_ENOMEM;
     c->order = order; c->K = K; c->F = scg_pow4(order + 1);
-    size_t slab = (size_t)K * SCG_A * c->F * sizeof(float);
-    if (slab > 227 * 1024) {  // the CTA accumulator must fit in shared memory
-        free(c);
-        return SCG_ELIMIT;
-    }
+    // (the dense per-step operator scg_sarsa_update keeps a [K][A*F] accumulator per CTA and refuses sizes beyond
+    // shared memory when it is called; the agent pipeline's sweep only accumulates the option slots in use)
     *out = c;   // the per-CTA dW slabs are allocated by the first sweep (ensure_partials)
     return 0;
 }
