@@ -26,7 +26,7 @@
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
-#define RING_CTAS 32
+#define RING_CTAS 64
 #define RING_NT 256
 
 // scratch layout (unsigned int): [RING_CTAS][16] per-CTA option counts | barrier counter | done ticket
@@ -51,16 +51,27 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
     const int vbeg = (int)(lo < mis ? mis : (lo < nv ? lo : nv)), vend = (int)(lo + L < nv ? lo + L : nv);
     auto walk = [&](auto &&fn) {            // fn(flat index, event byte) for every termination event of this thread's chunk
         int v = vbeg;
-        while (v < vend) {
-            if ((v & 15) == 0 && v + 16 <= vend) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(evv + v);
-                if (!(q.x | q.y | q.z | q.w)) { v += 16; continue; }
+        for (; v < vend && (v & 15); ++v) {          // unaligned head (first thread only)
+            const uint32_t e = evv[v];
+            if (e & SCG_EV_TERM) fn(v - mis, e);
+        }
+        for (; v + 16 <= vend; v += 16) {            // 16 bytes per load; the bytes are taken from the registers
+            const uint4 q = *reinterpret_cast<const uint4 *>(evv + v);
+            if (!((q.x | q.y | q.z | q.w) & 0x80808080u)) continue;
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(w4[k] & 0x80808080u)) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t e = (w4[k] >> (8 * j)) & 0xFFu;
+                    if (e & SCG_EV_TERM) fn(v + 4 * k + j - mis, e);
+                }
             }
-            const int e1 = min((v | 15) + 1, vend);
-            for (; v < e1; ++v) {
-                const uint32_t e = evv[v];
-                if (e & SCG_EV_TERM) fn(v - mis, e);
-            }
+        }
+        for (; v < vend; ++v) {                      // tail
+            const uint32_t e = evv[v];
+            if (e & SCG_EV_TERM) fn(v - mis, e);
         }
     };
     for (int o = 0; o < SCG_MAX_OPTIONS; ++o) cnt_s[o][tid] = 0;
@@ -92,10 +103,14 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
         __threadfence();
     }
     __syncthreads();
+    // every CTA's per-option totals -> shared memory with independent loads, then 16 threads form this CTA's bases
+    __shared__ uint32_t all_s[RING_CTAS * SCG_MAX_OPTIONS];
+    for (int i = tid; i < (int)gridDim.x * SCG_MAX_OPTIONS; i += RING_NT) all_s[i] = __ldcg(scratch + i);
+    __syncthreads();
     if (tid < SCG_MAX_OPTIONS) {
         uint32_t b = 0, t = 0;
         for (int c = 0; c < (int)gridDim.x; ++c) {
-            const uint32_t v = __ldcg(scratch + c * SCG_MAX_OPTIONS + tid);
+            const uint32_t v = all_s[c * SCG_MAX_OPTIONS + tid];
             if (c < (int)blockIdx.x) b += v;
             t += v;
         }
@@ -141,7 +156,7 @@ extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     }
     const long long n = (long long)T * ag->B;
     if (n > 0x7fffffffll) return SCG_ELIMIT;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(RING_CTAS, (n + RING_NT * 64 - 1) / (RING_NT * 64)));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(RING_CTAS, (n + RING_NT * 32 - 1) / (RING_NT * 32)));
     // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
     ctx->ring_gen += (unsigned int)grid;
     const size_t off = (size_t)ag->ring_len * ag->B;
