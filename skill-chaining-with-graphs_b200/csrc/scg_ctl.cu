@@ -26,74 +26,77 @@
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
-#define RING_CTAS 64
-#define RING_NT 256
+#define RING_CTAS 128
+#define RING_NT 1024
+#define RING_TILE (RING_NT * 4)      // bytes per tile: one 32-bit word per thread, coalesced
 
 // scratch layout (unsigned int): [RING_CTAS][16] per-CTA option counts | barrier counter | done ticket
 #define RING_BAR (RING_CTAS * SCG_MAX_OPTIONS)
 #define RING_DONE (RING_BAR + 1)
 #define RING_WORDS (RING_DONE + 1)
 
-__global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *__restrict__ ev, const float4 *__restrict__ rec,
-                                                  float *ex_xy, uint8_t *ex_label, long long *ex_count, uint32_t cap,
-                                                  unsigned int *scratch, unsigned int target) {
-    __shared__ uint32_t cnt_s[SCG_MAX_OPTIONS][RING_NT];   // [option][thread]: private column per thread, no conflicts
-    __shared__ uint32_t base_s[SCG_MAX_OPTIONS], tot_s[SCG_MAX_OPTIONS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = gridDim.x * RING_NT;
-    // contiguous chunk of the flat [step][env] byte array per thread; indices are taken relative to the 16-byte
-    // aligned address below `ev` so that whole chunks can be skipped 16 bytes at a time
-    const int mis = (int)(reinterpret_cast<uintptr_t>(ev) & 15);
-    const uint8_t *evv = ev - mis;
-    const long long nv = (long long)n + mis;
-    const int L = (int)((((nv + nthreads - 1) / nthreads) + 15) & ~15ll);
-    const long long lo = (long long)(blockIdx.x * RING_NT + tid) * L;
-    const int vbeg = (int)(lo < mis ? mis : (lo < nv ? lo : nv)), vend = (int)(lo + L < nv ? lo + L : nv);
-    auto walk = [&](auto &&fn) {            // fn(flat index, event byte) for every termination event of this thread's chunk
-        int v = vbeg;
-        for (; v < vend && (v & 15); ++v) {          // unaligned head (first thread only)
-            const uint32_t e = evv[v];
-            if (e & SCG_EV_TERM) fn(v - mis, e);
-        }
-        for (; v + 16 <= vend; v += 16) {            // 16 bytes per load; the bytes are taken from the registers
-            const uint4 q = *reinterpret_cast<const uint4 *>(evv + v);
-            if (!((q.x | q.y | q.z | q.w) & 0x80808080u)) continue;
-            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+// exclusive prefix of one value per thread over the CTA (1024 threads); *total receives the sum
+__device__ __forceinline__ uint32_t ring_block_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!(w4[k] & 0x80808080u)) continue;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t e = (w4[k] >> (8 * j)) & 0xFFu;
-                    if (e & SCG_EV_TERM) fn(v + 4 * k + j - mis, e);
-                }
-            }
-        }
-        for (; v < vend; ++v) {                      // tail
-            const uint32_t e = evv[v];
-            if (e & SCG_EV_TERM) fn(v - mis, e);
-        }
-    };
-    for (int o = 0; o < SCG_MAX_OPTIONS; ++o) cnt_s[o][tid] = 0;
-    // pass 1: count this thread's events per option
-    walk([&](int, uint32_t e) { cnt_s[e & SCG_EV_OPT][tid] += 1; });
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
-    // per option: exclusive prefix over the CTA's threads (warp w takes options w, w + 8), CTA total to scratch
-    for (int o = warp; o < SCG_MAX_OPTIONS; o += RING_NT / 32) {
-        uint32_t v[RING_NT / 32], s = 0;
-#pragma unroll
-        for (int i = 0; i < RING_NT / 32; ++i) { v[i] = cnt_s[o][lane * (RING_NT / 32) + i]; s += v[i]; }
-        uint32_t inc = s;
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t winc = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += u;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += u;
         }
-        uint32_t run = inc - s;
-#pragma unroll
-        for (int i = 0; i < RING_NT / 32; ++i) { cnt_s[o][lane * (RING_NT / 32) + i] = run; run += v[i]; }
-        if (lane == 31) scratch[blockIdx.x * SCG_MAX_OPTIONS + o] = inc;
+        warp_sums[lane] = winc - w;
+        if (lane == 31) *total = winc;
     }
+    __syncthreads();
+    return warp_sums[warp] + inc - v;
+}
+
+// CTA c owns the contiguous tiles [c * tiles_per_cta, ...) of the flat [step][env] event-byte array (n bytes, n % 4 == 0
+// after padding by the caller's layout: the array is read as aligned 32-bit words, `mis` leading bytes are skipped).
+__global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *__restrict__ ev, const float4 *__restrict__ rec,
+                                                  float *ex_xy, uint8_t *ex_label, long long *ex_count, uint32_t cap,
+                                                  unsigned int *scratch, unsigned int target, int tiles_per_cta) {
+    __shared__ uint32_t lst[RING_TILE];                 // this tile's events in flat order: option | hit << 4 | byte index << 8
+    __shared__ uint32_t rk[RING_TILE];                  // their rank among the CTA's events of the same option
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t cnt_s[SCG_MAX_OPTIONS], base_s[SCG_MAX_OPTIONS], tot_s[SCG_MAX_OPTIONS], run_s[SCG_MAX_OPTIONS];
+    __shared__ uint32_t slot0_s[SCG_MAX_OPTIONS];
+    __shared__ uint32_t n_tile_ev;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(ev) & 3);
+    const uint32_t *evw = reinterpret_cast<const uint32_t *>(ev - mis);
+    const long long nv = (long long)n + mis;            // bytes [mis, nv) of the aligned view are the events
+    const long long cta_lo = (long long)blockIdx.x * tiles_per_cta * RING_TILE;
+    auto load_word = [&](long long v0) -> uint32_t {    // the aligned word at byte offset v0, bytes outside [mis, nv) cleared
+        if (v0 >= nv) return 0u;
+        uint32_t w = __ldg(evw + (v0 >> 2));
+        if (v0 < mis) w &= 0xFFFFFFFFu << (8 * (mis - (int)v0));
+        if (v0 + 4 > nv) w &= 0xFFFFFFFFu >> (8 * (int)(v0 + 4 - nv));
+        return w;
+    };
+    if (tid < SCG_MAX_OPTIONS) { cnt_s[tid] = 0; run_s[tid] = 0; slot0_s[tid] = tid < K ? (uint32_t)((unsigned long long)ex_count[tid] % cap) : 0u; }
+    __syncthreads();
+    // pass A: this CTA's event count per option
+    for (int t = 0; t < tiles_per_cta; ++t) {
+        uint32_t w = load_word(cta_lo + (long long)t * RING_TILE + tid * 4) & 0x8F8F8F8Fu;
+        while (w & 0x80808080u) {
+            const int j = (__ffs(w & 0x80808080u) - 1) >> 3;
+            atomicAdd(&cnt_s[(w >> (8 * j)) & SCG_EV_OPT], 1u);
+            w &= ~(0xFFu << (8 * j));
+        }
+    }
+    __syncthreads();
+    if (tid < SCG_MAX_OPTIONS) scratch[blockIdx.x * SCG_MAX_OPTIONS + tid] = cnt_s[tid];
     // grid barrier (all CTAs are co-resident: gridDim.x <= RING_CTAS): generation-counted arrivals
     __syncthreads();
     if (tid == 0) {
@@ -103,35 +106,65 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
         __threadfence();
     }
     __syncthreads();
-    // every CTA's per-option totals -> shared memory with independent loads, then 16 threads form this CTA's bases
-    __shared__ uint32_t all_s[RING_CTAS * SCG_MAX_OPTIONS];
-    for (int i = tid; i < (int)gridDim.x * SCG_MAX_OPTIONS; i += RING_NT) all_s[i] = __ldcg(scratch + i);
+    // every CTA's per-option totals: threads (c, o) load them with independent loads, 16 threads form this CTA's bases
+    for (int i = tid; i < (int)gridDim.x * SCG_MAX_OPTIONS; i += RING_NT) rk[i] = __ldcg(scratch + i);
     __syncthreads();
     if (tid < SCG_MAX_OPTIONS) {
-        uint32_t b = 0, t = 0;
+        uint32_t b = 0, tt = 0;
         for (int c = 0; c < (int)gridDim.x; ++c) {
-            const uint32_t v = all_s[c * SCG_MAX_OPTIONS + tid];
+            const uint32_t v = rk[c * SCG_MAX_OPTIONS + tid];
             if (c < (int)blockIdx.x) b += v;
-            t += v;
+            tt += v;
         }
         base_s[tid] = b;
-        tot_s[tid] = t;
+        tot_s[tid] = tt;
     }
     __syncthreads();
-    // pass 2: place the events.  rank = position of the event among this pass's events of its option, in (step, env)
-    // order; only the last `cap` of them are written, so every slot has at most one writer
-    walk([&](int i, uint32_t e) {
-        const uint32_t o = e & SCG_EV_OPT;
-        const uint32_t rank = base_s[o] + cnt_s[o][tid]++;
-        if ((int)o >= K || (unsigned long long)rank + cap < tot_s[o]) return;
-        const uint32_t slot = (uint32_t)(((unsigned long long)ex_count[o] + rank) % cap);
-        const float4 r1 = __ldg(rec + (size_t)i * 2 + 1);
-        const size_t ei = (size_t)o * cap + slot;
-        *reinterpret_cast<float2 *>(ex_xy + 2 * ei) = make_float2(r1.z, r1.w);
-        ex_label[ei] = (e & SCG_EV_HIT) ? 1 : 0;
-    });
+    // pass B: per tile, the ordered event list (block scan), per-option ranks (warp o walks the list with ballots),
+    // then one thread per event places it.  rank = position among this launch's events of the option in (step, env)
+    // order; only the last `cap` of them are written, so every slot has exactly one writer.
+    for (int t = 0; t < tiles_per_cta; ++t) {
+        const long long v0 = cta_lo + (long long)t * RING_TILE + tid * 4;
+        const uint32_t w = load_word(v0);
+        const uint32_t flags = w & 0x80808080u;
+        uint32_t total = 0;
+        uint32_t off = ring_block_scan(__popc(flags), warp_sums, &n_tile_ev);
+        total = n_tile_ev;
+        if (flags) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t e = (w >> (8 * j)) & 0xFFu;
+                if (e & SCG_EV_TERM) lst[off++] = (e & SCG_EV_OPT) | ((e & SCG_EV_HIT) ? 16u : 0u) | ((uint32_t)(tid * 4 + j) << 8);
+            }
+        }
+        __syncthreads();
+        if (warp < SCG_MAX_OPTIONS && total) {
+            uint32_t run = run_s[warp];
+            for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool m = i < total && (lst[i] & SCG_EV_OPT) == (uint32_t)warp;
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (m) rk[i] = run + __popc(bal & ((1u << lane) - 1u));
+                run += __popc(bal);
+            }
+            if (lane == 0) run_s[warp] = run;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < total; i += RING_NT) {
+            const uint32_t e = lst[i], o = e & SCG_EV_OPT;
+            const uint32_t rank = base_s[o] + rk[i];
+            if ((int)o < K && (unsigned long long)rank + cap >= tot_s[o]) {
+                const uint32_t slot = (uint32_t)(((unsigned long long)slot0_s[o] + rank) % cap);
+                const long long f = cta_lo + (long long)t * RING_TILE + (e >> 8) - mis;     // flat [step][env] index
+                const float4 r1 = __ldg(rec + (size_t)f * 2 + 1);
+                const size_t ei = (size_t)o * cap + slot;
+                *reinterpret_cast<float2 *>(ex_xy + 2 * ei) = make_float2(r1.z, r1.w);
+                ex_label[ei] = (e & 16u) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
     // the last CTA to finish advances the counts (every CTA has read them by then)
-    __syncthreads();
     __shared__ bool last;
     if (tid == 0) {
         __threadfence();
@@ -156,7 +189,9 @@ extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     }
     const long long n = (long long)T * ag->B;
     if (n > 0x7fffffffll) return SCG_ELIMIT;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(RING_CTAS, (n + RING_NT * 32 - 1) / (RING_NT * 32)));
+    const long long n_tiles = (n + 3 + RING_TILE - 1) / RING_TILE;              // (+3: the aligned view may start up to 3 bytes early)
+    const int tiles_per_cta = (int)((n_tiles + RING_CTAS - 1) / RING_CTAS);
+    const int grid = (int)std::max<long long>(1, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
     // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
     ctx->ring_gen += (unsigned int)grid;
     const size_t off = (size_t)ag->ring_len * ag->B;
@@ -164,7 +199,7 @@ extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if ((rcp = scg_prof_push(ctx, 4, st, false))) return rcp;
     k_ring<<<grid, RING_NT, 0, st>>>((int)n, ag->K, ag->win_ev + off, reinterpret_cast<const float4 *>(ag->win_rec) + off * 2,
                                      ag->ex_xy, ag->ex_label, reinterpret_cast<long long *>(ag->ex_count),
-                                     ag->example_capacity, ctx->d_ring, ctx->ring_gen);
+                                     ag->example_capacity, ctx->d_ring, ctx->ring_gen, tiles_per_cta);
     SCG_LAUNCH_CHECK();
     if ((rcp = scg_prof_push(ctx, 4, st, true))) return rcp;
     ag->ring_len = ag->win_len;
