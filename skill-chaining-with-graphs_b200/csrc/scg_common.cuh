@@ -156,6 +156,21 @@ __device__ __forceinline__ int scg_eps_greedy(const float q[SCG_A], float eps, u
     return (u0 < eps) ? ra : best;
 }
 
+// ---- packed fp32 pairs ---------------------------------------------------------------------------
+// sm_100a has two-wide fp32 instructions (fma / mul / add .f32x2 -> SASS FFMA2 / FMUL2 / FADD2) on 64-bit register
+// pairs.  Measured on B200 (tools/probes/ffma2_probe.cu): 117 FMA/clk/SM packed against 73 scalar, and - what matters
+// for the issue-bound kernels here - half the instructions for the same arithmetic.  Each half is an ordinary IEEE
+// round-to-nearest fp32 operation, so results are bit-identical to the scalar form.
+typedef unsigned long long f2_t;   // two fp32: low word = first element
+__device__ __forceinline__ f2_t f2_pack(float x, float y) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ f2_t f2_dup(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ float f2_x(f2_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_y(f2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_neg(f2_t a) { return a ^ 0x8000000080000000ull; }
+
 // ---- complex helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ float2 scg_cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
