@@ -32,23 +32,6 @@ __device__ __forceinline__ float4 vfma(float s, float4 a, float4 c) {
 __device__ __forceinline__ float vfma(float s, float a, float c) { return fmaf(s, a, c); }
 __device__ __forceinline__ float4 vzero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// The window sweep keeps four consecutive features as two packed fp32 pairs and works with the two-wide instructions
-// (FFMA2 / FMUL2 / FADD2, scg_common.cuh): half the floating-point instructions of the scalar form.
-struct __align__(16) pk4 { f2_t a, b; };
-template <int VEC> struct VecW;
-template <> struct VecW<4> { using type = pk4; using scalar = f2_t; };
-template <> struct VecW<1> { using type = float; using scalar = float; };
-__device__ __forceinline__ pk4 wzero(pk4) { pk4 r; r.a = 0ull; r.b = 0ull; return r; }
-__device__ __forceinline__ float wzero(float) { return 0.f; }
-__device__ __forceinline__ pk4 wscale(pk4 v, f2_t s) { pk4 r; r.a = f2_mul(v.a, s); r.b = f2_mul(v.b, s); return r; }
-__device__ __forceinline__ float wscale(float v, float s) { return v * s; }
-__device__ __forceinline__ pk4 wfma(f2_t s, pk4 a, pk4 c) { pk4 r; r.a = f2_fma(s, a.a, c.a); r.b = f2_fma(s, a.b, c.b); return r; }
-__device__ __forceinline__ float wfma(float s, float a, float c) { return fmaf(s, a, c); }
-__device__ __forceinline__ pk4 wadd(pk4 a, pk4 b) { pk4 r; r.a = f2_add(a.a, b.a); r.b = f2_add(a.b, b.b); return r; }
-__device__ __forceinline__ float wadd(float a, float b) { return a + b; }
-__device__ __forceinline__ void wscalar(float x, f2_t &s) { s = f2_dup(x); }
-__device__ __forceinline__ void wscalar(float x, float &s) { s = x; }
-
 // z^c for 0 <= c < 8 from (z, z^2, z^4) with selects (no dynamic register indexing)
 __device__ __forceinline__ float2 cpow_sel(float2 z1, float2 z2, float2 z4, int c) {
     float2 r = (c & 1) ? z1 : make_float2(1.f, 0.f);
@@ -203,7 +186,7 @@ struct WinItem {   // a work item of the sweep: block `blk` of 8 steps of env `b
 // per-env control block written by the scan warp, read by every thread in the main phase (double-buffered)
 template <int NS>                      // NS: steps a window can have (8 for the single-block sweep, SCG_WIN_MAX otherwise)
 struct WinCtlT {
-    float4 gc[NS];                     // (G_t, G_t, c_t, c_t) per step: ready-made operand pairs of the packed FMAs
+    float2 gc[NS];                     // (G_t, c_t) per step
     uint32_t mask[NS][8];              // [segment][action]: steps of that segment taken with that action (5 used)
     uint32_t seg_o[NS];                // option of each segment (an env changes option only after a termination)
     float scale, carry;                // e <- scale * e_start;  d <- carry * e_start
@@ -213,26 +196,21 @@ struct WinCtlT {
 template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl, float *dW, int K_all) {
-    using V = typename VecW<VEC>::type;
-    using SC = typename VecW<VEC>::scalar;
-    using WinCtl = WinCtlT<MULTI ? SCG_WIN_MAX : SCG_WIN_TB>;
+    using V = typename VecT<VEC>::type;
+    using WinCtl = WinCtlT<MULTI ? SCG_WIN_MAX : SCG_WIN_TB>;   // (the small form keeps 8 CTAs per SM at order 3 with 4 options in use)
     constexpr int F = N1 * N1 * N1 * N1;
     constexpr int AF = SCG_A * F;
     constexpr int NCHR = F / VEC;          // chunks per action row
     constexpr int NN = N1 * N1;
     constexpr int TABN = SCG_WIN_TB * 2 * NN;             // entries of one table buffer
     constexpr int EPT = (TABN + NT - 1) / NT;             // table entries built per thread
-    // Table layout per step.  Scalar form (VEC 1): P01[NN] then P23[NN], one float2 (cos, sin) each.  Packed form
-    // (VEC 4): P01[NN] as float4 (cos, cos, -sin, -sin) - both operand pairs of the packed multiply ready-made - then
-    // P23 in groups of four entries as (cos x 4, sin x 4), so that a thread's four features load as two 16-byte pairs.
-    constexpr int TSTRIDE = VEC == 4 ? NN * 24 : 2 * NN * (int)sizeof(float2);   // bytes between consecutive steps' tables
-    constexpr int TABB = SCG_WIN_TB * TSTRIDE;             // bytes of one table buffer
+    constexpr int TSTRIDE = 2 * NN * (int)sizeof(float2); // bytes between the tables of consecutive steps
     static_assert(F % VEC == 0 && NT * CH >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
     static_assert(VEC == 1 || NN % VEC == 0, "a chunk shares its (c0, c1) digits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);                                      // [K][AF]
-    char *tab = reinterpret_cast<char *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));       // [2][TABB]
-    WinCtl *ctl = reinterpret_cast<WinCtl *>(tab + 2 * TABB);                              // [2]
+    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [2][TABN]
+    WinCtl *ctl = reinterpret_cast<WinCtl *>(tab + 2 * TABN);                              // [2]
     float *glpow = reinterpret_cast<float *>(ctl + 2);                                     // [36]: gl^n
 
     const int tid = threadIdx.x;
@@ -251,13 +229,8 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         const int f0 = (own[j] ? tid + j * NT : 0) * VEC;
-        if constexpr (VEC == 4) {
-            off01[j] = (f0 / NN) * 16;
-            off23[j] = NN * 16 + ((f0 % NN) / 4) * 32;
-        } else {
-            off01[j] = (f0 / NN) * (int)sizeof(float2);
-            off23[j] = (NN + f0 % NN) * (int)sizeof(float2);
-        }
+        off01[j] = (f0 / NN) * (int)sizeof(float2);
+        off23[j] = (NN + f0 % NN) * (int)sizeof(float2);
     }
     // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits,
     // and the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4)
@@ -297,7 +270,8 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     for (int j = 0; j < CH; ++j) {
 #pragma unroll
         for (int r = 0; r < SCG_A; ++r) {
-            e[j][r] = wzero(V()); e_nx[j][r] = wzero(V()); d[j][r] = wzero(V());
+            if constexpr (VEC == 4) { e[j][r] = vzero4(); e_nx[j][r] = vzero4(); d[j][r] = vzero4(); }
+            else { e[j][r] = 0.f; e_nx[j][r] = 0.f; d[j][r] = 0.f; }
         }
     }
 
@@ -324,7 +298,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     };
     // registers -> pair tables (buffer `par`) and, for an env's first block, its control block (buffer `epar`)
     auto build = [&](WinItem it, int par, int epar) {
-        char *tb = tab + par * TABB;
+        float2 *tb = tab + par * TABN;
         if (worker) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
@@ -333,22 +307,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
                 const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
                 const int idx = tid + k * NT;
-                if (idx < TABN) {
-                    const float cs = __cosf(xr), sn = __sinf(xr);
-                    if constexpr (VEC == 4) {
-                        const int ij = idx - (e_tt[k] * 2 + e_half[k]) * NN;
-                        char *st = tb + e_tt[k] * TSTRIDE;
-                        if (e_half[k] == 0) {
-                            *reinterpret_cast<float4 *>(st + ij * 16) = make_float4(cs, cs, -sn, -sn);
-                        } else {
-                            float *g4 = reinterpret_cast<float *>(st + NN * 16 + (ij >> 2) * 32) + (ij & 3);
-                            g4[0] = cs;
-                            g4[4] = sn;
-                        }
-                    } else {
-                        reinterpret_cast<float2 *>(tb)[idx] = make_float2(cs, sn);
-                    }
-                }
+                if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
             }
         }
         if (it.blk == 0 && scan_warp) {
@@ -371,7 +330,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             const bool dead = (dm >> t) != 0;                     // a termination at this step or later in the window
             const float cf = (act && !dead) ? glpow[__popc((am >> t) >> 1)] : 0.f;
             const float G = act ? D : 0.f;
-            if (t < T) cb.gc[t] = make_float4(G, G, cf, cf);
+            if (t < T) cb.gc[t] = make_float2(G, cf);
             // segments: maximal runs of steps under the same option
             const unsigned before = am & ((1u << t) - 1u);
             const int prev = before ? 31 - __clz(before) : t;
@@ -412,8 +371,8 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                         for (int r = 0; r < SCG_A; ++r) {
                             float *q = gp + (size_t)(r * NCHR + tid + j * NT) * VEC;
                             if constexpr (VEC == 4) {
-                                atomicAdd(q, f2_x(d[j][r].a)); atomicAdd(q + 1, f2_y(d[j][r].a));
-                                atomicAdd(q + 2, f2_x(d[j][r].b)); atomicAdd(q + 3, f2_y(d[j][r].b));
+                                atomicAdd(q, d[j][r].x); atomicAdd(q + 1, d[j][r].y);
+                                atomicAdd(q + 2, d[j][r].z); atomicAdd(q + 3, d[j][r].w);
                             } else {
                                 atomicAdd(q, d[j][r]);
                             }
@@ -429,7 +388,11 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             if (own[j]) {
 #pragma unroll
                 for (int r = 0; r < SCG_A; ++r) {
-                    ap[r * NCHR + tid + j * NT] = wadd(ap[r * NCHR + tid + j * NT], d[j][r]);
+                    V cur = ap[r * NCHR + tid + j * NT];
+                    if constexpr (VEC == 4)
+                        cur = make_float4(cur.x + d[j][r].x, cur.y + d[j][r].y, cur.z + d[j][r].z, cur.w + d[j][r].w);
+                    else cur = cur + d[j][r];
+                    ap[r * NCHR + tid + j * NT] = cur;
                 }
             }
         }
@@ -462,19 +425,17 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         if (nxt.blk == 0 && nxt.b < B) load_trace(nxt.b);
         // ---- main ----
         const WinCtl &cb = ctl[epar];
-        const char *tb0 = tab + par * TABB;
-        const float4 *gc = cb.gc + cur.blk * SCG_WIN_TB;
+        const char *tb0 = reinterpret_cast<const char *>(tab + par * TABN);
+        const float2 *gc = cb.gc + cur.blk * SCG_WIN_TB;
         if (cur.blk == 0) {
-            SC carry, scale;
-            wscalar(cb.carry, carry);
-            wscalar(cb.scale, scale);
+            const float carry = cb.carry, scale = cb.scale;
             o_cur = cb.seg_o[0];
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
 #pragma unroll
                 for (int r = 0; r < SCG_A; ++r) {
-                    d[j][r] = wscale(e[j][r], carry);    // carry-in: gl G_0 e_start
-                    e[j][r] = wscale(e[j][r], scale);
+                    d[j][r] = vscale(e[j][r], carry);    // carry-in: gl G_0 e_start
+                    e[j][r] = vscale(e[j][r], scale);
                 }
             }
         }
@@ -500,7 +461,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 for (int j = 0; j < CH; ++j) {
 #pragma unroll
                     for (int r = 0; r < SCG_A; ++r) {
-                        d[j][r] = wzero(V());
+                        if constexpr (VEC == 4) d[j][r] = vzero4(); else d[j][r] = 0.f;
                     }
                 }
                 o_cur = so;
@@ -511,31 +472,23 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 while (mm) {
                     const int tt = __ffs(mm) - 1;
                     mm &= mm - 1;
+                    const float2 g2 = gc[tt];
                     const char *tb = tb0 + tt * TSTRIDE;
-                    if constexpr (VEC == 4) {
-                        // phi of four features = cos01 * cos23 - sin01 * sin23, two features per instruction
-                        const pk4 gg = *reinterpret_cast<const pk4 *>(gc + tt);            // (G, G), (c, c)
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) {   // independent chunks: their loads and FMAs interleave
-                            const pk4 p = *reinterpret_cast<const pk4 *>(tb + off01[j]);   // (cos, cos), (-sin, -sin)
-                            const pk4 qc = *reinterpret_cast<const pk4 *>(tb + off23[j]);  // cos of the four (c2, c3)
-                            const pk4 qs = *reinterpret_cast<const pk4 *>(tb + off23[j] + 16);
-                            pk4 ph;
-                            ph.a = f2_fma(p.a, qc.a, f2_mul(p.b, qs.a));
-                            ph.b = f2_fma(p.a, qc.b, f2_mul(p.b, qs.b));
-                            d[j][r] = wfma(gg.a, ph, d[j][r]);
-                            e[j][r] = wfma(gg.b, ph, e[j][r]);
-                        }
-                    } else {
-                        const float4 g4 = gc[tt];
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
+                    for (int j = 0; j < CH; ++j) {       // independent chunks: their loads and FMAs interleave
+                        const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
+                        V ph;
+                        if constexpr (VEC == 4) {
+                            const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
+                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + 16);
+                            ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
+                                             fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
+                        } else {
                             const float2 q = *reinterpret_cast<const float2 *>(tb + off23[j]);
-                            const float ph = fmaf(p.x, q.x, -p.y * q.y);
-                            d[j][r] = wfma(g4.x, ph, d[j][r]);
-                            e[j][r] = wfma(g4.z, ph, e[j][r]);
+                            ph = fmaf(p.x, q.x, -p.y * q.y);
                         }
+                        d[j][r] = vfma(g2.x, ph, d[j][r]);
+                        e[j][r] = vfma(g2.y, ph, e[j][r]);
                     }
                 }
             }
@@ -735,11 +688,11 @@ static int ensure_partials(scg_ctx *ctx, int n) {
 }
 
 template <int N1>
-static size_t window_smem(const scg_ctx *ctx, int k_used, bool vec4, bool multi) {
+static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi) {
     constexpr int NN = N1 * N1;
-    const size_t tab = vec4 ? (size_t)SCG_WIN_TB * NN * 24 : (size_t)SCG_WIN_TB * 2 * NN * sizeof(float2);
-    const size_t ctl = multi ? sizeof(WinCtlT<SCG_WIN_MAX>) : sizeof(WinCtlT<SCG_WIN_TB>);
-    return (((size_t)k_used * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) + 2 * tab + 2 * ctl + 36 * sizeof(float);
+    return (((size_t)k_used * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
+           (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) +
+           2 * (multi ? sizeof(WinCtlT<SCG_WIN_MAX>) : sizeof(WinCtlT<SCG_WIN_TB>)) + 36 * sizeof(float);
 }
 
 // k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
@@ -747,7 +700,7 @@ static size_t window_smem(const scg_ctx *ctx, int k_used, bool vec4, bool multi)
 template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                             float *dW, cudaStream_t st) {
-    const size_t smem = window_smem<N1>(ctx, k_used, VEC == 4, MULTI);
+    const size_t smem = window_smem<N1>(ctx, k_used, MULTI);
     auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL>;
     constexpr int NTT = NT + (CTRL ? 32 : 0);
     static ScgKernelCfg cfgc = {};
@@ -798,17 +751,17 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
         case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 3:
-            if (win_ch3 == 1 && win_9cta3 && 9 * (window_smem<4>(ctx, k_used, true, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // nine CTAs per SM (<= 112 registers)
+            if (win_ch3 == 1 && win_9cta3 && 9 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // nine CTAs per SM (<= 112 registers)
                 grid = launch_window_t<4, 4, 64, 1, 9>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1, 8>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             break;
         case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 5:
-            if (win_ch5 == 2 && 2 * (window_smem<6>(ctx, k_used, true, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two 6-warp CTAs, two chunks per thread
+            if (win_ch5 == 2 && 2 * (window_smem<6>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two 6-warp CTAs, two chunks per thread
                 grid = launch_window_t<6, 4, 192, 2, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used, true, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
+            else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
                 grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else if (win_ctrl5) grid = launch_window_t<6, 4, 352, 1, 1, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
