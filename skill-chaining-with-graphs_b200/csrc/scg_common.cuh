@@ -212,6 +212,14 @@ template <> struct WCur<false> {
         a = __ldg(q);
         b = __ldg(q + 1);
     }
+    // the five action weights of feature f as the register pairs (w0, w1), (w2, w3) and w4
+    __device__ __forceinline__ void load2(int f, f2_t &w01, f2_t &w23, float &w4) const {
+        const float4 *q = p + (size_t)f * stride;
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(q));
+        w01 = a.x;
+        w23 = a.y;
+        w4 = __ldg(reinterpret_cast<const float *>(q + 1));
+    }
 };
 template <> struct WCur<true> {
     uint32_t addr, stride;  // bytes
@@ -222,28 +230,76 @@ template <> struct WCur<true> {
         asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(q));
         asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(q));
     }
+    __device__ __forceinline__ void load2(int f, f2_t &w01, f2_t &w23, float &w4) const {
+        uint32_t q = addr + (uint32_t)f * stride;
+        asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w01), "=l"(w23) : "r"(q));
+        asm("ld.shared.f32 %0, [%1+16];" : "=f"(w4) : "r"(q));
+    }
 };
+
+// ---- Q evaluation on the two-wide fp32 instructions ---------------------------------------------------------
+// The step kernel is bound by instruction issue, and most of its Q evaluation is FMAs.  Two features are formed per
+// instruction pair (phi = cos01 * cos23 - sin01 * sin23 on packed (c2, c3) table entries, the (c0, c1) phasor as the
+// broadcast scalar operand), and a feature's five action weights - which a 16-byte load already delivers as the
+// register pairs (w0, w1), (w2, w3) - are consumed by two FFMA2 with phi as the broadcast operand plus one FFMA:
+// 6 issue slots per feature instead of 9.  Accumulators: q01 = (Q0, Q1), q23 = (Q2, Q3), q4.
+struct QAcc {
+    f2_t q01, q23;
+    float q4;
+};
+__device__ __forceinline__ void qacc_zero(QAcc &q) { q.q01 = 0ull; q.q23 = 0ull; q.q4 = 0.f; }
+__device__ __forceinline__ void qacc_out(const QAcc &q, float out[SCG_A]) {
+    out[0] = f2_x(q.q01); out[1] = f2_y(q.q01); out[2] = f2_x(q.q23); out[3] = f2_y(q.q23); out[4] = q.q4;
+}
+template <bool SMEM>
+__device__ __forceinline__ void qacc_feature(const WCur<SMEM> &w, int f, float phi, QAcc &q) {
+    f2_t w01, w23;
+    float w4;
+    w.load2(f, w01, w23, w4);
+    const f2_t p2 = f2_dup(phi);          // folds into the broadcast-scalar operand form of FFMA2
+    q.q01 = f2_fma(w01, p2, q.q01);
+    q.q23 = f2_fma(w23, p2, q.q23);
+    q.q4 = fmaf(w4, phi, q.q4);
+}
+// z^c for c = 0 .. N1-1 as packed pairs: xs[i] = (Re z^(2i), Re z^(2i+1)), ys likewise (an odd N1 pads with z^N1)
+template <int N1>
+__device__ __forceinline__ void pow_pairs(float2 z, f2_t xs[(N1 + 1) / 2], f2_t ys[(N1 + 1) / 2]) {
+    float2 p = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < (N1 + 1) / 2; ++i) {
+        const float2 p1 = scg_cmul(p, z);
+        xs[i] = f2_pack(p.x, p1.x);
+        ys[i] = f2_pack(p.y, p1.y);
+        p = scg_cmul(p1, z);
+    }
+}
+// (phi_a, phi_b) = Re(u * t_a), Re(u * t_b) for the packed table entries (tx, ty) and the phasor u
+__device__ __forceinline__ f2_t phi_pair(float2 u, f2_t tx, f2_t ty) {
+    return f2_fma(f2_dup(u.x), tx, f2_mul(f2_dup(-u.y), ty));
+}
 
 // Q_o(s, .) for one env: nested loops over the multi-index with running phasor products
 // (cos(pi c.s) = Re prod_j z_j^{c_j}); the two innermost dimensions are unrolled and use a register
-// table of z_3 powers.  Each feature is consumed by five FFMAs the moment it is formed.
+// table of z_3 powers.  Each feature is consumed the moment it is formed.
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
-#pragma unroll
-    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
-    if constexpr (N1 <= 4) {
-        // small orders: the N1^2 products z_2^c2 z_3^c3 fit in registers, so a feature is Re(z01 * p23[j]) with one
-        // complex multiply per (c0, c1) pair instead of one per (c0, c1, c2) triple
-        float2 p23[N1 * N1];
+    QAcc acc;
+    qacc_zero(acc);
+    if constexpr (N1 == 2 || N1 == 4) {
+        // small even orders: the N1^2 products z_2^c2 z_3^c3 fit in registers (as packed pairs over c3), so a feature
+        // pair is one packed multiply-add with the (c0, c1) phasor
+        f2_t px[N1 * N1 / 2], py[N1 * N1 / 2];
         {
             float2 p2 = make_float2(1.f, 0.f);
 #pragma unroll
             for (int c2 = 0; c2 < N1; ++c2) {
                 float2 v = p2;
 #pragma unroll
-                for (int c3 = 0; c3 < N1; ++c3) {
-                    p23[c2 * N1 + c3] = v;
-                    v = scg_cmul(v, z[3]);
+                for (int c3 = 0; c3 < N1; c3 += 2) {
+                    const float2 v1 = scg_cmul(v, z[3]);
+                    px[(c2 * N1 + c3) / 2] = f2_pack(v.x, v1.x);
+                    py[(c2 * N1 + c3) / 2] = f2_pack(v.y, v1.y);
+                    v = scg_cmul(v1, z[3]);
                 }
                 p2 = scg_cmul(p2, z[2]);
             }
@@ -256,27 +312,21 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
 #pragma unroll 1
             for (int c1 = 0; c1 < N1; ++c1) {
 #pragma unroll
-                for (int j = 0; j < N1 * N1; ++j) {
-                    float phi = fmaf(z01.x, p23[j].x, -z01.y * p23[j].y);
-                    float4 wa, wb;
-                    w.load(f + j, wa, wb);
-                    q[0] = fmaf(wa.x, phi, q[0]);
-                    q[1] = fmaf(wa.y, phi, q[1]);
-                    q[2] = fmaf(wa.z, phi, q[2]);
-                    q[3] = fmaf(wa.w, phi, q[3]);
-                    q[4] = fmaf(wb.x, phi, q[4]);
+                for (int j = 0; j < N1 * N1 / 2; ++j) {
+                    const f2_t ph = phi_pair(z01, px[j], py[j]);
+                    qacc_feature(w, f + 2 * j, f2_x(ph), acc);
+                    qacc_feature(w, f + 2 * j + 1, f2_y(ph), acc);
                 }
                 f += N1 * N1;
                 z01 = scg_cmul(z01, z[1]);
             }
             z0 = scg_cmul(z0, z[0]);
         }
+        qacc_out(acc, q);
         return;
     }
-    float2 p3[N1];
-    p3[0] = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
+    f2_t p3x[(N1 + 1) / 2], p3y[(N1 + 1) / 2];
+    pow_pairs<N1>(z[3], p3x, p3y);
     float2 z0 = make_float2(1.f, 0.f);
     int f = 0;
 #pragma unroll 1
@@ -288,15 +338,10 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
 #pragma unroll
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-                for (int c3 = 0; c3 < N1; ++c3) {
-                    float phi = fmaf(z012.x, p3[c3].x, -z012.y * p3[c3].y);
-                    float4 wa, wb;
-                    w.load(f + c2 * N1 + c3, wa, wb);
-                    q[0] = fmaf(wa.x, phi, q[0]);
-                    q[1] = fmaf(wa.y, phi, q[1]);
-                    q[2] = fmaf(wa.z, phi, q[2]);
-                    q[3] = fmaf(wa.w, phi, q[3]);
-                    q[4] = fmaf(wb.x, phi, q[4]);
+                for (int c3 = 0; c3 < N1; c3 += 2) {
+                    const f2_t ph = phi_pair(z012, p3x[c3 / 2], p3y[c3 / 2]);
+                    qacc_feature(w, f + c2 * N1 + c3, f2_x(ph), acc);
+                    if (c3 + 1 < N1) qacc_feature(w, f + c2 * N1 + c3 + 1, f2_y(ph), acc);
                 }
                 z012 = scg_cmul(z012, z[2]);
             }
@@ -305,18 +350,17 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
         }
         z0 = scg_cmul(z0, z[0]);
     }
+    qacc_out(acc, q);
 }
 
 // The slice of Q_o(s, .) whose features have leading multi-index digit c0 (N1^3 features): N1 lanes
 // that share one env each take one digit and add their partial sums (option re-selection).
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_c0(int c0, const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
-    float2 p3[N1];
-    p3[0] = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int c = 1; c < N1; ++c) p3[c] = scg_cmul(p3[c - 1], z[3]);
-#pragma unroll
-    for (int a = 0; a < SCG_A; ++a) q[a] = 0.f;
+    f2_t p3x[(N1 + 1) / 2], p3y[(N1 + 1) / 2];
+    pow_pairs<N1>(z[3], p3x, p3y);
+    QAcc acc;
+    qacc_zero(acc);
     float2 z01 = make_float2(1.f, 0.f);
     for (int i = 0; i < c0; ++i) z01 = scg_cmul(z01, z[0]);
     int f = c0 * N1 * N1 * N1;
@@ -326,36 +370,29 @@ __device__ __forceinline__ void scg_q_c0(int c0, const float2 z[4], const WCur<S
 #pragma unroll
         for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-            for (int c3 = 0; c3 < N1; ++c3) {
-                float phi = fmaf(z012.x, p3[c3].x, -z012.y * p3[c3].y);
-                float4 wa, wb;
-                w.load(f + c2 * N1 + c3, wa, wb);
-                q[0] = fmaf(wa.x, phi, q[0]);
-                q[1] = fmaf(wa.y, phi, q[1]);
-                q[2] = fmaf(wa.z, phi, q[2]);
-                q[3] = fmaf(wa.w, phi, q[3]);
-                q[4] = fmaf(wb.x, phi, q[4]);
+            for (int c3 = 0; c3 < N1; c3 += 2) {
+                const f2_t ph = phi_pair(z012, p3x[c3 / 2], p3y[c3 / 2]);
+                qacc_feature(w, f + c2 * N1 + c3, f2_x(ph), acc);
+                if (c3 + 1 < N1) qacc_feature(w, f + c2 * N1 + c3 + 1, f2_y(ph), acc);
             }
             z012 = scg_cmul(z012, z[2]);
         }
         f += N1 * N1;
         z01 = scg_cmul(z01, z[1]);
     }
+    qacc_out(acc, q);
 }
 
 // Same for two states sharing the weight loads: qa = Q_o(sa, .), qb = Q_o(sb, .)
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4], const WCur<SMEM> &w,
                                            float qa[SCG_A], float qb[SCG_A]) {
-    float2 pa[N1], pb[N1];
-    pa[0] = pb[0] = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int c = 1; c < N1; ++c) {
-        pa[c] = scg_cmul(pa[c - 1], za[3]);
-        pb[c] = scg_cmul(pb[c - 1], zb[3]);
-    }
-#pragma unroll
-    for (int a = 0; a < SCG_A; ++a) qa[a] = qb[a] = 0.f;
+    f2_t pax[(N1 + 1) / 2], pay[(N1 + 1) / 2], pbx[(N1 + 1) / 2], pby[(N1 + 1) / 2];
+    pow_pairs<N1>(za[3], pax, pay);
+    pow_pairs<N1>(zb[3], pbx, pby);
+    QAcc A, Bq;
+    qacc_zero(A);
+    qacc_zero(Bq);
     float2 a0 = make_float2(1.f, 0.f), b0 = a0;
     int f = 0;
 #pragma unroll 1
@@ -367,21 +404,25 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
 #pragma unroll 1
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-                for (int c3 = 0; c3 < N1; ++c3) {
-                    float fa = fmaf(a012.x, pa[c3].x, -a012.y * pa[c3].y);
-                    float fb = fmaf(b012.x, pb[c3].x, -b012.y * pb[c3].y);
-                    float4 wa, wb;
-                    w.load(f + c3, wa, wb);
-                    qa[0] = fmaf(wa.x, fa, qa[0]);
-                    qa[1] = fmaf(wa.y, fa, qa[1]);
-                    qa[2] = fmaf(wa.z, fa, qa[2]);
-                    qa[3] = fmaf(wa.w, fa, qa[3]);
-                    qa[4] = fmaf(wb.x, fa, qa[4]);
-                    qb[0] = fmaf(wa.x, fb, qb[0]);
-                    qb[1] = fmaf(wa.y, fb, qb[1]);
-                    qb[2] = fmaf(wa.z, fb, qb[2]);
-                    qb[3] = fmaf(wa.w, fb, qb[3]);
-                    qb[4] = fmaf(wb.x, fb, qb[4]);
+                for (int c3 = 0; c3 < N1; c3 += 2) {
+                    const f2_t pa = phi_pair(a012, pax[c3 / 2], pay[c3 / 2]);
+                    const f2_t pb = phi_pair(b012, pbx[c3 / 2], pby[c3 / 2]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (c3 + h < N1) {
+                            f2_t w01, w23;
+                            float w4;
+                            w.load2(f + c3 + h, w01, w23, w4);
+                            const float fa = h ? f2_y(pa) : f2_x(pa), fb = h ? f2_y(pb) : f2_x(pb);
+                            const f2_t a2 = f2_dup(fa), b2 = f2_dup(fb);
+                            A.q01 = f2_fma(w01, a2, A.q01);
+                            A.q23 = f2_fma(w23, a2, A.q23);
+                            A.q4 = fmaf(w4, fa, A.q4);
+                            Bq.q01 = f2_fma(w01, b2, Bq.q01);
+                            Bq.q23 = f2_fma(w23, b2, Bq.q23);
+                            Bq.q4 = fmaf(w4, fb, Bq.q4);
+                        }
+                    }
                 }
                 f += N1;
                 a012 = scg_cmul(a012, za[2]);
@@ -393,6 +434,8 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
         a0 = scg_cmul(a0, za[0]);
         b0 = scg_cmul(b0, zb[0]);
     }
+    qacc_out(A, qa);
+    qacc_out(Bq, qb);
 }
 
 // initiation bits (oracle/agent.py initiation_bits): bit k iff active and z_k >= 0 (sigmoid(z) >= 0.5  <=>  z >= 0), with
