@@ -745,7 +745,9 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     if (win_2cta5 < 0) { const char *e = getenv("SCG_WIN_2CTA5"); win_2cta5 = e ? atoi(e) : 0; }   // measured: 80 registers + spills, 0.345 vs 0.258 ms/step: off
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
     switch (ctx->order) {
-        // <N1, floats per chunk, threads, chunks per thread>.  Measured on B200 (order 3, B = 65,536): two warps per
+        // <N1, floats per chunk, threads, chunks per thread>.  Register budget matters more than occupancy here: the
+        // order-3 sweep left uncapped takes 158 registers (6 CTAs / SM) and runs 0.157 ms; capped to 128 registers
+        // (8 CTAs / SM) 0.178 ms; 96 registers (9 CTAs) 0.178 ms.  Measured on B200 (order 3, B = 65,536): two warps per
         // env with one chunk per thread 0.155 ms; one warp per env with two chunks per thread (SCG_WIN_CH3=2) has 18 %
         // fewer instructions but only 8 warps/SM to hide the shared-memory latency: 0.159 ms.  Order 5: 2.27 vs 2.38 ms.
         case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
