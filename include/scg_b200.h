@@ -170,7 +170,8 @@ typedef struct scg_agent {
     int32_t gestation_successes, clf_steps; float clf_lr;   /* controller: promotion threshold, classifier fit */
     int32_t top_slots;               /* 0: options are chosen "first active initiation set"; n = ceil(K / 5): by the top-level
                                         SMDP learner whose weights are slots K .. K+n-1 of W / Wt / dW / cnt (K + n <= 16) */
-    float alpha_top, epsilon_top; int32_t reserved0;
+    float alpha_top, epsilon_top;
+    int32_t init_horizon;            /* an example is positive iff the option hit a target within this many steps of its start */
     /* per-env state (device) */
     float *x, *y, *vx, *vy;          /* current state s */
     float *x2, *y2, *vx2, *vy2;      /* the other state buffer: a step writes s' here, then the two swap */

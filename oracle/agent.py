@@ -24,7 +24,7 @@ One agent step t, for every env (this is the definition the fused GPU pipeline m
      r     = r_env + (option_bonus if hit and not env_done)
   4. a2 = eps-greedy(Q_o(s2, .); Philox(seed; env, t, STREAM_ACTION))
   5. Sarsa(lambda) update of option o with (s, a, r, s2, a2, done=term)
-  6. where term: append (option start position, label = hit) to option o's example ring;
+  6. where term: append (option start position, label = hit and t_opt <= init_horizon) to option o's example ring;
      n_success[o] += hit, n_fail[o] += not hit
   7. where env_done or episode timed out: env reset to a start state, ep_steps = 0
   8. where term: o' = first active k with I_k(s_next), else g;  t_opt = 0; start position = s_next
@@ -80,6 +80,7 @@ class AgentConfig:
     example_capacity: int = 4096
     clf_steps: int = 200
     clf_lr: float = 1.0
+    init_horizon: int = 1 << 30   # an example is positive iff the option hit a target within this many steps of its start
     graph: bool = False
     windowed: bool = False      # Sarsa(lambda) in the forward-view window form (OptionSet.flush) instead of the dense sweep
     top_level: bool = False     # option choice by the learned SMDP value function Q_top instead of "first active"
@@ -205,7 +206,7 @@ class SkillChainAgent:
             k = o[b]
             slot = self.ex_count[k] % cfg.example_capacity
             self.ex_xy[k, slot] = self.start_xy[b]
-            self.ex_label[k, slot] = 1 if hit[b] else 0
+            self.ex_label[k, slot] = 1 if (hit[b] and self.t_opt[b] <= cfg.init_horizon) else 0
             self.ex_count[k] += 1
             if hit[b]:
                 self.n_success[k] += 1

@@ -49,6 +49,7 @@ class AgentConfig:
     example_capacity: int = 4096
     clf_steps: int = 200
     clf_lr: float = 1.0
+    init_horizon: int = 1 << 30   # an example is positive iff the option hit a target within this many steps of its start
     graph: bool = False
     cull: bool = True
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
@@ -268,6 +269,7 @@ class SkillChainAgent:
         g.graph, g.gestation_successes = int(bool(cfg.graph)), int(cfg.gestation_successes)
         g.clf_steps, g.clf_lr = int(cfg.clf_steps), float(cfg.clf_lr)
         g.top_slots, g.alpha_top, g.epsilon_top = self.top_slots, float(cfg.alpha_top), float(cfg.epsilon_top)
+        g.init_horizon = int(min(cfg.init_horizon, 1 << 30))
         s, s2 = self._sbuf
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))

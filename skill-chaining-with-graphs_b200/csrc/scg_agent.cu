@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                 // 6: example for option o's initiation classifier: the event byte and the option's start position go
                 // with the record; k_ring appends them to the ring in the oracle's order (step, then env)
                 rec[1] = make_float4(delta, __uint_as_float(meta), stx, sty);
-                args.ev[(size_t)s * g.B + b] = term ? (uint8_t)(SCG_EV_TERM | (hit ? SCG_EV_HIT : 0) | o) : (uint8_t)0;
+                args.ev[(size_t)s * g.B + b] = term ? (uint8_t)(SCG_EV_TERM | ((hit && t_opt <= g.init_horizon) ? SCG_EV_HIT : 0) | o) : (uint8_t)0;
                 if (term) atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
                 // 7: env reset
                 if (reset) {

@@ -516,6 +516,38 @@ def test_agent_run_and_manage_promotes_option(scg, torch):
     assert int((ag.option == 1).sum()) > 0                 # the new gestating option is being executed
 
 
+def test_run_episode_matches_oracle(scg, torch):
+    """SkillChainAgent.run_episode against the oracle's: same stopping rule (every env has finished one more episode),
+    same step count, finished / goal counts and mean return of the last finished episodes.  epsilon = 1 makes every
+    action exploratory (identical Philox draws on both sides), so the two free-running agents follow identical
+    trajectories; check_every=1 evaluates the stopping rule after every step, as the oracle does."""
+    B, K = 512, 3
+    kw = dict(sync_interval=4, option_timeout=6, epsilon=1.0, alpha=1e-3, max_episode_steps=14, gestation_successes=10 ** 9)
+    oag, gag = _paired_agents(scg, torch, B, 2, K, "easy", 41, **kw)
+    tx, ty, tr = oag.map.target
+    rng = np.random.default_rng(2)
+    S = oag.env.state.copy()
+    S[: B // 4, 0] = tx + rng.uniform(-0.1, 0.0, B // 4)          # a quarter starts next to the goal: some episodes end there
+    S[: B // 4, 1] = ty + rng.uniform(-0.05, 0.05, B // 4)
+    oag.env.reset(states=S)
+    oag.start_xy = oag.env.state[:, :2].copy()
+    gag.s.copy_(torch.as_tensor(S.T.copy()))
+    gag.start_xy.copy_(torch.as_tensor(S[:, :2].copy()))
+    gag.invalidate()
+    for rounds in range(2):                                        # two consecutive calls: the base is per call
+        o = oag.run_episode(max_steps=40, manage_every=8)
+        g = gag.run_episode(max_steps=40, manage_every=8, check_every=1)
+        assert g["steps"] == o["steps"] and g["finished"] == o["finished"] == B and g["goals"] == o["goals"]
+        assert g["env_steps"] == o["env_steps"] and g["n_active"] == o["n_active"]
+        assert abs(g["mean_return"] - o["mean_return"]) <= 1e-6 * abs(o["mean_return"])
+        assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), oag.env.state.view(np.uint32))
+        assert np.array_equal(gag.ep_count.cpu().numpy(), oag.episodes)
+    assert o["goals"] > 0 and o["steps"] <= 14
+    # the default (check every manage_every steps) stops at the next multiple of 8
+    g2 = gag.run_episode(max_steps=40, manage_every=8)
+    assert g2["steps"] % 8 == 0 and g2["finished"] == B
+
+
 # ---- top-level SMDP learner over the options (SURVEY.md section 8 f-3) ------------------------------------------
 @pytest.mark.parametrize("order,K,n_active,name,B,launch", [
     (3, 4, 2, "easy", 3000, "window"),
