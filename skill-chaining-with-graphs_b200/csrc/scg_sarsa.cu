@@ -603,7 +603,7 @@ __global__ void k_make_rec(int B, const float *__restrict__ x, const float *__re
 // Slots k >= K_opt hold the top-level learner (oracle/option.py): step size alpha_top, mean over the window's events.
 template <int N1>
 __global__ void k_apply(int K, int K_opt, float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ dW,
-                        const int *__restrict__ cnt, float alpha, float alpha_top, float steps) {
+                        int *cnt, float alpha, float alpha_top, float steps, unsigned int *ticket) {
     constexpr int F = N1 * N1 * N1 * N1;
     int n = K * SCG_A * F;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -623,10 +623,15 @@ __global__ void k_apply(int K, int K_opt, float *__restrict__ W, float *__restri
         Wt[((size_t)f * K + k) * SCG_WT_STRIDE + a] = w;
         dW[i] = 0.f;
     }
-}
-__global__ void k_zero_int(int n, int *p) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0;
+    // the last block to finish zeroes cnt for the next window (every block has read it by then): no extra launch
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < K) cnt[threadIdx.x] = 0;
 }
 
 // ---- launch plumbing ----------------------------------------------------------------------------
@@ -845,9 +850,27 @@ extern "C" int scg_apply_top(int order, int K, int K_opt, float *W, float *Wt, f
     float steps = (float)std::max(window_steps, 1);
     int F = scg_pow4(order + 1);
     int grid = std::max(1, std::min((K * SCG_A * F + 255) / 256, SCG_NUM_SMS * 8));
-    DISPATCH_ORDER(order, k_apply<N1><<<grid, 256, 0, st>>>(K, K_opt, W, Wt, dW, cnt, alpha, alpha_top, steps));
-    SCG_LAUNCH_CHECK();
-    k_zero_int<<<1, 32, 0, st>>>(K, cnt);
+    // one "blocks done" counter per (device, stream): launches on one stream are ordered, so the counter (which atomicInc
+    // wraps back to 0) is reusable launch after launch; applies running concurrently on other streams have their own
+    struct Slot { int dev; cudaStream_t st; unsigned int *ticket; };
+    static Slot slots[64];
+    static int n_slots = 0;
+    int dev = 0;
+    SCG_CUDA_OK(cudaGetDevice(&dev));
+    unsigned int *ticket = nullptr;
+    for (int i = 0; i < n_slots; ++i)
+        if (slots[i].dev == dev && slots[i].st == st) ticket = slots[i].ticket;
+    if (!ticket) {
+        if (n_slots >= 64) {           // many short-lived streams: wait for everything, start the table over
+            SCG_CUDA_OK(cudaDeviceSynchronize());
+            for (int i = 0; i < n_slots; ++i) cudaFree(slots[i].ticket);
+            n_slots = 0;
+        }
+        SCG_CUDA_OK(cudaMalloc((void **)&ticket, sizeof(unsigned int)));
+        SCG_CUDA_OK(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+        slots[n_slots++] = Slot{dev, st, ticket};
+    }
+    DISPATCH_ORDER(order, k_apply<N1><<<grid, 256, 0, st>>>(K, K_opt, W, Wt, dW, cnt, alpha, alpha_top, steps, ticket));
     SCG_LAUNCH_CHECK();
     return 0;
 }

@@ -59,7 +59,8 @@ def main():
     ap.add_argument("--alpha", type=float, default=2e-3)
     ap.add_argument("--alpha-top", type=float, default=1e-3)
     ap.add_argument("--epsilon", type=float, default=0.1)
-    ap.add_argument("--gestation", type=int, default=3000)
+    ap.add_argument("--gestation", type=int, default=200000)
+    ap.add_argument("--train-seconds", type=float, default=30.0, help="keep learning this long after the chain is complete")
     ap.add_argument("--horizon", type=int, default=40)
     ap.add_argument("--option-timeout", type=int, default=120)
     ap.add_argument("--max-episode-steps", type=int, default=1500)
@@ -106,6 +107,15 @@ def main():
             done = (covered and c["n_active"] >= args.min_chain) or c["n_active"] >= args.options - 1
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    # the chain is in place: keep learning the option policies and the top-level values for a while
+    t1 = time.perf_counter()
+    train_steps = 0
+    while time.perf_counter() - t1 < args.train_seconds:
+        ag.run(16 * args.chunk)
+        ag.manage()
+        train_steps += 16 * args.chunk
+        torch.cuda.synchronize()
+    train_wall = time.perf_counter() - t1
     c = ag.controller_state(sync=True)
     cnt = ag.counters()
     # how much of the free space each initiation set covers, and whether it contains the map's start
@@ -113,7 +123,7 @@ def main():
     inside = ag.options.initiation(probe)[:, :c["n_active"]].float().mean(dim=0).cpu().numpy().tolist() if c["n_active"] else []
     after = evaluate(scg, torch, base, ag, args, trained=True)
     print(json.dumps(dict(map=args.map, batch=args.batch, graph=args.graph, top_level=not args.no_top_level,
-                          wall_s=round(wall, 3), steps=steps, env_steps=steps * args.batch, n_active=c["n_active"],
+                          wall_s=round(wall, 3), train_after_s=round(train_wall, 2), train_after_steps=train_steps, steps=steps, env_steps=steps * args.batch, n_active=c["n_active"],
                           chain_complete=done, start_covered=start_covered(c["n_active"]), parents=c["parents"],
                           initiation_set_fraction_of_free_space=[round(v, 3) for v in inside],
                           goals=cnt["goals"], episodes=cnt["episodes"], mean_return=cnt["mean_return"],
