@@ -371,6 +371,37 @@ def run_ours(args):
     n_e2e = max(3, min(n_blocks, -(-256 // max(args.steps, 1))))
     e2e = e2e_blocks(host_steps, n_e2e)
     e2e_ms = float(np.median(e2e))
+
+    # where an end-to-end step goes: the pieces timed one by one with CUDA events (pinned host buffers, this stream)
+    def ev_time(fn, reps=20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e3
+
+    hbuf = ag._host[0]
+    dS, dO = ag.s.clone(), ag._out.clone()
+    pin_out = torch.empty((4, B), dtype=torch.float32).pin_memory()
+    brk = {
+        "h2d_state_action_us": ev_time(lambda: (ag.s.copy_(hbuf["s"], non_blocking=True), ag.action.copy_(hbuf["a"], non_blocking=True))),
+        "d2h_state_results_us": ev_time(lambda: (hbuf["s2"].copy_(dS, non_blocking=True), pin_out.copy_(dO, non_blocking=True))),
+    }
+
+    def one_step():
+        ag.invalidate()
+        ag.step()
+
+    brk["step_kernel_single_step_requeried_q_us"] = ev_time(one_step, reps=2 * ag.win_cap) - (m["k3_ms"] + m["side_ms"][2] + m["side_ms"][3] + m["side_ms"][4]) * 1e3 / ag.win_cap
+    brk["sweep_reduce_apply_ring_per_step_us"] = (m["k3_ms"] + m["side_ms"][2] + m["side_ms"][3] + m["side_ms"][4]) * 1e3 / ag.win_cap
+    brk["measured_total_us"] = e2e_ms * 1e3 / args.steps
+    brk["host_and_launch_latency_us"] = brk["measured_total_us"] - sum(v for k, v in brk.items() if k != "measured_total_us")
+    brk["note"] = ("copies are PCIe-bound and cannot overlap the step (the caller needs the results before it can supply the "
+                   "next inputs); the sweep / apply chain of a full window must finish before the next step's Q evaluation")
     # informational: the same loop for a caller that needs the state only once per sync interval (run_host)
     Ts = args.sync_interval
     hw = dict(s=ag.s.cpu().numpy().copy(), a=ag.action.cpu().numpy().copy())
@@ -472,7 +503,7 @@ def run_ours(args):
             "e2e": {"value": total_env_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": B * scg.SkillChainAgent.HOST_H2D_BYTES_PER_ENV,
                     "d2h_bytes_per_step": B * scg.SkillChainAgent.HOST_D2H_BYTES_PER_ENV,
-                    "blocks_ms": e2e,
+                    "blocks_ms": e2e, "breakdown_per_step": brk,
                     "api": "SkillChainAgent.step_host -> scg_agent_step_host (pinned host buffers)"},
             "e2e_per_sync_interval": {"value": B * world * n_calls * Ts / (e2e_win_ms * 1e-3), "unit": UNIT,
                                       "h2d_bytes_per_call": B * 20, "d2h_bytes_per_call": B * 32, "steps_per_call": Ts,
