@@ -59,9 +59,9 @@ def main():
     ap.add_argument("--alpha", type=float, default=2e-3)
     ap.add_argument("--alpha-top", type=float, default=1e-3)
     ap.add_argument("--epsilon", type=float, default=0.1)
-    ap.add_argument("--gestation", type=int, default=200000)
-    ap.add_argument("--train-seconds", type=float, default=30.0, help="keep learning this long after the chain is complete")
-    ap.add_argument("--horizon", type=int, default=40)
+    ap.add_argument("--gestation", type=int, default=20000)
+    ap.add_argument("--train-seconds", type=float, default=25.0, help="keep learning this long after the chain is complete")
+    ap.add_argument("--horizon", type=int, default=120)
     ap.add_argument("--option-timeout", type=int, default=120)
     ap.add_argument("--max-episode-steps", type=int, default=1500)
     ap.add_argument("--starts", type=int, default=255)
