@@ -230,7 +230,10 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     for (int j = 0; j < CH; ++j) {
         const int f0 = (own[j] ? tid + j * NT : 0) * VEC;
         off01[j] = (f0 / NN) * (int)sizeof(float2);
-        off23[j] = (NN + f0 % NN) * (int)sizeof(float2);
+        // P23: scalar form one float2 per (c2, c3); vector form in two halves - entries (4g, 4g+1) of every group g of
+        // four, then entries (4g+2, 4g+3) - so that the 16-byte loads of a warp's NN/4 distinct groups are contiguous
+        // (order 5: 9 groups at a 32-byte stride collided three to a bank quad: 9.4 wavefronts per load; now 2)
+        off23[j] = VEC == 4 ? NN * (int)sizeof(float2) + ((f0 % NN) / 4) * 16 : (NN + f0 % NN) * (int)sizeof(float2);
     }
     // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits,
     // and the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4)
@@ -307,7 +310,14 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
                 const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
                 const int idx = tid + k * NT;
-                if (idx < TABN) tb[idx] = make_float2(__cosf(xr), __sinf(xr));
+                if (idx < TABN) {
+                    int at = idx;
+                    if (VEC == 4 && e_half[k]) {
+                        const int ij = idx - (e_tt[k] * 2 + 1) * NN, g = ij >> 2, kk = ij & 3;
+                        at = (e_tt[k] * 2 + 1) * NN + (kk < 2 ? 2 * g + kk : NN / 2 + 2 * g + (kk - 2));
+                    }
+                    tb[at] = make_float2(__cosf(xr), __sinf(xr));
+                }
             }
         }
         if (it.blk == 0 && scan_warp) {
@@ -480,7 +490,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                         V ph;
                         if constexpr (VEC == 4) {
                             const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
-                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + 16);
+                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + (NN / 4) * 16);
                             ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
                                              fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
                         } else {
