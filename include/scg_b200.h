@@ -172,6 +172,8 @@ typedef struct scg_agent {
                                         SMDP learner whose weights are slots K .. K+n-1 of W / Wt / dW / cnt (K + n <= 16) */
     float alpha_top, epsilon_top;
     int32_t init_horizon;            /* an example is positive iff the option hit a target within this many steps of its start */
+    float merge_overlap, goal_x, goal_y; int32_t reserved1;   /* option graph: merge detection threshold (0: every older option
+                                        and the goal are targets), the goal position (oracle/agent.py merged_parents) */
     /* per-env state (device) */
     float *x, *y, *vx, *vy;          /* current state s */
     float *x2, *y2, *vx2, *vy2;      /* the other state buffer: a step writes s' here, then the two swap */

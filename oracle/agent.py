@@ -81,6 +81,8 @@ class AgentConfig:
     clf_steps: int = 200
     clf_lr: float = 1.0
     init_horizon: int = 1 << 30   # an example is positive iff the option hit a target within this many steps of its start
+    merge_overlap: float = 0.0    # graph mode: an older option's initiation set becomes a target of the next option iff at
+                                  # least this fraction of the promoted option's positive examples lies inside it (0: all)
     graph: bool = False
     windowed: bool = False      # Sarsa(lambda) in the forward-view window form (OptionSet.flush) instead of the dense sweep
     top_level: bool = False     # option choice by the learned SMDP value function Q_top instead of "first active"
@@ -280,10 +282,33 @@ class SkillChainAgent:
         self.n_active += 1
         n = self.n_active
         if cfg.graph:
-            self.parents[n] = np.uint32((1 << n) - 1) | GOAL_BIT
+            self.parents[n] = self.merged_parents(g, X, y)
         else:
             self.parents[n] = np.uint32(1 << (n - 1))
         return True
+
+    def merged_parents(self, g, X, y):
+        """Option graph, merge detection ("a new option may adopt an existing option's initiation
+        set as an additional target when their chains meet").  The next option's targets are the initiation set of the
+        option just promoted (g), every older active option j whose initiation set MEETS g's - at least
+        cfg.merge_overlap of g's positive examples (start positions from which g reached its target) lie inside I_j -
+        and the goal if it lies inside I_g or merge_overlap is 0.  With merge_overlap = 0 every older option and the
+        goal qualify: the plain graph mode."""
+        cfg = self.cfg
+        pm = np.uint32(1 << g)
+        pos = np.asarray(X, dtype=np.float32).reshape(-1, 2)[np.asarray(y).reshape(-1) != 0]
+        if len(pos):
+            st = np.concatenate([pos, np.zeros_like(pos)], axis=1)
+            inside = self.options.initiation_logit(st) >= f32(0.0)                   # (n_pos, K)
+        for j in range(g):
+            frac = f32(inside[:, j].sum()) / f32(len(pos)) if len(pos) else f32(0.0)
+            if frac >= f32(cfg.merge_overlap):
+                pm |= np.uint32(1 << j)
+        tx, ty, _ = self.map.target
+        goal_in = self.options.initiation_logit(np.array([[tx, ty, 0, 0]], dtype=np.float32))[0, g] >= f32(0.0)
+        if cfg.merge_overlap <= 0.0 or goal_in:
+            pm |= GOAL_BIT
+        return pm
 
     def run_episode(self, max_steps=2000, manage_every=64):
         """Step until every env has finished at least one more episode, or `max_steps` steps."""

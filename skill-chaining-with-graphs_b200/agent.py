@@ -50,6 +50,8 @@ class AgentConfig:
     clf_steps: int = 200
     clf_lr: float = 1.0
     init_horizon: int = 1 << 30   # an example is positive iff the option hit a target within this many steps of its start
+    merge_overlap: float = 0.0    # graph mode: an older option's initiation set becomes a target of the next option iff at
+                                  # least this fraction of the promoted option's positive examples lies inside it (0: all)
     graph: bool = False
     cull: bool = True
     window: int = 0          # steps per trace sweep; 0 = min(sync_interval, 8)
@@ -270,6 +272,8 @@ class SkillChainAgent:
         g.clf_steps, g.clf_lr = int(cfg.clf_steps), float(cfg.clf_lr)
         g.top_slots, g.alpha_top, g.epsilon_top = self.top_slots, float(cfg.alpha_top), float(cfg.epsilon_top)
         g.init_horizon = int(min(cfg.init_horizon, 1 << 30))
+        g.merge_overlap = float(cfg.merge_overlap)
+        g.goal_x, g.goal_y = float(self.map.target[0]), float(self.map.target[1])
         s, s2 = self._sbuf
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
@@ -516,6 +520,8 @@ class SkillChainAgent:
         self._ctl.n_active = n
         self._ctl.n_promotions += 1
         self._ctl.last_promotion_step = int(self._struct.step)
+        if cfg.graph and cfg.merge_overlap > 0.0:
+            raise _lib.ScgError("merge detection (merge_overlap > 0) needs the device controller (sync_backend='p2p')")
         self.parents_host[n] = (((1 << n) - 1) | GOAL_BIT) if cfg.graph else (1 << (n - 1))
         self._push_ctl()
 

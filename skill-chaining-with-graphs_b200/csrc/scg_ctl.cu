@@ -352,8 +352,46 @@ __device__ __forceinline__ void manage_accum(float px, float py, float lab, cons
     for (int j = 0; j < SCG_N_PSI; ++j) g[j] = fmaf(d, psi[j], g[j]);
 }
 
+// Sum `nval` (<= XCHG_M_WORDS) per-rank values over the ranks through the peer-memory block: publish, signal every peer,
+// wait for every peer, add in rank order (identical on every rank).  vals: shared memory, in/out.  One flag round;
+// `seq` is the round counter every rank advances in step.  Returns false (and raises the sticky flag) if a peer never came.
+__device__ __forceinline__ bool manage_exchange(const ManageArgs &a, float *vals, int nval, uint32_t &seq, int *s_abort) {
+    const int tid = threadIdx.x;
+    unsigned char *mine = a.peer[a.rank] + a.m_off;
+    seq += 1;
+    float *mb = reinterpret_cast<float *>(mine + XCHG_M_BUF) + (seq & 1u) * XCHG_M_WORDS;
+    if (tid < nval) mb[tid] = vals[tid];
+    __syncthreads();
+    if (tid < a.world && tid != a.rank) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t *>(a.peer[tid] + a.m_off + XCHG_M_FLAG) + a.rank, seq);
+        const uint32_t *lf = reinterpret_cast<const uint32_t *>(mine + XCHG_M_FLAG) + tid;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(lf) - seq) < 0) {
+            if (clock64() - t0 > a.timeout_cycles) {
+                *reinterpret_cast<volatile uint32_t *>(a.status) = 1u;
+                __threadfence_system();
+                *s_abort = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nval && !*s_abort) {
+        float v = 0.f;
+        for (int r = 0; r < a.world; ++r) {
+            const float *pb = reinterpret_cast<const float *>(a.peer[r] + a.m_off + XCHG_M_BUF) + (seq & 1u) * XCHG_M_WORDS;
+            v += (r == a.rank) ? mb[tid] : ld_sys_f32(pb + tid);
+        }
+        vals[tid] = v;
+    }
+    __syncthreads();
+    return !*s_abort;
+}
+
 __global__ void __launch_bounds__(MANAGE_NT) k_manage(const __grid_constant__ ManageArgs a) {
     __shared__ float sm[33 * 8];
+    __shared__ float xv[XCHG_M_WORDS];           // values summed over ranks: a fit step's (6 sums, N) / the merge counts
     __shared__ int s_go, s_abort;
     const scg_agent_t &g = a.ag;
     scg_ctl_t *ctl = g.ctl;
@@ -389,7 +427,6 @@ __global__ void __launch_bounds__(MANAGE_NT) k_manage(const __grid_constant__ Ma
         float th[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unsigned char *mine = a.world > 1 ? a.peer[a.rank] + a.m_off : nullptr;
         uint32_t seq = (a.world > 1) ? *reinterpret_cast<uint32_t *>(mine + XCHG_M_SEQ) : 0u;
-        // does any rank have examples?  (one exchange round when there are several ranks; also the first fit round)
         for (int it = 0; it < g.clf_steps && !s_abort; ++it) {
             float gs[SCG_N_PSI] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -408,62 +445,71 @@ __global__ void __launch_bounds__(MANAGE_NT) k_manage(const __grid_constant__ Ma
                 for (int j = 0; j < SCG_N_PSI; ++j) {
                     float v = sm[lane * 8 + j];          // 32 warps
                     v = scg_warp_sum(v);
-                    if (lane == 0) sm[32 * 8 + j] = v;
+                    if (lane == 0) xv[j] = v;
                 }
-                if (lane == 0) sm[32 * 8 + 6] = (float)N;
+                if (lane == 0) xv[6] = (float)N;
             }
             __syncthreads();
-            if (a.world > 1) {
-                // exchange round: publish (6 sums, N), signal every peer, wait for every peer, add in rank order
-                seq += 1;
-                float *mb = reinterpret_cast<float *>(mine + XCHG_M_BUF) + (seq & 1u) * 8;
-                if (tid < 8) mb[tid] = tid < 7 ? sm[32 * 8 + tid] : 0.f;
-                __syncthreads();
-                if (tid < a.world && tid != a.rank) {
-                    __threadfence_system();
-                    st_release_sys(reinterpret_cast<uint32_t *>(a.peer[tid] + a.m_off + XCHG_M_FLAG) + a.rank, seq);
-                    const uint32_t *lf = reinterpret_cast<const uint32_t *>(mine + XCHG_M_FLAG) + tid;
-                    const long long t0 = clock64();
-                    while ((int32_t)(ld_acquire_sys(lf) - seq) < 0) {
-                        if (clock64() - t0 > a.timeout_cycles) {
-                            *reinterpret_cast<volatile uint32_t *>(a.status) = 1u;
-                            __threadfence_system();
-                            s_abort = 1;
-                            break;
-                        }
-                    }
-                }
-                __syncthreads();
-                if (tid < 7 && !s_abort) {
-                    float v = 0.f;
-                    for (int r = 0; r < a.world; ++r) {
-                        const float *pb = reinterpret_cast<const float *>(a.peer[r] + a.m_off + XCHG_M_BUF) + (seq & 1u) * 8;
-                        v += (r == a.rank) ? mb[tid] : ld_sys_f32(pb + tid);
-                    }
-                    sm[32 * 8 + tid] = v;
-                }
-                __syncthreads();
-            }
-            const float ntot = sm[32 * 8 + 6];
+            if (a.world > 1) manage_exchange(a, xv, 7, seq, &s_abort);
+            const float ntot = xv[6];
             if (ntot > 0.f) {      // no examples anywhere: theta stays 0 (initiation set = everywhere), as in the oracle
 #pragma unroll
                 for (int j = 0; j < SCG_N_PSI; ++j)
-                    th[j] = __fsub_rn(th[j], __fmul_rn(g.clf_lr, __fdiv_rn(sm[32 * 8 + j], ntot)));
+                    th[j] = __fsub_rn(th[j], __fmul_rn(g.clf_lr, __fdiv_rn(xv[j], ntot)));
             }
             __syncthreads();
         }
-        if (a.world > 1 && tid == 0) *reinterpret_cast<uint32_t *>(mine + XCHG_M_SEQ) = seq;
-        if (!s_abort) {
-            if (tid < SCG_N_PSI) g.theta[gi * SCG_N_PSI + tid] = th[tid];
-            if (tid == 0) {
-                const int n = gi + 1;
-                ctl->parents[n] = g.graph ? (((1u << n) - 1u) | SCG_GOAL_BIT) : (1u << (n - 1));
-                ctl->active_mask |= (1u << gi);
-                ctl->n_promotions += 1;
-                ctl->last_promotion_step = g.step;
-                __threadfence();
-                ctl->n_active = n;
+        if (!s_abort && tid < SCG_N_PSI) g.theta[gi * SCG_N_PSI + tid] = th[tid];
+        __syncthreads();
+        // the next gestating slot's targets.  chain: {g}.  graph: {g}, every older option whose initiation set holds at
+        // least merge_overlap of g's positive examples, and the goal if it lies inside I_g or merge_overlap is 0
+        // (oracle/agent.py merged_parents; merge_overlap = 0: all of them)
+        uint32_t pm = 1u << gi;
+        if (g.graph && !s_abort) {
+            if (tid < XCHG_M_WORDS) xv[tid] = 0.f;
+            __syncthreads();
+            if (g.merge_overlap > 0.f) {
+                // inside-counts of the positive examples, per older option (theta_gi was just written: not needed here)
+                for (int j = 0; j < gi; ++j) {
+                    float c = 0.f, np = 0.f;
+                    for (int i = tid; i < N; i += MANAGE_NT) {
+                        if (Y[i]) {
+                            const float x = X[2 * i], y = X[2 * i + 1];
+                            np += 1.f;
+                            if (scg_init_logit(g.theta + j * SCG_N_PSI, x, y, __fmul_rn(x, x), __fmul_rn(x, y), __fmul_rn(y, y)) >= 0.f)
+                                c += 1.f;
+                        }
+                    }
+                    c = scg_warp_sum(c);
+                    np = scg_warp_sum(np);
+                    if (lane == 0) { atomicAdd(&xv[j], c); if (j == 0) atomicAdd(&xv[SCG_MAX_OPTIONS], np); }
+                }
+                if (gi == 0) {      // no older option: still count the positives (not used)
+                }
+                __syncthreads();
+                if (a.world > 1) manage_exchange(a, xv, SCG_MAX_OPTIONS + 1, seq, &s_abort);
+                const float npos = xv[SCG_MAX_OPTIONS];
+                for (int j = 0; j < gi; ++j) {
+                    const float frac = npos > 0.f ? __fdiv_rn(xv[j], npos) : 0.f;
+                    if (frac >= g.merge_overlap) pm |= 1u << j;
+                }
+                const float gx = g.goal_x, gy = g.goal_y;
+                const float zg = scg_init_logit(g.theta + gi * SCG_N_PSI, gx, gy, __fmul_rn(gx, gx), __fmul_rn(gx, gy), __fmul_rn(gy, gy));
+                // (theta_gi as written above: every thread reads it after the barrier)
+                if (zg >= 0.f) pm |= SCG_GOAL_BIT;
+            } else {
+                pm = ((1u << (gi + 1)) - 1u) | SCG_GOAL_BIT;
             }
+        }
+        if (a.world > 1 && tid == 0) *reinterpret_cast<uint32_t *>(mine + XCHG_M_SEQ) = seq;
+        if (!s_abort && tid == 0) {
+            const int n = gi + 1;
+            ctl->parents[n] = pm;
+            ctl->active_mask |= (1u << gi);
+            ctl->n_promotions += 1;
+            ctl->last_promotion_step = g.step;
+            __threadfence();
+            ctl->n_active = n;
         }
     }
     __syncthreads();

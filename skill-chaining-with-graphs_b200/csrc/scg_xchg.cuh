@@ -26,11 +26,13 @@ struct scg_xchg {
 // controller region of the block (the classifier fit of scg_agent_manage exchanges per-step gradient sums through it):
 //   u32 mflag[XCHG_MAX_WORLD]   round number last signalled by each peer
 //   u32 mseq                    rounds completed so far (kept on the device: only the kernel knows whether it promoted)
-//   f32 mbuf[2][8]              this rank's (6 gradient sums, example count, pad) of the current / previous round
+//   f32 mbuf[2][32]             this rank's values of the current / previous round: (6 gradient sums, example count) of a
+//                               fit step, or (inside-counts of up to 16 older options, positive count) of the merge detection
 #define XCHG_M_FLAG 0
 #define XCHG_M_SEQ (XCHG_MAX_WORLD * 4)
 #define XCHG_M_BUF (XCHG_MAX_WORLD * 4 + 16)
-#define XCHG_M_BYTES (XCHG_M_BUF + 2 * 8 * 4)
+#define XCHG_M_WORDS 32
+#define XCHG_M_BYTES (XCHG_M_BUF + 2 * XCHG_M_WORDS * 4)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {

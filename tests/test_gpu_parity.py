@@ -665,15 +665,15 @@ def test_example_rings_match_oracle_past_capacity(scg, torch, B, cap, launch):
     assert int(gag.ex_count.sum()) == int(gag.n_success.sum() + gag.n_fail.sum())
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_manage_on_device_matches_oracle(scg, torch, graph):
+@pytest.mark.parametrize("graph,merge_overlap", [(False, 0.0), (True, 0.0), (True, 0.25)])
+def test_manage_on_device_matches_oracle(scg, torch, graph, merge_overlap):
     """scg_agent_manage (decision + classifier fit + promotion in ONE kernel, no host round trip) against
     oracle.manage(): same decision at the same call, theta within 1e-4, same parents / masks; below the threshold and at
     the last slot nothing happens."""
     from oracle_replay import activate, default_theta
     B, K = 4096, 4
     kw = dict(sync_interval=4, option_timeout=6, epsilon=0.3, alpha=1e-3, gestation_successes=40, clf_steps=120, clf_lr=2.0,
-              graph=graph)
+              graph=graph, merge_overlap=merge_overlap)
     oag, gag = _paired_agents(scg, torch, B, 2, K, "easy", 19, **kw)
     tx, ty, tr = oag.map.target
     rng = np.random.default_rng(0)
@@ -686,7 +686,7 @@ def test_manage_on_device_matches_oracle(scg, torch, graph):
     gag.start_xy.copy_(torch.as_tensor(S[:, :2].copy()))
     gag.invalidate()
     promoted = []
-    for w in range(6):
+    for w in range(10):
         pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 4)
         for t in range(4):
             out = oag.step(follow=dict(action=acts[t + 1], option=opts[t + 1]))
