@@ -710,6 +710,43 @@ def test_manage_on_device_matches_oracle(scg, torch, graph, merge_overlap):
     assert full.manage(wait=True) is False and full.controller_state()["n_active"] == 1
 
 
+def test_merge_detection_wires_the_meeting_chains(scg, torch):
+    """Option graph with merge detection: the option being promoted (2) has its positive examples inside I_0 (x >= 0.6)
+    but outside I_1 (y <= 0.45), so the next slot's targets must be {2, 0} and not 1; the goal joins iff it lies inside
+    the freshly fit I_2.  Same rings injected on both sides; device controller against oracle.manage()."""
+    from oracle_replay import activate, default_theta
+    B, K = 256, 5
+    kw = dict(sync_interval=4, graph=True, merge_overlap=0.5, gestation_successes=10, clf_steps=150, clf_lr=2.0)
+    oag, gag = _paired_agents(scg, torch, B, 2, K, "easy", 53, **kw)
+    theta = default_theta(K)
+    activate(oag, theta, 2, graph=True)
+    _set_gpu_options(gag, torch, theta, 2, graph=True)
+    rng = np.random.default_rng(8)
+    n = 3000
+    X = rng.random((n, 2)).astype(np.float32)
+    y = ((X[:, 0] > 0.7) & (X[:, 1] > 0.6)).astype(np.uint8)          # positives: upper right corner -> inside I_0 only
+    oag.ex_xy[2, :n], oag.ex_label[2, :n], oag.ex_count[2], oag.n_success[2] = X, y, n, 1000
+    gag._ex_xy[2, :n].copy_(torch.as_tensor(X)); gag._ex_label[2, :n].copy_(torch.as_tensor(y))
+    gag._ex_count[2] = n
+    gag.n_success[2] = 1000
+    assert oag.manage() is True and gag.manage(wait=True) is True
+    c = gag.controller_state()
+    assert c["n_active"] == oag.n_active == 3 and c["parents"] == [int(v) for v in oag.parents]
+    pm = c["parents"][3]
+    assert pm & 0b100 and pm & 0b001 and not pm & 0b010
+    assert_close(gag.options.theta[2].cpu().numpy(), oag.options.theta[2], what="theta of the promoted option")
+    # merge_overlap = 0 wires every older option and the goal (the plain graph mode)
+    oag2, gag2 = _paired_agents(scg, torch, B, 2, K, "easy", 53, **dict(kw, merge_overlap=0.0))
+    activate(oag2, theta, 2, graph=True)
+    _set_gpu_options(gag2, torch, theta, 2, graph=True)
+    oag2.ex_xy[2, :n], oag2.ex_label[2, :n], oag2.ex_count[2], oag2.n_success[2] = X, y, n, 1000
+    gag2._ex_xy[2, :n].copy_(torch.as_tensor(X)); gag2._ex_label[2, :n].copy_(torch.as_tensor(y))
+    gag2._ex_count[2] = n
+    gag2.n_success[2] = 1000
+    assert oag2.manage() and gag2.manage(wait=True)
+    assert gag2.controller_state()["parents"][3] == int(oag2.parents[3]) == (0b111 | (1 << 31))
+
+
 def test_promotion_the_host_has_not_seen_yet_is_still_correct(scg, torch):
     """The host sizes the on-chip weight staging and the sweep's accumulator with its LOWER BOUND of n_active; options
     the device promoted since are handled by the kernels' global-memory paths.  A twin launched with a stale bound
