@@ -189,12 +189,11 @@ struct WinCtlT {
     float2 gc[NS];                     // (G_t, c_t) per step
     uint32_t mask[NS][8];              // [segment][action]: steps of that segment taken with that action (5 used)
     uint32_t seg_o[NS];                // option of each segment (an env changes option only after a termination)
-    uint32_t info[NS];                 // per step: action (bits 0-2), contributes (bit 3), option changed here (bit 4), option (bits 8-15)
     float scale, carry;                // e <- scale * e_start;  d <- carry * e_start
     int nseg, pad;
 };
 
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool TM>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl, float *dW, int K_all) {
     using V = typename VecT<VEC>::type;
@@ -350,7 +349,6 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             const int seg = __popc(chg & ((2u << t) - 1u));
             const int nseg = am ? __popc(chg) + 1 : 0;
             const bool nz = act && (G != 0.f || cf != 0.f);
-            if (t < T) cb.info[t] = a | (nz ? 8u : 0u) | (((chg >> t) & 1u) ? 16u : 0u) | (o << 8);
             for (int sgm = 0; sgm < nseg; ++sgm) {
                 const unsigned in_seg = __ballot_sync(FULL, act && seg == sgm);
                 const uint32_t os = __shfl_sync(FULL, o, __ffs(in_seg) - 1);
@@ -451,52 +449,6 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 }
             }
         }
-        if constexpr (TM && !MULTI && VEC == 4) {
-            // time-major form (windows of at most 8 steps): the steps in order, fully unrolled, so that every table
-            // address is a constant offset and no bit-scan / loop-carried index chain sits in front of the loads; the
-            // action row is chosen by a switch on a value that is uniform over the CTA (all threads sweep the same env)
-#pragma unroll
-            for (int tt = 0; tt < SCG_WIN_TB; ++tt) {
-                if (tt < T) {
-                    const uint32_t info = cb.info[tt];
-                    if (info & 16u) {                    // the env changed option here (after a termination)
-                        flush_d();
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-#pragma unroll
-                            for (int r = 0; r < SCG_A; ++r) d[j][r] = vzero4();
-                        }
-                        o_cur = info >> 8;
-                    }
-                    if (info & 8u) {
-                        const float2 g2 = gc[tt];
-                        const char *tb = tb0 + tt * TSTRIDE;
-                        V ph[CH];
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
-                            const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
-                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + (NN / 4) * 16);
-                            ph[j] = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
-                                                fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
-                        }
-                        switch (info & 7u) {
-#define TM_ROW(R)                                                            \
-    case R:                                                                  \
-        _Pragma("unroll") for (int j = 0; j < CH; ++j) {                     \
-            d[j][R] = vfma(g2.x, ph[j], d[j][R]);                            \
-            e[j][R] = vfma(g2.y, ph[j], e[j][R]);                            \
-        }                                                                    \
-        break;
-                            TM_ROW(0) TM_ROW(1) TM_ROW(2) TM_ROW(3)
-                            default:
-                            TM_ROW(4)
-#undef TM_ROW
-                        }
-                    }
-                }
-            }
-        } else {
         const int nseg = cb.nseg;
         for (int sgm = 0; sgm < nseg; ++sgm) {
             // this segment's steps inside this block, one bit mask per action
@@ -550,7 +502,6 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                     }
                 }
             }
-        }
         }
         if (cur.blk == NBLK - 1) {
             flush_d();
@@ -761,11 +712,11 @@ static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi) {
 
 // k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
 // the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool TM>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                             float *dW, cudaStream_t st) {
     const size_t smem = window_smem<N1>(ctx, k_used, MULTI);
-    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL, TM>;
+    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL>;
     constexpr int NTT = NT + (CTRL ? 32 : 0);
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
@@ -786,13 +737,8 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4
 template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false>
 static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                            float *dW, cudaStream_t st) {
-    static int tm = -1;   // SCG_WIN_TM=0: the per-action bit-mask loops instead of the time-major form (windows <= 8 steps)
-    if (tm < 0) { const char *e = getenv("SCG_WIN_TM"); tm = e ? atoi(e) : 1; }
-    if (T <= SCG_WIN_TB) {
-        if (tm && VEC == 4) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL, true>(ctx, B, T, k_used, rec, trace, gl, dW, st);
-        return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL, false>(ctx, B, T, k_used, rec, trace, gl, dW, st);
-    }
-    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL, false>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
