@@ -27,6 +27,7 @@
 
 int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, float *trace, float gl, float *dW,
                       cudaStream_t st);
+int scg_reduce_window(scg_ctx *ctx, int n_slabs, int k_used, float *dW, cudaStream_t st, bool overlap_prev);
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st);
 
@@ -438,15 +439,19 @@ static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_age
 extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if (!ctx || !ag) return SCG_EINVAL;
     if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; ag->ring_len = 0; return 0; }
-    int rc = scg_agent_ring(ctx, ag, stream);      // the window's option terminations -> example rings
-    if (rc) return rc;
     // option ids in the records are 0 .. n_active (the gestating slot); n_active is the host's lower bound of the
     // device's value: records of an option promoted since then are folded through the sweep's global-memory path
     const int k_used = std::min(ag->K, std::max(ag->n_active, 0) + 1);
+    int rc;
     if ((rc = scg_launch_top(ctx, ag, (cudaStream_t)stream))) return rc;     // the top-level learner's SMDP updates
-    rc = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda, ag->dW,
-                               (cudaStream_t)stream);
-    if (rc) return rc;
+    const int n_slabs = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda,
+                                          ag->dW, (cudaStream_t)stream);
+    if (n_slabs <= 0) return n_slabs == 0 ? SCG_EINVAL : n_slabs;
+    // the window's option terminations -> example rings.  Independent of the slab reduction queued right behind it,
+    // which therefore starts under it (programmatic dependent launch)
+    const bool ring_due = ag->ring_len < ag->win_len;
+    if ((rc = scg_agent_ring(ctx, ag, stream))) return rc;
+    if ((rc = scg_reduce_window(ctx, n_slabs, k_used, ag->dW, (cudaStream_t)stream, ring_due))) return rc;
     ag->win_len = 0;
     ag->ring_len = 0;
     return 0;

@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
     __shared__ uint32_t slot0_s[SCG_MAX_OPTIONS];
     __shared__ uint32_t n_tile_ev;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // nothing queued behind this kernel by scg_agent_flush depends on it (the slab reduction): let it start now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int mis = (int)(reinterpret_cast<uintptr_t>(ev) & 3);
     const uint32_t *evw = reinterpret_cast<const uint32_t *>(ev - mis);
     const long long nv = (long long)n + mis;            // bytes [mis, nv) of the aligned view are the events

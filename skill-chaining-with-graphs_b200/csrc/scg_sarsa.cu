@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) k_reduce(int n_partials, int n, const flo
 }
 
 // slabs -> dW on stream st
-static int reduce_slabs(scg_ctx *ctx, int n_slabs, int n, float *dW, cudaStream_t st) {
+static int reduce_slabs(scg_ctx *ctx, int n_slabs, int n, float *dW, cudaStream_t st, bool overlap_prev = false) {
     const int nx_max = (ctx->K * SCG_A * ctx->F + 255) / 256;
     if (ctx->deterministic && !ctx->d_red) {
         SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_red, (size_t)SCG_RED_SLICES * ctx->K * SCG_A * ctx->F * sizeof(float)));
@@ -585,8 +585,20 @@ static int reduce_slabs(scg_ctx *ctx, int n_slabs, int n, float *dW, cudaStream_
         SCG_CUDA_OK(cudaMemsetAsync(ctx->d_tickets, 0, (size_t)nx_max * sizeof(unsigned int), st));
     }
     dim3 g((n + 255) / 256, std::min(n_slabs, SCG_RED_SLICES));
-    k_reduce<<<g, 256, 0, st>>>(n_slabs, n, ctx->d_partial, ctx->d_red, ctx->deterministic ? ctx->d_tickets : nullptr, dW);
-    SCG_LAUNCH_CHECK();
+    // overlap_prev: the kernel launched just before this one (the example-ring pass) is independent of the reduction, so
+    // the reduction may start under it (programmatic dependent launch; k_ring releases its dependents at its start)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g;
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_prev ? 1 : 0;
+    SCG_CUDA_OK(cudaLaunchKernelEx(&cfg, k_reduce, n_slabs, n, (const float *)ctx->d_partial, ctx->d_red,
+                                   ctx->deterministic ? ctx->d_tickets : (unsigned int *)nullptr, dW));
+    ++g_scg_launches;
     return 0;
 }
 
@@ -743,7 +755,8 @@ static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
 
-// fold the T recorded steps of the window into dW and the traces
+// fold the T recorded steps of the window into the traces and the per-CTA dW slabs; returns the number of slabs (> 0)
+// or an error (<= 0); scg_reduce_window then folds the slabs into dW
 int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, float *trace, float gl, float *dW,
                       cudaStream_t st) {
     if (T < 1 || T > SCG_WIN_MAX || k_used < 1 || k_used > ctx->K) return SCG_EINVAL;
@@ -786,9 +799,14 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
         default: return SCG_ELIMIT;
     }
     if (grid <= 0) return grid == 0 ? SCG_EINVAL : grid;
-    if ((rc = scg_prof_push(ctx, 1, st, true))) return rc;
+    if ((rc = scg_prof_push(ctx, 1, st, true))) return rc < 0 ? rc : -rc;
+    return grid;
+}
+
+int scg_reduce_window(scg_ctx *ctx, int n_slabs, int k_used, float *dW, cudaStream_t st, bool overlap_prev) {
+    int rc;
     if ((rc = scg_prof_push(ctx, 2, st, false))) return rc;
-    if ((rc = reduce_slabs(ctx, grid, k_used * SCG_A * ctx->F, dW, st))) return rc;
+    if ((rc = reduce_slabs(ctx, n_slabs, k_used * SCG_A * ctx->F, dW, st, overlap_prev && !ctx->prof_on))) return rc;
     return scg_prof_push(ctx, 2, st, true);
 }
 
