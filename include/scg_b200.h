@@ -166,7 +166,8 @@ typedef struct scg_agent {
     float gamma, lambda, epsilon, option_bonus;
     int32_t option_timeout, max_episode_steps, cull, carry_valid;
     float alpha; int32_t window_steps, win_cap, win_len;
-    int32_t ring_len;                /* slabs of the open window whose option terminations are already in the example rings */
+    int32_t ev_cap, ev_len, ring_len; /* event history: capacity in steps (>= 2 * win_cap), steps recorded, steps already
+                                        appended to the example rings (ring_len <= ev_len; the open window is the last win_len) */
     int32_t gestation_successes, clf_steps; float clf_lr;   /* controller: promotion threshold, classifier fit */
     int32_t top_slots;               /* 0: options are chosen "first active initiation set"; n = ceil(K / 5): by the top-level
                                         SMDP learner whose weights are slots K .. K+n-1 of W / Wt / dW / cnt (K + n <= 16) */
@@ -188,8 +189,10 @@ typedef struct scg_agent {
     float *delta;                    /* [B] TD errors of this step */
     float *q_carry;                  /* [B] Q_o(s, a) of the pending (state, action), valid iff carry_valid */
     float *win_rec;                  /* [win_cap][B][8] step records of the open window */
-    uint8_t *win_ev;                 /* [win_cap][B] option-termination events of the open window (0 = none) */
-    float *win_top;                  /* [win_cap][B][8] top-level SMDP updates of the open window, valid where win_ev says
+    uint8_t *ev_hist;                /* [ev_cap][B] option-termination events, one byte per env-step (0 = none), kept until the
+                                        example-ring pass has consumed them (scg_agent_ring: at manage / when the history is full) */
+    float *ev_pos;                   /* [ev_cap][B][2] where the terminated option had started (written where ev_hist says so) */
+    float *win_top;                  /* [win_cap][B][8] top-level SMDP updates of the open window, valid where the event byte says
                                         "terminated": s0 (4), delta_top, option bits (top_slots > 0 only) */
     float *trace;                    /* [B][A][F], as of the last flush */
     /* per-option state (device) */
@@ -209,10 +212,12 @@ typedef struct scg_agent {
  * win_len reaches win_cap.  Clear carry_valid whenever state, action, option or weights are changed
  * from outside (scg_apply changes the weights: callers clear it after every apply). */
 int scg_agent_step(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
-/* Fold the open window into dW and the traces (no-op when win_len == 0); appends its examples first. */
+/* Fold the open window into dW and the traces (no-op when win_len == 0). */
 int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);
-/* Append the option-termination examples of the open window's not yet processed steps to the example rings
- * (oracle/agent.py step, item 6).  Deterministic: the examples of a step are appended in env order, steps in order,
+/* Append the option-termination examples of the recorded, not yet processed steps to the example rings
+ * (oracle/agent.py step, item 6).  The step kernel only leaves an event byte and a start position per termination; the
+ * rings are brought up to date here - by scg_agent_manage, when the event history is full, or on request - so the pass
+ * runs once per controller interval, not once per window.  Deterministic: the examples of a step are appended in env order, steps in order,
  * exactly the oracle's sequence, whatever the launch geometry; when more than `example_capacity` examples of one option
  * arrive, the last `example_capacity` survive.  Called by flush and manage; call it before reading the rings. */
 int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream);

@@ -39,7 +39,7 @@ class AgentStruct(C.Structure):
         ("option_timeout", C.c_int32), ("max_episode_steps", C.c_int32), ("cull", C.c_int32),
         ("carry_valid", C.c_int32),
         ("alpha", C.c_float), ("window_steps", C.c_int32), ("win_cap", C.c_int32), ("win_len", C.c_int32),
-        ("ring_len", C.c_int32), ("gestation_successes", C.c_int32), ("clf_steps", C.c_int32), ("clf_lr", C.c_float),
+        ("ev_cap", C.c_int32), ("ev_len", C.c_int32), ("ring_len", C.c_int32), ("gestation_successes", C.c_int32), ("clf_steps", C.c_int32), ("clf_lr", C.c_float),
         ("top_slots", C.c_int32), ("alpha_top", C.c_float), ("epsilon_top", C.c_float), ("init_horizon", C.c_int32),
         ("merge_overlap", C.c_float), ("goal_x", C.c_float), ("goal_y", C.c_float), ("reserved1", C.c_int32),
         ("x", C.c_void_p), ("y", C.c_void_p), ("vx", C.c_void_p), ("vy", C.c_void_p),
@@ -48,7 +48,7 @@ class AgentStruct(C.Structure):
         ("start_xy", C.c_void_p), ("start_vxy", C.c_void_p), ("opt_ret", C.c_void_p), ("opt_disc", C.c_void_p),
         ("ep_return", C.c_void_p), ("ep_count", C.c_void_p), ("last_return", C.c_void_p),
         ("reward", C.c_void_p), ("flags", C.c_void_p), ("delta", C.c_void_p), ("q_carry", C.c_void_p),
-        ("win_rec", C.c_void_p), ("win_ev", C.c_void_p), ("win_top", C.c_void_p), ("trace", C.c_void_p),
+        ("win_rec", C.c_void_p), ("ev_hist", C.c_void_p), ("ev_pos", C.c_void_p), ("win_top", C.c_void_p), ("trace", C.c_void_p),
         ("W", C.c_void_p), ("Wt", C.c_void_p), ("theta", C.c_void_p), ("dW", C.c_void_p),
         ("cnt", C.c_void_p), ("ctl", C.c_void_p),
         ("ex_xy", C.c_void_p), ("ex_label", C.c_void_p),

@@ -49,6 +49,7 @@ class AgentConfig:
     example_capacity: int = 4096
     clf_steps: int = 200
     clf_lr: float = 1.0
+    event_history: int = 64       # steps of option-termination events kept on the device between example-ring passes
     init_horizon: int = 1 << 30   # an example is positive iff the option hit a target within this many steps of its start
     merge_overlap: float = 0.0    # graph mode: an older option's initiation set becomes a target of the next option iff at
                                   # least this fraction of the promoted option's positive examples lies inside it (0: all)
@@ -100,7 +101,11 @@ class SkillChainAgent:
         self.last_return = torch.zeros(B, **f32)            # task return of each env's last finished episode
         self.q_carry = torch.zeros(B, **f32)
         self.win_rec = torch.zeros((self.win_cap, B, 8), **f32)
-        self.win_ev = torch.zeros((self.win_cap, max(B, 1)), dtype=torch.uint8, device=dev)
+        # option-termination events (one byte per env-step + the option's start position) wait here until the
+        # controller needs the example rings: one ring pass per manage() instead of one per window
+        self.ev_cap = max(int(cfg.event_history), 2 * self.win_cap)
+        self.ev_hist = torch.zeros((self.ev_cap, max(B, 1)), dtype=torch.uint8, device=dev)
+        self.ev_pos = torch.zeros((self.ev_cap, max(B, 1), 2), **f32)
         # top-level learner: s0 = (start_xy, start_vxy), discounted return and discount of the running option, and the
         # SMDP update records of the open window
         self.start_vxy = torch.zeros((B, 2), **f32)
@@ -267,7 +272,8 @@ class SkillChainAgent:
         g.gamma, g.lam, g.epsilon, g.option_bonus = cfg.gamma, cfg.lam, cfg.epsilon, cfg.option_bonus
         g.option_timeout, g.max_episode_steps, g.cull = cfg.option_timeout, cfg.max_episode_steps, int(cfg.cull)
         g.alpha, g.win_cap = cfg.alpha, self.win_cap
-        g.step = g.window_steps = g.win_len = g.carry_valid = g.ring_len = g.n_active = 0
+        g.step = g.window_steps = g.win_len = g.carry_valid = g.ring_len = g.ev_len = g.n_active = 0
+        g.ev_cap = self.ev_cap
         g.graph, g.gestation_successes = int(bool(cfg.graph)), int(cfg.gestation_successes)
         g.clf_steps, g.clf_lr = int(cfg.clf_steps), float(cfg.clf_lr)
         g.top_slots, g.alpha_top, g.epsilon_top = self.top_slots, float(cfg.alpha_top), float(cfg.epsilon_top)
@@ -278,7 +284,7 @@ class SkillChainAgent:
         g.x, g.y, g.vx, g.vy = (s[i].data_ptr() for i in range(4))
         g.x2, g.y2, g.vx2, g.vy2 = (s2[i].data_ptr() for i in range(4))
         for name in ("action", "option", "t_opt", "ep_steps", "start_xy", "ep_return", "reward", "flags", "delta",
-                     "q_carry", "win_rec", "win_ev", "ctl", "n_success", "n_fail", "n_success_global", "stats",
+                     "q_carry", "win_rec", "ev_hist", "ev_pos", "ctl", "n_success", "n_fail", "n_success_global", "stats",
                      "ep_count", "last_return", "start_vxy", "opt_ret", "opt_disc"):
             setattr(g, name, getattr(self, name).data_ptr())
         g.ex_xy, g.ex_label, g.ex_count = self._ex_xy.data_ptr(), self._ex_label.data_ptr(), self._ex_count.data_ptr()
@@ -548,6 +554,7 @@ class SkillChainAgent:
         """Write everything needed to resume this rank (option weights, classifiers, option graph, per-env state and
         traces, counters) to `path` (.npz).  The open window is folded in first."""
         self.flush()
+        self._ring()
         o, g = self.options, self._struct
         c = self.controller_state(sync=True)
         arrs = {k.lstrip("_"): getattr(self, k).cpu().numpy() for k in self._CKPT_TENSORS}
@@ -582,7 +589,7 @@ class SkillChainAgent:
         if len(z["meta"]) > 4:
             self._ctl.n_promotions, self._ctl.last_promotion_step = int(z["meta"][4]), int(z["meta"][5])
         self._push_ctl()
-        g.step, g.window_steps, g.win_len, g.ring_len = int(z["meta"][2]), int(z["meta"][3]), 0, 0
+        g.step, g.window_steps, g.win_len, g.ring_len, g.ev_len = int(z["meta"][2]), int(z["meta"][3]), 0, 0, 0
         o.window_steps = int(z["meta"][3])
         g.carry_valid = 0
 

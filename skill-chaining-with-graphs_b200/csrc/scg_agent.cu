@@ -40,6 +40,7 @@ struct StepArgs {
     int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
     float4 *rec;  // this step's slab of the window: [B][2]
     uint8_t *ev;  // this step's slab of the event bytes: [B]
+    float2 *pos;  // this step's slab of option start positions: [B]
     float *top;   // this step's slab of the top-level update records: [B][8] (top_slots > 0)
 };
 
@@ -246,11 +247,15 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                 const uint32_t meta = (uint32_t)a | ((uint32_t)o << 8) | (term ? SCG_META_ZERO_AFTER : 0u) | SCG_META_ACTIVE;
                 float4 *rec = args.rec + ((size_t)s * g.B + b) * 2;
                 rec[0] = make_float4(sx, sy, svx, svy);
-                // 6: example for option o's initiation classifier: the event byte and the option's start position go
-                // with the record; k_ring appends them to the ring in the oracle's order (step, then env)
-                rec[1] = make_float4(delta, __uint_as_float(meta), stx, sty);
+                rec[1] = make_float4(delta, __uint_as_float(meta), 0.f, 0.f);
+                // 6: example for option o's initiation classifier: an event byte per env-step and, at a termination, the
+                // option's start position go to the event history; k_ring appends them to the ring in the oracle's order
+                // (step, then env) when the controller next needs the rings
                 args.ev[(size_t)s * g.B + b] = term ? (uint8_t)(SCG_EV_TERM | ((hit && t_opt <= g.init_horizon) ? SCG_EV_HIT : 0) | o) : (uint8_t)0;
-                if (term) atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
+                if (term) {
+                    args.pos[(size_t)s * g.B + b] = make_float2(stx, sty);
+                    atomicAdd((hit ? g.n_success : g.n_fail) + o, 1);
+                }
                 // 7: env reset
                 if (reset) {
                     const uint4 rr = scg_draw(g.seed, env, step, SCG_STREAM_RESET);
@@ -431,14 +436,17 @@ static int check_agent(const scg_map_t *map, const scg_ctx_t *ctx, const scg_age
         return SCG_EINVAL;
     if (ag->B < 0 || ag->win_cap < 1 || ag->win_cap > SCG_WIN_MAX || ag->win_len < 0 || ag->win_len >= ag->win_cap)
         return SCG_EINVAL;
-    if (ag->n_active < 0 || ag->n_active > ag->K - 1 || !ag->ctl || !ag->win_ev) return SCG_EINVAL;
+    if (ag->n_active < 0 || ag->n_active > ag->K - 1 || !ag->ctl || !ag->ev_hist || !ag->ev_pos) return SCG_EINVAL;
+    if (ag->ev_cap < 2 * ag->win_cap || ag->ev_len < ag->win_len || ag->ev_len > ag->ev_cap || ag->ring_len < 0 ||
+        ag->ring_len > ag->ev_len)
+        return SCG_EINVAL;
     if (map->hdr.blob_bytes > 160 * 1024) return SCG_ELIMIT;
     return 0;
 }
 
 extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if (!ctx || !ag) return SCG_EINVAL;
-    if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; ag->ring_len = 0; return 0; }
+    if (ag->win_len <= 0 || ag->B <= 0) { ag->win_len = 0; return 0; }
     // option ids in the records are 0 .. n_active (the gestating slot); n_active is the host's lower bound of the
     // device's value: records of an option promoted since then are folded through the sweep's global-memory path
     const int k_used = std::min(ag->K, std::max(ag->n_active, 0) + 1);
@@ -447,13 +455,10 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     const int n_slabs = scg_launch_window(ctx, ag->B, ag->win_len, k_used, ag->win_rec, ag->trace, ag->gamma * ag->lambda,
                                           ag->dW, (cudaStream_t)stream);
     if (n_slabs <= 0) return n_slabs == 0 ? SCG_EINVAL : n_slabs;
-    // the window's option terminations -> example rings.  Independent of the slab reduction queued right behind it,
-    // which therefore starts under it (programmatic dependent launch)
-    const bool ring_due = ag->ring_len < ag->win_len;
-    if ((rc = scg_agent_ring(ctx, ag, stream))) return rc;
-    if ((rc = scg_reduce_window(ctx, n_slabs, k_used, ag->dW, (cudaStream_t)stream, ring_due))) return rc;
+    if ((rc = scg_reduce_window(ctx, n_slabs, k_used, ag->dW, (cudaStream_t)stream, false))) return rc;
     ag->win_len = 0;
-    ag->ring_len = 0;
+    // the event history must have room for the next full window: when it has not, bring the rings up to date now
+    if (ag->ev_len + ag->win_cap > ag->ev_cap && (rc = scg_agent_ring(ctx, ag, stream))) return rc;
     return 0;
 }
 
@@ -472,7 +477,8 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1) + ag->top_slots;   // + the top-level learner's slots
     args.w_bytes = args.k_stage * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
-    args.ev = ag->win_ev + (size_t)ag->win_len * ag->B;
+    args.ev = ag->ev_hist + (size_t)ag->ev_len * ag->B;
+    args.pos = reinterpret_cast<float2 *>(ag->ev_pos) + (size_t)ag->ev_len * ag->B;
     args.top = ag->win_top ? ag->win_top + (size_t)ag->win_len * ag->B * 8 : nullptr;
     args.n_steps = n;
     // weights go to shared memory when two CTAs per SM still fit next to the map, or one big CTA
@@ -493,6 +499,7 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     ag->step += n;
     ag->window_steps += n;
     ag->win_len += n;
+    ag->ev_len += n;
     ag->carry_valid = 1;
     if (ag->win_len >= ag->win_cap && !defer_flush) return scg_agent_flush(ctx, ag, stream);
     return 0;

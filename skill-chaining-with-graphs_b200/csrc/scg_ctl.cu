@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t ring_block_scan(uint32_t v, uint32_t *warp_s
 
 // CTA c owns the contiguous tiles [c * tiles_per_cta, ...) of the flat [step][env] event-byte array (n bytes, n % 4 == 0
 // after padding by the caller's layout: the array is read as aligned 32-bit words, `mis` leading bytes are skipped).
-__global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *__restrict__ ev, const float4 *__restrict__ rec,
+__global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *__restrict__ ev, const float2 *__restrict__ pos,
                                                   float *ex_xy, uint8_t *ex_label, long long *ex_count, uint32_t cap,
                                                   unsigned int *scratch, unsigned int target, int tiles_per_cta) {
     __shared__ uint32_t lst[RING_TILE];                 // this tile's events in flat order: option | hit << 4 | byte index << 8
@@ -73,8 +73,6 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
     __shared__ uint32_t slot0_s[SCG_MAX_OPTIONS];
     __shared__ uint32_t n_tile_ev;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // nothing queued behind this kernel by scg_agent_flush depends on it (the slab reduction): let it start now
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int mis = (int)(reinterpret_cast<uintptr_t>(ev) & 3);
     const uint32_t *evw = reinterpret_cast<const uint32_t *>(ev - mis);
     const long long nv = (long long)n + mis;            // bytes [mis, nv) of the aligned view are the events
@@ -158,9 +156,8 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
             if ((int)o < K && (unsigned long long)rank + cap >= tot_s[o]) {
                 const uint32_t slot = (uint32_t)(((unsigned long long)slot0_s[o] + rank) % cap);
                 const long long f = cta_lo + (long long)t * RING_TILE + (e >> 8) - mis;     // flat [step][env] index
-                const float4 r1 = __ldg(rec + (size_t)f * 2 + 1);
                 const size_t ei = (size_t)o * cap + slot;
-                *reinterpret_cast<float2 *>(ex_xy + 2 * ei) = make_float2(r1.z, r1.w);
+                *reinterpret_cast<float2 *>(ex_xy + 2 * ei) = __ldg(pos + f);
                 ex_label[ei] = (e & 16u) ? 1 : 0;
             }
         }
@@ -178,33 +175,36 @@ __global__ void __launch_bounds__(RING_NT) k_ring(int n, int K, const uint8_t *_
 
 extern "C" int scg_agent_ring(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
     if (!ctx || !ag) return SCG_EINVAL;
-    if (ag->ring_len < 0 || ag->ring_len > ag->win_len) return SCG_EINVAL;
-    const int T = ag->win_len - ag->ring_len;
-    if (T == 0 || ag->B <= 0) { ag->ring_len = ag->win_len; return 0; }
-    if (!ag->win_ev || !ag->win_rec || !ag->ex_xy || !ag->ex_label || !ag->ex_count || ag->example_capacity == 0)
-        return SCG_EINVAL;
+    if (ag->ring_len < 0 || ag->ring_len > ag->ev_len || ag->ev_len > ag->ev_cap) return SCG_EINVAL;
+    const int T = ag->ev_len - ag->ring_len;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!ctx->d_ring) {
-        SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_ring, RING_WORDS * sizeof(unsigned int)));
-        SCG_CUDA_OK(cudaMemsetAsync(ctx->d_ring, 0, RING_WORDS * sizeof(unsigned int), st));
-        ctx->ring_gen = 0;
+    if (T > 0 && ag->B > 0) {
+        if (!ag->ev_hist || !ag->ev_pos || !ag->ex_xy || !ag->ex_label || !ag->ex_count || ag->example_capacity == 0)
+            return SCG_EINVAL;
+        if (!ctx->d_ring) {
+            SCG_CUDA_OK(cudaMalloc((void **)&ctx->d_ring, RING_WORDS * sizeof(unsigned int)));
+            SCG_CUDA_OK(cudaMemsetAsync(ctx->d_ring, 0, RING_WORDS * sizeof(unsigned int), st));
+            ctx->ring_gen = 0;
+        }
+        const long long n = (long long)T * ag->B;
+        if (n > 0x7fffffffll) return SCG_ELIMIT;
+        const long long n_tiles = (n + 3 + RING_TILE - 1) / RING_TILE;              // (+3: the aligned view may start up to 3 bytes early)
+        const int tiles_per_cta = (int)((n_tiles + RING_CTAS - 1) / RING_CTAS);
+        const int grid = (int)std::max<long long>(1, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
+        // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
+        ctx->ring_gen += (unsigned int)grid;
+        const size_t off = (size_t)ag->ring_len * ag->B;
+        int rcp;
+        if ((rcp = scg_prof_push(ctx, 4, st, false))) return rcp;
+        k_ring<<<grid, RING_NT, 0, st>>>((int)n, ag->K, ag->ev_hist + off, reinterpret_cast<const float2 *>(ag->ev_pos) + off,
+                                         ag->ex_xy, ag->ex_label, reinterpret_cast<long long *>(ag->ex_count),
+                                         ag->example_capacity, ctx->d_ring, ctx->ring_gen, tiles_per_cta);
+        SCG_LAUNCH_CHECK();
+        if ((rcp = scg_prof_push(ctx, 4, st, true))) return rcp;
     }
-    const long long n = (long long)T * ag->B;
-    if (n > 0x7fffffffll) return SCG_ELIMIT;
-    const long long n_tiles = (n + 3 + RING_TILE - 1) / RING_TILE;              // (+3: the aligned view may start up to 3 bytes early)
-    const int tiles_per_cta = (int)((n_tiles + RING_CTAS - 1) / RING_CTAS);
-    const int grid = (int)std::max<long long>(1, (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
-    // the barrier counter counts arrivals of all launches so far: this launch is complete at (sum of earlier grids) + grid
-    ctx->ring_gen += (unsigned int)grid;
-    const size_t off = (size_t)ag->ring_len * ag->B;
-    int rcp;
-    if ((rcp = scg_prof_push(ctx, 4, st, false))) return rcp;
-    k_ring<<<grid, RING_NT, 0, st>>>((int)n, ag->K, ag->win_ev + off, reinterpret_cast<const float4 *>(ag->win_rec) + off * 2,
-                                     ag->ex_xy, ag->ex_label, reinterpret_cast<long long *>(ag->ex_count),
-                                     ag->example_capacity, ctx->d_ring, ctx->ring_gen, tiles_per_cta);
-    SCG_LAUNCH_CHECK();
-    if ((rcp = scg_prof_push(ctx, 4, st, true))) return rcp;
-    ag->ring_len = ag->win_len;
+    ag->ring_len = ag->ev_len;
+    // between windows the consumed history is recycled (inside a window its tail still feeds the top-level learner)
+    if (ag->win_len == 0) ag->ev_len = ag->ring_len = 0;
     return 0;
 }
 
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top(int n, int K, int top_slots, con
 // fold the open window's top-level update records (slabs 0 .. win_len-1) into dW / cnt
 int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st) {
     if (ag->top_slots <= 0 || ag->win_len <= 0 || ag->B <= 0) return 0;
-    if (!ag->win_top || !ag->win_ev) return SCG_EINVAL;
+    if (!ag->win_top || !ag->ev_hist || ag->ev_len < ag->win_len) return SCG_EINVAL;
     const long long n = (long long)ag->win_len * ag->B;
     if (n > 0x7fffffffll) return SCG_ELIMIT;
     const int grid = (int)std::max<long long>(1, std::min<long long>(TOP_CTAS, (n + 4095) / 4096));
@@ -314,7 +314,7 @@ int scg_launch_top(scg_ctx *ctx, const scg_agent_t *ag, cudaStream_t st) {
         static ScgKernelCfg cfgc = {};                                                                              \
         int per_sm = 0;                                                                                             \
         rc = scg_configure(cfgc, k_top<N>, TOP_NT, smem, &per_sm);                                                  \
-        if (!rc) k_top<N><<<grid, TOP_NT, smem, st>>>((int)n, ag->K, ag->top_slots, ag->win_ev, top, ag->dW, ag->cnt); \
+        if (!rc) k_top<N><<<grid, TOP_NT, smem, st>>>((int)n, ag->K, ag->top_slots, ag->ev_hist + (size_t)(ag->ev_len - ag->win_len) * ag->B, top, ag->dW, ag->cnt); \
     }
     switch (ctx->order) {
         case 1: LAUNCH_TOP(2); break;
