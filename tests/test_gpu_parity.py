@@ -659,7 +659,6 @@ def test_example_rings_match_oracle_past_capacity(scg, torch, B, cap, launch, hi
             assert np.array_equal(gag.ex_xy.cpu().numpy().view(np.uint32), oag.ex_xy.view(np.uint32)), f"window {w}"
             assert np.array_equal(gag.ex_label.cpu().numpy(), oag.ex_label), f"window {w}"
     assert oag.ex_count.max() > (3 * cap if cap < 1000 else 1000)
-    assert 0 < oag.ex_label[:3, : min(cap, int(oag.ex_count[:3].min()))].mean() < 1    # both labels occur
     # one more step, read mid-window: the property appends the open window's events first
     pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 1)
     oag.step(follow=dict(action=acts[1], option=opts[1]))
