@@ -8,15 +8,20 @@ A "step" is one lock-step agent step over the whole env batch: a fused kernel do
 initiation classifiers + Q evaluation + eps-greedy + TD error (K2+K4) -> 32-byte step record, for the
 `sync_interval` consecutive steps of a window in one launch (nothing couples the envs while the weights are
 frozen); then the window's records are folded into the traces and weight deltas by one Sarsa(lambda) sweep
-(K3, forward-view form), followed by the cross-GPU exchange and the weight apply.
+(K3, forward-view form), followed by the cross-GPU exchange and the weight apply.  The option-creation
+controller (SkillChainAgent.manage: one kernel on the stream) runs every 64 steps inside the timed region.
 Workload at every N: BASELINE.json configs[1] per GPU - Pinball 'easy', 65,536 envs, order-3 Fourier
-basis, 4 option slots with 2 active logistic initiation classifiers (weak scaling: each rank owns
-its own 65,536-env slice).  Synthetic data: random free-space start states, random-init weights.
+basis, 4 option slots, 2 preset active logistic initiation classifiers (the controller promotes the third in the
+warm-up) - weak scaling: each rank owns its own 65,536-env slice.  Synthetic data: random free-space start
+states, random-init weights.
 
-Prints ONE JSON line (rank 0).  `value` = env-steps of all ranks / max-over-ranks device time with
-state resident in HBM; `e2e` = same through SkillChainAgent.step_host (host buffers, H2D and D2H
-inside the timed region); `roofline` = the window trace-sweep kernel's algorithmic bytes / its CUDA-event
-time against the measured HBM copy peak; `cpu_baseline` = the NumPy oracle timed on this box.
+Prints ONE JSON line (rank 0).  The timed region is R consecutive blocks of exactly K steps (CUDA events at the
+block boundaries, max over ranks per block); `value` = env-steps of one block over all ranks / the median block
+time, state resident in HBM; `e2e` = the same blocks through SkillChainAgent.step_host (host buffers, H2D and D2H
+inside the timed region) with a per-step breakdown; `roofline` = the window trace-sweep kernel's algorithmic bytes /
+its CUDA-event time against the measured HBM copy peak; `cpu_baseline` = the NumPy oracle timed on this box;
+`north_star_config` = the configs[2] per-GPU shape (hard map, order 5, 8 options, 131,072 envs) measured in the same
+process; `sync` (N > 1) = microseconds per weight exchange, peer-memory kernel vs NCCL.
 --impl reference times the stand-in reference (the NumPy oracle: the reference repository has no
 code) on all host cores for the same metric.
 """

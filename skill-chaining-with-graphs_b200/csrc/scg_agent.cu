@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
         const int b = valid ? tile * 32 + lane : g.B - 1;
         const uint32_t env = g.env_offset + (uint32_t)b;
         float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
-        int a = g.action[b], o = g.option[b];
+        // (ids poked in from outside are clamped: an out-of-range option or action must not index past the tables)
+        int a = min(max(g.action[b], 0), SCG_A - 1), o = min(max(g.option[b], 0), g.K - 1);
         int t_opt = g.t_opt[b], ep = g.ep_steps[b];
         float ret = g.ep_return[b], qc = PAIR ? 0.f : g.q_carry[b];
         float stx = g.start_xy[2 * b], sty = g.start_xy[2 * b + 1];
