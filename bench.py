@@ -50,6 +50,10 @@ def workload(args):
                 option_timeout=250, max_episode_steps=2000, graph=bool(getattr(args, "graph", False)))
 
 
+def wl_episode_steps(args):
+    return workload(args)["max_episode_steps"]
+
+
 def gpu_only(args):
     """AgentConfig fields that only the GPU backend has."""
     return dict(sync_backend=args.sync_backend, window=args.window)
@@ -78,6 +82,7 @@ def config_json(args, n_gpus):
         "options": args.options, "sync_interval": args.sync_interval, "map": args.map,
         "parallelism": f"env-sharded x{n_gpus}, sum of (dW, cnt) over ranks every sync interval "
                        f"({'one NVLink peer-memory exchange+apply kernel' if getattr(args, 'sync_backend', 'p2p') == 'p2p' else 'NCCL all-reduce'})",
+        "episode_phase": "ep_steps uniformly random in [0, max_episode_steps) at the start (steady state of a long run)",
         "l2": f"traces {args.batch * 5 * F * 4 / 2**20:.0f} MiB per GPU > 126 MiB L2, swept once per {T}-step window "
               "(inputs larger than L2; no explicit flush)",
     }
@@ -148,6 +153,7 @@ def _cpu_worker(wl, batch, steps, seed, q, warmup=1):
     setup_classifiers(ag.options.theta)
     ag.active[:N_PRESET_ACTIVE] = True
     ag.n_active = N_PRESET_ACTIVE
+    ag.ep_steps[:] = rng.integers(0, wl["max_episode_steps"], batch).astype(np.int32)      # random episode phases, as on the GPU
     ag.parents[1], ag.parents[2] = (np.uint32(1 | (1 << 31)), np.uint32(3 | (1 << 31))) if wl.get("graph") else (1, 2)
     for _ in range(max(warmup, 1)):             # untimed warm-up
         ag.step()
@@ -238,6 +244,9 @@ def make_agent(scg, torch, args, rank, world):
     setup_classifiers(theta)
     ag.options.theta.copy_(torch.as_tensor(theta))
     ag.active_mask, ag.n_active = (1 << N_PRESET_ACTIVE) - 1, N_PRESET_ACTIVE
+    # steady state of a long run: the envs are at uniformly random phases of their episodes (all of them starting
+    # at step 0 would time out together 2000 steps later and restart from the one start state in lock-step)
+    ag.ep_steps.copy_(torch.as_tensor(rng.integers(0, wl_episode_steps(args), B).astype(np.int32)))
     GOAL = 1 << 31
     ag.parents_host[1], ag.parents_host[2] = (1 | GOAL, 3 | GOAL) if args.graph else (1, 2)
     ag._push_parents()
@@ -481,7 +490,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_json(args, world),
             "timed_region": {"blocks": len(m["blocks"]), "steps_per_block": args.steps, "block_ms_median": m["ms_block"],
-                             "block_ms_min": min(m["blocks"]), "block_ms_max": max(m["blocks"]),
+                             "block_ms_min": min(m["blocks"]), "block_ms_max": max(m["blocks"]), "blocks_ms": m["blocks"],
                              "warmup_steps_run": n_warm,
                              "note": "value = steps of one block / median block time; blocks are consecutive slices of the "
                                      "steady state (windows, syncs and the controller cadence run on across them), each "
