@@ -299,6 +299,13 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise scg.ScgError("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    if world > 1 and args.pin_cores:
+        # one process per GPU: give each rank its own slice of the host cores (its launch thread, its copies' staging and
+        # the NCCL helper threads then do not migrate over the other ranks' cores)
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 1:
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
@@ -556,6 +563,7 @@ def main():
     ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--window", type=int, default=0, help="steps per trace sweep (0 = min(sync interval, 8))")
     ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps (0 = enough for ~1024 steps, at least 3)")
+    ap.add_argument("--pin-cores", type=int, default=0, help="N > 1: pin each rank to its own slice of the host cores")
     ap.add_argument("--no-north-star", action="store_true", help="skip the extra configs[2]-shape measurement")
     ap.add_argument("--graph", action="store_true", help="option-graph variant (configs[4]): an option's targets are the "
                     "initiation sets of ALL earlier options and the goal, so chains merge")
