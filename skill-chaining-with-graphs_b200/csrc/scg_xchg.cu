@@ -80,19 +80,34 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
     __syncthreads();
     if (s_timeout) return;                            // no apply, dW of this slice kept
     // 4. sum in rank order, apply
-    float v = 0.f;
-    for (int r = 0; r < a.world; ++r) {
-        if (r == a.rank) { v += my; continue; }
-        const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
-        v += ld_sys_f32(prow + i);
+    // every peer's copy of this slice: all the NVLink loads are issued before the first one is consumed (one round trip,
+    // not one per peer), then added in rank order
+    float pv[XCHG_MAX_WORLD], pc[XCHG_MAX_WORLD], ps[XCHG_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
+        pv[r] = 0.f; pc[r] = 0.f; ps[r] = 0.f;
+        if (r < a.world && r != a.rank) {
+            const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+            pv[r] = ld_sys_f32(prow + i);
+            if (i < a.K) {
+                pc[r] = ld_sys_f32(prow + XCHG_SLICE + i);
+                if (c == 0) ps[r] = ld_sys_f32(prow + XCHG_SLICE + 16 + i);
+            }
+        }
     }
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r)
+        if (r < a.world) v += (r == a.rank) ? my : pv[r];
     if (i < a.K) {
         int tot = 0;
         long long succ = 0;   // the counters are 32-bit and wrap: summed as unsigned
-        for (int r = 0; r < a.world; ++r) {
-            const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
-            tot += __float_as_int(r == a.rank ? xrow[XCHG_SLICE + i] : ld_sys_f32(prow + XCHG_SLICE + i));
-            if (c == 0) succ += (unsigned int)__float_as_int(r == a.rank ? xrow[XCHG_SLICE + 16 + i] : ld_sys_f32(prow + XCHG_SLICE + 16 + i));
+#pragma unroll
+        for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
+            if (r < a.world) {
+                tot += __float_as_int(r == a.rank ? xrow[XCHG_SLICE + i] : pc[r]);
+                if (c == 0) succ += (unsigned int)__float_as_int(r == a.rank ? xrow[XCHG_SLICE + 16 + i] : ps[r]);
+            }
         }
         s_cnt[i] = tot;
         // every rank publishes the same global success count, so the option-creation controller takes the same
