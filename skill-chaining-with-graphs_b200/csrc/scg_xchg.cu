@@ -44,9 +44,10 @@ struct SyncArgs {
 };
 
 template <int N1>
-__global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ SyncArgs a) {
+__global__ void __launch_bounds__(XCHG_SLICE, 8) k_sync(const __grid_constant__ SyncArgs a) {
     constexpr int F = N1 * N1 * N1 * N1;
     __shared__ int s_cnt[SCG_MAX_OPTIONS];
+    __shared__ float s_hdr[XCHG_MAX_WORLD * XCHG_HDR];
     __shared__ int s_timeout;
     if (threadIdx.x == 0) s_timeout = 0;
     const int c = blockIdx.x, i = threadIdx.x, j = c * XCHG_SLICE + i;
@@ -80,34 +81,37 @@ __global__ void __launch_bounds__(XCHG_SLICE) k_sync(const __grid_constant__ Syn
     __syncthreads();
     if (s_timeout) return;                            // no apply, dW of this slice kept
     // 4. sum in rank order, apply
-    // every peer's copy of this slice: all the NVLink loads are issued before the first one is consumed (one round trip,
-    // not one per peer), then added in rank order
-    float pv[XCHG_MAX_WORLD], pc[XCHG_MAX_WORLD], ps[XCHG_MAX_WORLD];
-#pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
-        pv[r] = 0.f; pc[r] = 0.f; ps[r] = 0.f;
-        if (r < a.world && r != a.rank) {
-            const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
-            pv[r] = ld_sys_f32(prow + i);
-            if (i < a.K) {
-                pc[r] = ld_sys_f32(prow + XCHG_SLICE + i);
-                if (c == 0) ps[r] = ld_sys_f32(prow + XCHG_SLICE + 16 + i);
-            }
-        }
+    // every peer's copy of this slice: the NVLink loads of (up to) eight peers are issued before the first one is
+    // consumed - one round trip per sync on an 8-GPU box, not one per peer - then added in rank order.  The 32-word
+    // headers (update counts, success counters) are fetched by all threads together into shared memory.
+    for (int h = i; h < a.world * XCHG_HDR; h += XCHG_SLICE) {
+        const int r = h / XCHG_HDR, wd = h - r * XCHG_HDR;
+        const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+        s_hdr[h] = (r == a.rank) ? xrow[XCHG_SLICE + wd] : ld_sys_f32(prow + XCHG_SLICE + wd);
     }
     float v = 0.f;
+    for (int r0 = 0; r0 < a.world; r0 += 8) {
+        float pv[8];
 #pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r)
-        if (r < a.world) v += (r == a.rank) ? my : pv[r];
+        for (int q = 0; q < 8; ++q) {
+            const int r = r0 + q;
+            pv[q] = 0.f;
+            if (r < a.world && r != a.rank) {
+                const float *prow = reinterpret_cast<const float *>(a.peer[r] + a.flag_bytes) + ((size_t)buf * a.slices + c) * XCHG_ROW;
+                pv[q] = ld_sys_f32(prow + i);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r0 + q < a.world) v += (r0 + q == a.rank) ? my : pv[q];
+    }
+    __syncthreads();
     if (i < a.K) {
         int tot = 0;
         long long succ = 0;   // the counters are 32-bit and wrap: summed as unsigned
-#pragma unroll
-        for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
-            if (r < a.world) {
-                tot += __float_as_int(r == a.rank ? xrow[XCHG_SLICE + i] : pc[r]);
-                if (c == 0) succ += (unsigned int)__float_as_int(r == a.rank ? xrow[XCHG_SLICE + 16 + i] : ps[r]);
-            }
+        for (int r = 0; r < a.world; ++r) {
+            tot += __float_as_int(s_hdr[r * XCHG_HDR + i]);
+            if (c == 0) succ += (unsigned int)__float_as_int(s_hdr[r * XCHG_HDR + 16 + i]);
         }
         s_cnt[i] = tot;
         // every rank publishes the same global success count, so the option-creation controller takes the same
