@@ -107,8 +107,12 @@ int scg_td_error(int order, int K, int B, const float *x, const float *y, const 
  * trace is [B][A][F]; dW [K][A][F] and cnt [K] accumulate over the sync window. */
 int scg_ctx_create(int order, int K, scg_ctx_t **out);
 int scg_ctx_destroy(scg_ctx_t *ctx);
-/* on != 0: the per-CTA dW slabs are summed in a fixed order (no floating-point atomics), so a run is reproducible bit
- * for bit; off (default): one atomic per address per slice, ~1 us per step faster at configs[1]. */
+/* on != 0: reproducible runs.  The per-CTA dW slabs are summed in a fixed order (no floating-point atomics) and
+ * scg_agent_manage waits for its kernel, so that the host sizes the following launches with exact knowledge of the
+ * controller state; together with the deterministic example rings (scg_agent_ring) weights, traces, rings and classifiers
+ * then reproduce bit for bit for the same inputs.  Not covered: the top-level learner's window update (k_top adds with
+ * atomics) and the double-precision sum of finished returns in `stats` (integer-valued rewards: exact in practice).
+ * off (default): one atomic per address per slice, ~1 us per step faster at configs[1]. */
 int scg_ctx_set_deterministic(scg_ctx_t *ctx, int on);
 int scg_sarsa_update(scg_ctx_t *ctx, int B, const float *x, const float *y, const float *vx,
                      const float *vy, const int *a, const int *option, const float *delta,
