@@ -357,7 +357,7 @@ def run_ours(args):
                     ctl=ag.controller_state(sync=True))
 
     n_warm = max(args.warmup, 16)          # at least two windows, so the preset gestating option has qualified by the end
-    n_blocks = args.blocks or max(3, -(-1024 // max(args.steps, 1)))
+    n_blocks = args.blocks or max(5, -(-1024 // max(args.steps, 1)))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sync-backend", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--window", type=int, default=0, help="steps per trace sweep (0 = min(sync interval, 8))")
-    ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps (0 = enough for ~1024 steps, at least 3)")
+    ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps (0 = enough for ~1024 steps, at least 5)")
     ap.add_argument("--pin-cores", type=int, default=0, help="N > 1: pin each rank to its own slice of the host cores")
     ap.add_argument("--no-north-star", action="store_true", help="skip the extra configs[2]-shape measurement")
     ap.add_argument("--graph", action="store_true", help="option-graph variant (configs[4]): an option's targets are the "
