@@ -1517,6 +1517,52 @@ def test_empty_batch_and_bad_arguments(scg, torch):
     assert lib.scg_xchg_create(o.ctx, 3, 2, C.byref(C.c_void_p())) == -1
 
 
+@pytest.mark.parametrize("B,K,order,top,window,hist", [(1, 1, 1, True, 1, 1), (33, 1, 2, False, 3, 4), (70, 2, 3, True, 8, 16),
+                                                       (257, 13, 2, True, 5, 64), (64, 16, 1, False, 2, 64), (5, 3, 4, True, 7, 14)])
+def test_controller_and_top_level_edge_shapes_match_oracle(scg, torch, B, K, order, top, window, hist):
+    """Edge shapes of the round-2 machinery against the oracle: one env, one option slot (nothing can ever be promoted),
+    the largest slot counts (13 options + 3 top-level slots = 16; 16 options without), windows of one step, an event
+    history of the minimum size, more manage() calls than promotions.  Ten followed steps + controller calls; states and
+    counters bit for bit, TD errors / weights / classifiers element-wise."""
+    from oracle_replay import activate, default_theta
+    kw = dict(sync_interval=window, option_timeout=3, epsilon=0.4, alpha=2e-3, max_episode_steps=6, gestation_successes=1,
+              clf_steps=20, clf_lr=1.0, top_level=top, alpha_top=1e-3, epsilon_top=0.3, example_capacity=16)
+    oag, gag = _paired_agents(scg, torch, B, order, K, "easy", 61, window=window, event_history=hist, **kw)
+    if top:
+        oag.opt_s0 = oag.env.state.copy()
+    tx, ty, tr = oag.map.target
+    S = oag.env.state.copy()
+    S[::2, 0], S[::2, 1], S[::2, 2], S[::2, 3] = tx - 0.03, ty, 1.0, 0.0        # every other env flies into the goal
+    oag.env.reset(states=S)
+    oag.start_xy = oag.env.state[:, :2].copy()
+    oag.opt_s0 = oag.env.state.copy()
+    gag.s.copy_(torch.as_tensor(S.T.copy()))
+    gag.start_xy.copy_(torch.as_tensor(S[:, :2].copy()))
+    gag.start_vxy.copy_(torch.as_tensor(S[:, 2:].copy()))
+    gag.invalidate()
+    n_prom = 0
+    for t in range(10):
+        pre, dl, acts, opts, term = _gpu_run_window(gag, torch, 1)
+        assert np.array_equal(oag.env.state.view(np.uint32), pre[0].view(np.uint32)), f"step {t}: pre-step state"
+        out = oag.step(follow=dict(action=acts[1], option=opts[1]))
+        assert np.array_equal(out["term"], term[0]), f"step {t}: termination flags"
+        assert_close(dl[0], out["delta"], what=f"step {t}: TD error")
+        if t % 3 == 2:
+            op, gp = oag.manage(), gag.manage(wait=True)
+            assert op == gp, f"step {t}: promotion decision"
+            n_prom += int(op)
+            c = gag.controller_state()
+            assert c["n_active"] == oag.n_active and c["parents"] == [int(v) for v in oag.parents]
+            assert_close(gag.options.theta.cpu().numpy(), oag.options.theta, what=f"step {t}: classifiers")
+    assert np.array_equal(gag.state.cpu().numpy().view(np.uint32), oag.env.state.view(np.uint32))
+    assert np.array_equal(gag.ex_count.cpu().numpy(), oag.ex_count)
+    assert np.array_equal(gag.ex_xy.cpu().numpy().view(np.uint32), oag.ex_xy.view(np.uint32))
+    assert np.array_equal(gag.n_success.cpu().numpy(), oag.n_success) and np.array_equal(gag.ep_count.cpu().numpy(), oag.episodes)
+    assert_close(gag.options.W.cpu().numpy(), oag.options.W, what="weights (all slots)")
+    assert_close(gag.options.trace.cpu().numpy(), oag.options.trace, what="traces")
+    assert n_prom == (0 if K == 1 else min(K - 1, 3)) or B < 8
+
+
 def test_full_size_order5_hard_window_and_sharding(scg, torch):
     """configs[2] per-GPU shape (hard map, 131,072 envs, order 5, 8 option slots): 8 steps as one window == as two
     windows of 4, and the two half-batches reproduce the whole batch (states bit-identical, dW to rounding)."""
