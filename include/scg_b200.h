@@ -283,6 +283,13 @@ int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag,
                         const float *h_state_soa, const int *h_action, float *h_state2_soa,
                         float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
 
+/* HOST-buffer variant of scg_agent_run for a caller that only needs the state every n_steps steps: state and action go
+ * host->device once, the n_steps steps (with the syncs that fall due) run device-resident inside the library, and next
+ * state, last reward / flags / TD error and next action come back once; waits for the copies. */
+int scg_agent_run_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, const float *h_state_soa,
+                       const int *h_action, int n_steps, int sync_interval, scg_xchg_t *xchg, float *h_state2_soa,
+                       float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
+
 /* Per-kernel device timing of the agent pipeline with CUDA events on the launch stream.
  * scg_profile_begin arms it (up to max_events kernel launches of the kinds in kind_mask are recorded);
  * scg_profile_end waits for the recorded events and returns, per kind, the summed milliseconds and the

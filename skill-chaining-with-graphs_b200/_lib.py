@@ -107,6 +107,7 @@ _SIGS = {
     "scg_xchg_sync": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "scg_xchg_sync_top": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int, _P, _P, _P]),
     "scg_agent_step_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct)] + [_P] * 8),
+    "scg_agent_run_host": (C.c_int, [_P, _P, C.POINTER(AgentStruct), _P, _P, C.c_int, C.c_int, _P] + [_P] * 6),
     "scg_profile_begin": (C.c_int, [_P, C.c_int, C.c_int]),
     "scg_profile_end": (C.c_int, [_P, _P, _P]),
 }

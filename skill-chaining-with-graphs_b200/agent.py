@@ -421,13 +421,22 @@ class SkillChainAgent:
         else:
             hn["a"][...] = action
             src_a = h["a"]
-        self.s.copy_(src_s, non_blocking=True)
-        self.action.copy_(src_a, non_blocking=True)
-        self.invalidate()
-        self.run(n_steps)
-        h["s2"].copy_(self.s, non_blocking=True)
-        h["out"].copy_(self._out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if world_size(self.pg) == 1 or self._xchg is not None:
+            # the whole call stays inside the library: copies in, n_steps steps with their syncs, copies out
+            g = self._sync_struct()
+            out = h["out"]
+            check(self.lib.scg_agent_run_host(self.map.handle, self.options.ctx, C.byref(g), ptr(src_s), ptr(src_a),
+                                              int(n_steps), int(self.cfg.sync_interval), self._xchg, ptr(h["s2"]),
+                                              ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), _lib.current_stream()))
+            self.options.window_steps = int(g.window_steps)
+        else:
+            self.s.copy_(src_s, non_blocking=True)
+            self.action.copy_(src_a, non_blocking=True)
+            self.invalidate()
+            self.run(n_steps)
+            h["s2"].copy_(self.s, non_blocking=True)
+            h["out"].copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return hn["s2"], hn["a2"], hn["r"], hn["f"], hn["d"]
 
     HOST_H2D_BYTES_PER_ENV = 20      # state 16 + action 4

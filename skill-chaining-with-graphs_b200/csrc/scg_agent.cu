@@ -594,6 +594,40 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_age
     return 0;
 }
 
+// n_steps steps for a caller that only needs the state every n_steps steps: one host->device copy of state and action,
+// the device-resident loop (windows, syncs, exchange), one device->host copy of the results; the loop stays in the library
+extern "C" int scg_agent_run_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, const float *h_state_soa,
+                                  const int *h_action, int n_steps, int sync_interval, scg_xchg_t *xchg,
+                                  float *h_state2_soa, float *h_reward, int *h_flags, int *h_action2, float *h_delta,
+                                  void *stream) {
+    if (!map || !ctx || !ag || !h_state_soa || !h_action || !h_state2_soa || !h_reward || !h_flags || !h_action2 ||
+        !h_delta || n_steps < 0)
+        return SCG_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)ag->B * sizeof(float);
+    int rc;
+    {
+        void *dst[4] = {ag->x, ag->y, ag->vx, ag->vy};
+        const void *src[4] = {h_state_soa, h_state_soa + ag->B, h_state_soa + 2 * (size_t)ag->B, h_state_soa + 3 * (size_t)ag->B};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyHostToDevice, st))) return rc;
+    }
+    SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
+    ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
+    if ((rc = scg_agent_run(map, ctx, ag, n_steps, sync_interval, xchg, stream))) return rc;
+    {
+        void *dst[4] = {h_state2_soa, h_state2_soa + ag->B, h_state2_soa + 2 * (size_t)ag->B, h_state2_soa + 3 * (size_t)ag->B};
+        const void *src[4] = {ag->x, ag->y, ag->vx, ag->vy};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+    }
+    {
+        void *dst[4] = {h_reward, h_flags, h_action2, h_delta};
+        const void *src[4] = {ag->reward, ag->flags, ag->action, ag->delta};
+        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+    }
+    SCG_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // ---- per-kernel timing ---------------------------------------------------------------------------------
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end) {
     if (!ctx->prof_on || !((ctx->prof_mask >> kind) & 1)) return 0;
