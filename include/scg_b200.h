@@ -88,8 +88,11 @@ int scg_step_host(scg_map_t *map, int B, float *state_soa /* HOST [4][B] in/out 
 
 /* ---- K2: Fourier features, Q evaluation, action selection, TD error ------------------------
  * mirrors oracle/fourier.py FourierBasis.features, oracle/option.py OptionSet.q / act / td_error.
- * W is [K][A][F]; Wt is the packed copy [F][K][8] (feature-major, 5 actions + 3 pad per option) made
- * by scg_pack_weights (or scg_apply). */
+ * W is [K][A][F]; Wt is the packed copy the kernels read, made by scg_pack_weights (and kept current by scg_apply /
+ * scg_xchg_sync): [K][scg_packed_slot_floats(order)] fp32, a slot holding its features in pairs of 12 floats
+ * (w0a w1a w2a w3a | w0b w1b w2b w3b | w4a w4b 0 0) - the operands of the two-wide FMAs, 1.5 16-byte loads per
+ * feature - padded so that consecutive slots start 16 bytes apart modulo 128 (shared-memory banks). */
+int scg_packed_slot_floats(int order);
 int scg_features(int order, int B, const float *x, const float *y, const float *vx, const float *vy,
                  float *phi /* [B][F] */, void *stream);
 int scg_pack_weights(int order, int K, const float *W, float *Wt, void *stream);

@@ -74,6 +74,7 @@ _SIGS = {
     "scg_reset": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, _P]),
     "scg_step_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     "scg_features": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "scg_packed_slot_floats": (C.c_int, [C.c_int]),
     "scg_pack_weights": (C.c_int, [C.c_int, C.c_int, _P, _P, _P]),
     "scg_q_eval": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "scg_select": (C.c_int, [C.c_int, _P, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P]),

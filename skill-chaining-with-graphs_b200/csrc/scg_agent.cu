@@ -44,9 +44,10 @@ struct StepArgs {
     float *top;   // this step's slab of the top-level update records: [B][8] (top_slots > 0)
 };
 
-// bulk-TMA staging of up to two global blocks into shared memory behind one mbarrier
-__device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, int bytes0, unsigned char *dst1,
-                                       const void *src1, int bytes1, unsigned long long *bar) {
+// bulk-TMA staging of up to three global blocks into shared memory behind one mbarrier
+__device__ __forceinline__ void stage3(unsigned char *dst0, const void *src0, int bytes0, unsigned char *dst1,
+                                       const void *src1, int bytes1, unsigned char *dst2, const void *src2, int bytes2,
+                                       unsigned long long *bar) {
     uint32_t bar_a = smem_u32(bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
@@ -54,7 +55,8 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes0 + bytes1)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                     "r"(bytes0 + bytes1 + bytes2)
                      : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(dst0)),
@@ -64,6 +66,11 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(dst1)),
                          "l"(src1), "r"(bytes1), "r"(bar_a)
+                         : "memory");
+        if (bytes2 > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(dst2)),
+                         "l"(src2), "r"(bytes2), "r"(bar_a)
                          : "memory");
     }
     uint32_t ok = 0;
@@ -83,8 +90,9 @@ __device__ __forceinline__ void stage2(unsigned char *dst0, const void *src0, in
 // phasors and weight-table slot (valid on the lanes of mask); q receives the 5 values on those lanes.
 template <int N1, bool SMEMW>
 __device__ __forceinline__ void warp_compact_q(unsigned mask, bool in_mask, int lane, const float2 z[4], int slot_id,
-                                               const float *Wt_staged, int Kw, int k_opt, int K, const float *Wt_global,
-                                               int Kall, float q[SCG_A]) {
+                                               const float *Wt_staged, int k_opt, int K, const float *Wt_global,
+                                               float q[SCG_A]) {
+    constexpr int SF = WtLayout<N1>::SLOT_FLOATS;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int PER = 32 / N1;                                 // envs served per pass
     const int my_rank = __popc(mask & ((1u << lane) - 1u));      // rank of this lane among the lanes of mask
@@ -105,9 +113,9 @@ __device__ __forceinline__ void warp_compact_q(unsigned mask, bool in_mask, int 
         // promoted after the host sized this launch) is read through the global path
         const bool staged = os < k_opt || os >= K;
         if (SMEMW && __any_sync(FULL, have && !staged)) {
-            if (have) scg_q_c0<N1, false>(c0, zs, WCur<false>(Wt_global, Kall, os), qp);
+            if (have) scg_q_c0<N1, false>(c0, zs, WCur<false>(Wt_global, SF, os), qp);
         } else {
-            if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(SMEMW ? Wt_staged : Wt_global, Kw, SMEMW && os >= K ? os - K + k_opt : os), qp);
+            if (have) scg_q_c0<N1, SMEMW>(c0, zs, WCur<SMEMW>(SMEMW ? Wt_staged : Wt_global, SF, SMEMW && os >= K ? os - K + k_opt : os), qp);
         }
 #pragma unroll
         for (int dd = 1; dd < N1; ++dd) {                        // group head (c0 == 0) gathers the partial sums
@@ -139,29 +147,17 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     // may have rewritten the weights.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
-    // the map always moves with one bulk-TMA copy; so do the weights when every option is staged (contiguous table);
-    // when only the options in use are staged, their slots are gathered feature by feature with plain 16-byte copies
-    // staged slots: the option slots in use (0 .. k_opt-1) followed by the top-level learner's slots (K .. Kall-1)
-    const int Kall = g.K + g.top_slots, k_opt = args.k_stage - g.top_slots;
-    const bool bulk_w = SMEMW && k_opt == g.K;
-    stage2(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, bulk_w ? args.w_bytes : 0, &bar);
-    if (SMEMW && !bulk_w) {
-        const int per_f = 2 * args.k_stage, total = (args.w_bytes >> 4);
-        const float4 *src = reinterpret_cast<const float4 *>(g.Wt);
-        float4 *dst = reinterpret_cast<float4 *>(w_smem);
-        for (int c = threadIdx.x; c < total; c += blockDim.x) {
-            const int f = c / per_f, j = c - f * per_f;
-            const int sl = j >> 1, src_slot = sl < k_opt ? sl : sl - k_opt + g.K;
-            dst[c] = __ldg(src + (size_t)f * 2 * Kall + 2 * src_slot + (j & 1));
-        }
-        __syncthreads();
-    }
+    // the map moves with one bulk-TMA copy, and so do the weights: a slot of the packed table is contiguous, so the
+    // staged table is the option slots in use (0 .. k_opt-1) followed by the top-level learner's slots (K .. Kall-1)
+    constexpr int SF = WtLayout<N1>::SLOT_FLOATS, SB = WtLayout<N1>::SLOT_BYTES;
+    const int k_opt = args.k_stage - g.top_slots;
+    stage3(smem, args.map_blob, args.blob_bytes, w_smem, g.Wt, SMEMW ? k_opt * SB : 0, w_smem + (size_t)k_opt * SB,
+           g.Wt + (size_t)g.K * SF, SMEMW ? g.top_slots * SB : 0, &bar);
     if (!args.wait_first) asm volatile("griddepcontrol.wait;" ::: "memory");
     const StepMap m = make_step_map(smem);
     const ScgMapHeader *mh = reinterpret_cast<const ScgMapHeader *>(smem);
     const float *Wt = SMEMW ? reinterpret_cast<const float *>(w_smem) : g.Wt;
     const int K = g.K;
-    const int Kw = SMEMW ? args.k_stage : Kall;       // slots per feature in the weight table being read
     // controller state lives on the device (scg_agent_manage promotes options in place): the launch was sized with the
     // host's lower bound of n_active (k_stage), the truth is read here
     const int n_act = g.ctl->n_active;
@@ -208,14 +204,14 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                 float2 za[4];
                 scg_phasors(sx, sy, svx, svy, za);
                 float qa[SCG_A];
-                if (unstaged) scg_q_pair<N1, false>(za, zb, WCur<false>(g.Wt, Kall, o), qa, qb);
-                else scg_q_pair<N1, SMEMW>(za, zb, WCur<SMEMW>(Wt, Kw, o), qa, qb);
+                if (unstaged) scg_q_pair<N1, false>(za, zb, WCur<false>(g.Wt, SF, o), qa, qb);
+                else scg_q_pair<N1, SMEMW>(za, zb, WCur<SMEMW>(Wt, SF, o), qa, qb);
                 qsa = 0.f;
 #pragma unroll
                 for (int i = 0; i < SCG_A; ++i) qsa = (i == a) ? qa[i] : qsa;
             } else {
-                if (unstaged) scg_q_one<N1, false>(zb, WCur<false>(g.Wt, Kall, o), qb);
-                else scg_q_one<N1, SMEMW>(zb, WCur<SMEMW>(Wt, Kw, o), qb);
+                if (unstaged) scg_q_one<N1, false>(zb, WCur<false>(g.Wt, SF, o), qb);
+                else scg_q_one<N1, SMEMW>(zb, WCur<SMEMW>(Wt, SF, o), qb);
             }
             // 2-3: initiation bits of s2, termination, option reward
             const uint32_t bits = scg_init_bits(g.theta, K, amask, nx, ny);
@@ -299,7 +295,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     const unsigned rmask = __ballot_sync(FULL, tv && reset);
                     for (int sl = 0; sl < g.top_slots; ++sl) {
                         float qt[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                        warp_compact_q<N1, SMEMW>(tmask, tv, lane, zb, K + sl, Wt, Kw, k_opt, K, g.Wt, Kall, qt);
+                        warp_compact_q<N1, SMEMW>(tmask, tv, lane, zb, K + sl, Wt, k_opt, K, g.Wt, qt);
 #pragma unroll
                         for (int i = 0; i < SCG_A; ++i) {
                             const int j = sl * SCG_A + i;
@@ -310,7 +306,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                         }
                         if (rmask) {          // envs that were reset choose at the start state instead
                             float qr[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                            warp_compact_q<N1, SMEMW>(rmask, tv && reset, lane, zn, K + sl, Wt, Kw, k_opt, K, g.Wt, Kall, qr);
+                            warp_compact_q<N1, SMEMW>(rmask, tv && reset, lane, zn, K + sl, Wt, k_opt, K, g.Wt, qr);
 #pragma unroll
                             for (int i = 0; i < SCG_A; ++i) {
                                 const int j = sl * SCG_A + i;
@@ -321,7 +317,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     float2 z0[4];
                     scg_phasors(stx, sty, stvx, stvy, z0);
                     float q0v[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                    warp_compact_q<N1, SMEMW>(tmask, tv, lane, z0, K + o / SCG_A, Wt, Kw, k_opt, K, g.Wt, Kall, q0v);
+                    warp_compact_q<N1, SMEMW>(tmask, tv, lane, z0, K + o / SCG_A, Wt, k_opt, K, g.Wt, q0v);
                     if (tv) {
                         float q0 = 0.f;
                         const int row = o - (o / SCG_A) * SCG_A;
@@ -341,7 +337,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
                     }
                 }
                 float qn[SCG_A] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                warp_compact_q<N1, SMEMW>(tmask, tv, lane, zn, o_next, Wt, Kw, k_opt, K, g.Wt, Kall, qn);
+                warp_compact_q<N1, SMEMW>(tmask, tv, lane, zn, o_next, Wt, k_opt, K, g.Wt, qn);
                 if (tv) {
                     a_next = scg_eps_greedy(qn, g.epsilon, scg_draw(g.seed, env, step, SCG_STREAM_RESELECT));
 #pragma unroll
@@ -476,7 +472,7 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.blob_bytes = map->hdr.blob_bytes;
     // only the options that can be executed (ids 0 .. n_active) need their weights on chip
     args.k_stage = std::min(ag->K, std::max(ag->n_active, 0) + 1) + ag->top_slots;   // + the top-level learner's slots
-    args.w_bytes = args.k_stage * ctx->F * SCG_WT_STRIDE * (int)sizeof(float);
+    args.w_bytes = args.k_stage * scg_wt_slot_floats(ag->order) * (int)sizeof(float);
     args.rec = reinterpret_cast<float4 *>(ag->win_rec) + (size_t)ag->win_len * ag->B * 2;
     args.ev = ag->ev_hist + (size_t)ag->ev_len * ag->B;
     args.pos = reinterpret_cast<float2 *>(ag->ev_pos) + (size_t)ag->ev_len * ag->B;

@@ -6,7 +6,6 @@
 #include "../../include/scg_b200.h"
 
 #define SCG_A SCG_N_ACTIONS
-#define SCG_WT_STRIDE 8  // packed weights: [K][F][8] (5 actions + 3 pad) -> two 16-byte loads per feature
 #define SCG_REC_FLOATS 12
 #define SCG_WREC_FLOATS 8
 #define SCG_NUM_SMS 148
@@ -193,73 +192,88 @@ __device__ __forceinline__ void scg_phasors(float x, float y, float vx, float vy
 }
 
 // ---- packed weights ------------------------------------------------------------------------------
-// Wt is [F][K][8] fp32: feature-major, then option, then 5 action weights + 3 pad, so that one feature
-// of one option is two 16-byte loads, and the K options of a feature sit in consecutive 32-byte slots
-// (lanes of a warp that execute different options hit different shared-memory banks).  Measured on B200: a
-// 16-byte shared load with 2-3 distinct addresses costs ~3.7 wavefronts, the [F][K][6] / three 8-byte loads
-// alternative ~2.2 each - the same LSU time with more instructions, so the 16-byte form stays.
-// WCur walks the table for one option, from global memory (read-only path) or from a shared-memory copy.
+// Packed weights "Wt": [slot][pair][12] fp32.  A pair is two features that differ only in the last multi-index digit
+// (c3 = 2j, 2j + 1; an odd N1 pairs its last feature with a phantom whose weights are 0): 48 bytes
+//     (w0a w1a w2a w3a | w0b w1b w2b w3b | w4a w4b 0 0)
+// = three 16-byte loads that deliver the register pairs (w0, w1), (w2, w3) of both features and the pair (w4a, w4b) -
+// exactly the operands of the two-wide FMAs - 1.5 loads per feature.  Pairs of a slot are contiguous, so every address is
+// the slot base plus a constant (no per-feature address arithmetic), a slot is one bulk copy into shared memory, and the
+// slot stride is padded to 16 bytes mod 128 so that lanes of a warp on different slots hit different banks.
+template <int N1>
+struct WtLayout {
+    static constexpr int NP = (N1 + 1) / 2;                 // pairs per (c0, c1, c2) row
+    static constexpr int P = N1 * N1 * N1 * NP;             // pairs per slot
+    static constexpr int RAW = P * 48;
+    static constexpr int SLOT_BYTES = RAW + ((16 - RAW % 128) + 128) % 128;
+    static constexpr int SLOT_FLOATS = SLOT_BYTES / 4;
+    // float offset inside a slot of weight (action a, feature f)
+    __host__ __device__ static inline int index(int a, int f) {
+        const int row = f / N1, c3 = f - row * N1;
+        const int pi = row * NP + (c3 >> 1), h = c3 & 1;
+        return pi * 12 + (a < 4 ? h * 4 + a : 8 + h);
+    }
+};
+static inline int scg_wt_slot_floats(int order) {
+    switch (order) {
+        case 1: return WtLayout<2>::SLOT_FLOATS;
+        case 2: return WtLayout<3>::SLOT_FLOATS;
+        case 3: return WtLayout<4>::SLOT_FLOATS;
+        case 4: return WtLayout<5>::SLOT_FLOATS;
+        case 5: return WtLayout<6>::SLOT_FLOATS;
+        default: return 0;
+    }
+}
 __device__ __forceinline__ uint32_t scg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// WCur walks one slot of the table, from global memory (read-only path) or from a shared-memory copy.
+// load_pair(pi): (w0a, w1a), (w2a, w3a), (w0b, w1b), (w2b, w3b), (w4a, w4b) of pair pi.
 template <bool SMEM> struct WCur;
 template <> struct WCur<false> {
-    const float4 *p;
-    int stride;  // float4 units between consecutive features
-    __device__ __forceinline__ WCur(const float *Wt, int K, int o)
-        : p(reinterpret_cast<const float4 *>(Wt) + 2 * o), stride(2 * K) {}
-    __device__ __forceinline__ void load(int f, float4 &a, float4 &b) const {
-        const float4 *q = p + (size_t)f * stride;
-        a = __ldg(q);
-        b = __ldg(q + 1);
-    }
-    // the five action weights of feature f as the register pairs (w0, w1), (w2, w3) and w4
-    __device__ __forceinline__ void load2(int f, f2_t &w01, f2_t &w23, float &w4) const {
-        const float4 *q = p + (size_t)f * stride;
-        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(q));
-        w01 = a.x;
-        w23 = a.y;
-        w4 = __ldg(reinterpret_cast<const float *>(q + 1));
+    const ulonglong2 *p;
+    __device__ __forceinline__ WCur(const float *Wt, int slot_floats, int slot)
+        : p(reinterpret_cast<const ulonglong2 *>(Wt + (size_t)slot * slot_floats)) {}
+    __device__ __forceinline__ void load_pair(int pi, f2_t &a01, f2_t &a23, f2_t &b01, f2_t &b23, f2_t &w4) const {
+        const ulonglong2 *q = p + 3 * pi;
+        const ulonglong2 u = __ldg(q), v = __ldg(q + 1), w = __ldg(q + 2);
+        a01 = u.x; a23 = u.y; b01 = v.x; b23 = v.y; w4 = w.x;
     }
 };
 template <> struct WCur<true> {
-    uint32_t addr, stride;  // bytes
-    __device__ __forceinline__ WCur(const float *Wt_smem, int K, int o)
-        : addr(scg_smem_u32(Wt_smem) + 32u * (uint32_t)o), stride(32u * (uint32_t)K) {}
-    __device__ __forceinline__ void load(int f, float4 &a, float4 &b) const {
-        uint32_t q = addr + (uint32_t)f * stride;
-        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(q));
-        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(q));
-    }
-    __device__ __forceinline__ void load2(int f, f2_t &w01, f2_t &w23, float &w4) const {
-        uint32_t q = addr + (uint32_t)f * stride;
-        asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w01), "=l"(w23) : "r"(q));
-        asm("ld.shared.f32 %0, [%1+16];" : "=f"(w4) : "r"(q));
+    uint32_t addr;  // bytes
+    __device__ __forceinline__ WCur(const float *Wt_smem, int slot_floats, int slot)
+        : addr(scg_smem_u32(Wt_smem) + 4u * (uint32_t)slot_floats * (uint32_t)slot) {}
+    __device__ __forceinline__ void load_pair(int pi, f2_t &a01, f2_t &a23, f2_t &b01, f2_t &b23, f2_t &w4) const {
+        const uint32_t q = addr + 48u * (uint32_t)pi;
+        asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a01), "=l"(a23) : "r"(q));
+        asm("ld.shared.v2.b64 {%0, %1}, [%2+16];" : "=l"(b01), "=l"(b23) : "r"(q));
+        asm("ld.shared.b64 %0, [%1+32];" : "=l"(w4) : "r"(q));
     }
 };
 
 // ---- Q evaluation on the two-wide fp32 instructions ---------------------------------------------------------
 // The step kernel is bound by instruction issue, and most of its Q evaluation is FMAs.  Two features are formed per
 // instruction pair (phi = cos01 * cos23 - sin01 * sin23 on packed (c2, c3) table entries, the (c0, c1) phasor as the
-// broadcast scalar operand), and a feature's five action weights - which a 16-byte load already delivers as the
-// register pairs (w0, w1), (w2, w3) - are consumed by two FFMA2 with phi as the broadcast operand plus one FFMA:
-// 6 issue slots per feature instead of 9.  Accumulators: q01 = (Q0, Q1), q23 = (Q2, Q3), q4.
+// broadcast scalar operand), and the pair's weights are consumed by four FFMA2 with phi_a / phi_b as the broadcast
+// operand plus one FFMA2 on (w4a, w4b) x (phi_a, phi_b): 5 issue slots per feature (3 loads, 2 to form phi, 5 FMAs per
+// pair) instead of 9 in scalar form.  Accumulators: q01 = (Q0, Q1), q23 = (Q2, Q3), q4 = (even, odd) partial sums of Q4.
 struct QAcc {
-    f2_t q01, q23;
-    float q4;
+    f2_t q01, q23, q4;
 };
-__device__ __forceinline__ void qacc_zero(QAcc &q) { q.q01 = 0ull; q.q23 = 0ull; q.q4 = 0.f; }
+__device__ __forceinline__ void qacc_zero(QAcc &q) { q.q01 = 0ull; q.q23 = 0ull; q.q4 = 0ull; }
 __device__ __forceinline__ void qacc_out(const QAcc &q, float out[SCG_A]) {
-    out[0] = f2_x(q.q01); out[1] = f2_y(q.q01); out[2] = f2_x(q.q23); out[3] = f2_y(q.q23); out[4] = q.q4;
+    out[0] = f2_x(q.q01); out[1] = f2_y(q.q01); out[2] = f2_x(q.q23); out[3] = f2_y(q.q23);
+    out[4] = f2_x(q.q4) + f2_y(q.q4);
 }
 template <bool SMEM>
-__device__ __forceinline__ void qacc_feature(const WCur<SMEM> &w, int f, float phi, QAcc &q) {
-    f2_t w01, w23;
-    float w4;
-    w.load2(f, w01, w23, w4);
-    const f2_t p2 = f2_dup(phi);          // folds into the broadcast-scalar operand form of FFMA2
-    q.q01 = f2_fma(w01, p2, q.q01);
-    q.q23 = f2_fma(w23, p2, q.q23);
-    q.q4 = fmaf(w4, phi, q.q4);
+__device__ __forceinline__ void qacc_pair(const WCur<SMEM> &w, int pi, f2_t ph, QAcc &q) {
+    f2_t a01, a23, b01, b23, w4;
+    w.load_pair(pi, a01, a23, b01, b23, w4);
+    const f2_t pa = f2_dup(f2_x(ph)), pb = f2_dup(f2_y(ph));     // fold into the broadcast-scalar operand form of FFMA2
+    q.q01 = f2_fma(a01, pa, q.q01);
+    q.q23 = f2_fma(a23, pa, q.q23);
+    q.q01 = f2_fma(b01, pb, q.q01);
+    q.q23 = f2_fma(b23, pb, q.q23);
+    q.q4 = f2_fma(w4, ph, q.q4);
 }
 // z^c for c = 0 .. N1-1 as packed pairs: xs[i] = (Re z^(2i), Re z^(2i+1)), ys likewise (an odd N1 pads with z^N1)
 template <int N1>
@@ -280,44 +294,41 @@ __device__ __forceinline__ f2_t phi_pair(float2 u, f2_t tx, f2_t ty) {
 
 // Q_o(s, .) for one env: nested loops over the multi-index with running phasor products
 // (cos(pi c.s) = Re prod_j z_j^{c_j}); the two innermost dimensions are unrolled and use a register
-// table of z_3 powers.  Each feature is consumed the moment it is formed.
+// table of z_3 powers.  Each feature pair is consumed the moment it is formed.
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
+    constexpr int NP = WtLayout<N1>::NP;
     QAcc acc;
     qacc_zero(acc);
     if constexpr (N1 == 2 || N1 == 4) {
         // small even orders: the N1^2 products z_2^c2 z_3^c3 fit in registers (as packed pairs over c3), so a feature
         // pair is one packed multiply-add with the (c0, c1) phasor
-        f2_t px[N1 * N1 / 2], py[N1 * N1 / 2];
+        f2_t px[N1 * NP], py[N1 * NP];
         {
             float2 p2 = make_float2(1.f, 0.f);
 #pragma unroll
             for (int c2 = 0; c2 < N1; ++c2) {
                 float2 v = p2;
 #pragma unroll
-                for (int c3 = 0; c3 < N1; c3 += 2) {
+                for (int j = 0; j < NP; ++j) {
                     const float2 v1 = scg_cmul(v, z[3]);
-                    px[(c2 * N1 + c3) / 2] = f2_pack(v.x, v1.x);
-                    py[(c2 * N1 + c3) / 2] = f2_pack(v.y, v1.y);
+                    px[c2 * NP + j] = f2_pack(v.x, v1.x);
+                    py[c2 * NP + j] = f2_pack(v.y, v1.y);
                     v = scg_cmul(v1, z[3]);
                 }
                 p2 = scg_cmul(p2, z[2]);
             }
         }
         float2 z0 = make_float2(1.f, 0.f);
-        int f = 0;
+        int pi = 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < N1; ++c0) {
             float2 z01 = z0;
 #pragma unroll 1
             for (int c1 = 0; c1 < N1; ++c1) {
 #pragma unroll
-                for (int j = 0; j < N1 * N1 / 2; ++j) {
-                    const f2_t ph = phi_pair(z01, px[j], py[j]);
-                    qacc_feature(w, f + 2 * j, f2_x(ph), acc);
-                    qacc_feature(w, f + 2 * j + 1, f2_y(ph), acc);
-                }
-                f += N1 * N1;
+                for (int j = 0; j < N1 * NP; ++j) qacc_pair(w, pi + j, phi_pair(z01, px[j], py[j]), acc);
+                pi += N1 * NP;
                 z01 = scg_cmul(z01, z[1]);
             }
             z0 = scg_cmul(z0, z[0]);
@@ -325,10 +336,10 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
         qacc_out(acc, q);
         return;
     }
-    f2_t p3x[(N1 + 1) / 2], p3y[(N1 + 1) / 2];
+    f2_t p3x[NP], p3y[NP];
     pow_pairs<N1>(z[3], p3x, p3y);
     float2 z0 = make_float2(1.f, 0.f);
-    int f = 0;
+    int pi = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < N1; ++c0) {
         float2 z01 = z0;
@@ -338,14 +349,10 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
 #pragma unroll
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-                for (int c3 = 0; c3 < N1; c3 += 2) {
-                    const f2_t ph = phi_pair(z012, p3x[c3 / 2], p3y[c3 / 2]);
-                    qacc_feature(w, f + c2 * N1 + c3, f2_x(ph), acc);
-                    if (c3 + 1 < N1) qacc_feature(w, f + c2 * N1 + c3 + 1, f2_y(ph), acc);
-                }
+                for (int j = 0; j < NP; ++j) qacc_pair(w, pi + c2 * NP + j, phi_pair(z012, p3x[j], p3y[j]), acc);
                 z012 = scg_cmul(z012, z[2]);
             }
-            f += N1 * N1;
+            pi += N1 * NP;
             z01 = scg_cmul(z01, z[1]);
         }
         z0 = scg_cmul(z0, z[0]);
@@ -357,27 +364,24 @@ __device__ __forceinline__ void scg_q_one(const float2 z[4], const WCur<SMEM> &w
 // that share one env each take one digit and add their partial sums (option re-selection).
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_c0(int c0, const float2 z[4], const WCur<SMEM> &w, float q[SCG_A]) {
-    f2_t p3x[(N1 + 1) / 2], p3y[(N1 + 1) / 2];
+    constexpr int NP = WtLayout<N1>::NP;
+    f2_t p3x[NP], p3y[NP];
     pow_pairs<N1>(z[3], p3x, p3y);
     QAcc acc;
     qacc_zero(acc);
     float2 z01 = make_float2(1.f, 0.f);
     for (int i = 0; i < c0; ++i) z01 = scg_cmul(z01, z[0]);
-    int f = c0 * N1 * N1 * N1;
+    int pi = c0 * N1 * N1 * NP;
 #pragma unroll 1
     for (int c1 = 0; c1 < N1; ++c1) {
         float2 z012 = z01;
 #pragma unroll
         for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-            for (int c3 = 0; c3 < N1; c3 += 2) {
-                const f2_t ph = phi_pair(z012, p3x[c3 / 2], p3y[c3 / 2]);
-                qacc_feature(w, f + c2 * N1 + c3, f2_x(ph), acc);
-                if (c3 + 1 < N1) qacc_feature(w, f + c2 * N1 + c3 + 1, f2_y(ph), acc);
-            }
+            for (int j = 0; j < NP; ++j) qacc_pair(w, pi + c2 * NP + j, phi_pair(z012, p3x[j], p3y[j]), acc);
             z012 = scg_cmul(z012, z[2]);
         }
-        f += N1 * N1;
+        pi += N1 * NP;
         z01 = scg_cmul(z01, z[1]);
     }
     qacc_out(acc, q);
@@ -387,14 +391,15 @@ __device__ __forceinline__ void scg_q_c0(int c0, const float2 z[4], const WCur<S
 template <int N1, bool SMEM>
 __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4], const WCur<SMEM> &w,
                                            float qa[SCG_A], float qb[SCG_A]) {
-    f2_t pax[(N1 + 1) / 2], pay[(N1 + 1) / 2], pbx[(N1 + 1) / 2], pby[(N1 + 1) / 2];
+    constexpr int NP = WtLayout<N1>::NP;
+    f2_t pax[NP], pay[NP], pbx[NP], pby[NP];
     pow_pairs<N1>(za[3], pax, pay);
     pow_pairs<N1>(zb[3], pbx, pby);
     QAcc A, Bq;
     qacc_zero(A);
     qacc_zero(Bq);
     float2 a0 = make_float2(1.f, 0.f), b0 = a0;
-    int f = 0;
+    int pi = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < N1; ++c0) {
         float2 a01 = a0, b01 = b0;
@@ -404,27 +409,25 @@ __device__ __forceinline__ void scg_q_pair(const float2 za[4], const float2 zb[4
 #pragma unroll 1
             for (int c2 = 0; c2 < N1; ++c2) {
 #pragma unroll
-                for (int c3 = 0; c3 < N1; c3 += 2) {
-                    const f2_t pa = phi_pair(a012, pax[c3 / 2], pay[c3 / 2]);
-                    const f2_t pb = phi_pair(b012, pbx[c3 / 2], pby[c3 / 2]);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (c3 + h < N1) {
-                            f2_t w01, w23;
-                            float w4;
-                            w.load2(f + c3 + h, w01, w23, w4);
-                            const float fa = h ? f2_y(pa) : f2_x(pa), fb = h ? f2_y(pb) : f2_x(pb);
-                            const f2_t a2 = f2_dup(fa), b2 = f2_dup(fb);
-                            A.q01 = f2_fma(w01, a2, A.q01);
-                            A.q23 = f2_fma(w23, a2, A.q23);
-                            A.q4 = fmaf(w4, fa, A.q4);
-                            Bq.q01 = f2_fma(w01, b2, Bq.q01);
-                            Bq.q23 = f2_fma(w23, b2, Bq.q23);
-                            Bq.q4 = fmaf(w4, fb, Bq.q4);
-                        }
-                    }
+                for (int j = 0; j < NP; ++j) {
+                    const f2_t pa = phi_pair(a012, pax[j], pay[j]);
+                    const f2_t pb = phi_pair(b012, pbx[j], pby[j]);
+                    f2_t a01w, a23w, b01w, b23w, w4;
+                    w.load_pair(pi + j, a01w, a23w, b01w, b23w, w4);
+                    const f2_t paa = f2_dup(f2_x(pa)), pab = f2_dup(f2_y(pa));
+                    const f2_t pba = f2_dup(f2_x(pb)), pbb = f2_dup(f2_y(pb));
+                    A.q01 = f2_fma(a01w, paa, A.q01);
+                    A.q23 = f2_fma(a23w, paa, A.q23);
+                    A.q01 = f2_fma(b01w, pab, A.q01);
+                    A.q23 = f2_fma(b23w, pab, A.q23);
+                    A.q4 = f2_fma(w4, pa, A.q4);
+                    Bq.q01 = f2_fma(a01w, pba, Bq.q01);
+                    Bq.q23 = f2_fma(a23w, pba, Bq.q23);
+                    Bq.q01 = f2_fma(b01w, pbb, Bq.q01);
+                    Bq.q23 = f2_fma(b23w, pbb, Bq.q23);
+                    Bq.q4 = f2_fma(w4, pb, Bq.q4);
                 }
-                f += N1;
+                pi += NP;
                 a012 = scg_cmul(a012, za[2]);
                 b012 = scg_cmul(b012, zb[2]);
             }

@@ -50,14 +50,27 @@ __global__ void k_features(int B, const float *__restrict__ x, const float *__re
     }
 }
 
-__global__ void k_pack_weights(int F, int K, const float *__restrict__ W, float *__restrict__ Wt) {
-    int n = K * F;
+// W [K][5][F] -> the packed pair layout (scg_common.cuh WtLayout): one thread per (slot, pair)
+template <int N1>
+__global__ void k_pack_weights(int K, const float *__restrict__ W, float *__restrict__ Wt) {
+    using L = WtLayout<N1>;
+    constexpr int F = N1 * N1 * N1 * N1;
+    const int n = K * L::P;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int k = i / F, f = i - k * F;
-        float *o = Wt + ((size_t)f * K + k) * SCG_WT_STRIDE;
+        const int k = i / L::P, pi = i - k * L::P;
+        const int row = pi / L::NP, j = pi - row * L::NP;
+        const int fa = row * N1 + 2 * j;
+        const bool has_b = 2 * j + 1 < N1;          // an odd N1 pairs its last feature with a phantom of weight 0
+        const float *w = W + (size_t)k * SCG_A * F;
+        float *o = Wt + (size_t)k * L::SLOT_FLOATS + pi * 12;
 #pragma unroll
-        for (int a = 0; a < SCG_A; ++a) o[a] = W[((size_t)k * SCG_A + a) * F + f];
-        o[5] = o[6] = o[7] = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            o[a] = w[(size_t)a * F + fa];
+            o[4 + a] = has_b ? w[(size_t)a * F + fa + 1] : 0.f;
+        }
+        o[8] = w[(size_t)4 * F + fa];
+        o[9] = has_b ? w[(size_t)4 * F + fa + 1] : 0.f;
+        o[10] = o[11] = 0.f;
     }
 }
 
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(128) k_q_eval(int K, int B, const float *__res
         scg_phasors(x[b], y[b], vx[b], vy[b], z);
         int o = min(max(option[b], 0), K - 1);
         float q[SCG_A];
-        scg_q_one<N1, false>(z, WCur<false>(Wt, K, o), q);
+        scg_q_one<N1, false>(z, WCur<false>(Wt, WtLayout<N1>::SLOT_FLOATS, o), q);
 #pragma unroll
         for (int a = 0; a < SCG_A; ++a) Q[(size_t)b * SCG_A + a] = q[a];
     }
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(128) k_td(int K, int B, const float *__restric
         scg_phasors(x2[b], y2[b], vx2[b], vy2[b], zb);
         int o = min(max(option[b], 0), K - 1);
         float qa[SCG_A], qb[SCG_A];
-        scg_q_pair<N1, false>(za, zb, WCur<false>(Wt, K, o), qa, qb);
+        scg_q_pair<N1, false>(za, zb, WCur<false>(Wt, WtLayout<N1>::SLOT_FLOATS, o), qa, qb);
         int ia = a[b], ib = a2[b];
         float qsa = 0.f, qs2 = 0.f;
 #pragma unroll
@@ -236,11 +249,13 @@ extern "C" int scg_features(int order, int B, const float *x, const float *y, co
     return 0;
 }
 
+extern "C" int scg_packed_slot_floats(int order) { return scg_wt_slot_floats(order); }
+
 extern "C" int scg_pack_weights(int order, int K, const float *W, float *Wt, void *stream) {
     if (order < 1 || order > SCG_MAX_ORDER || K < 1 || K > SCG_MAX_OPTIONS) return SCG_ELIMIT;
     if (!W || !Wt) return SCG_EINVAL;
     int F = scg_pow4(order + 1);
-    k_pack_weights<<<grid_for(K * F, 256), 256, 0, (cudaStream_t)stream>>>(F, K, W, Wt);
+    DISPATCH_ORDER(order, k_pack_weights<N1><<<grid_for(K * WtLayout<N1>::P, 256), 256, 0, (cudaStream_t)stream>>>(K, W, Wt));
     SCG_LAUNCH_CHECK();
     return 0;
 }

@@ -642,7 +642,7 @@ __global__ void k_apply(int K, int K_opt, float *__restrict__ W, float *__restri
             w = __fadd_rn(w, __fmul_rn(__fmul_rn(top ? alpha_top : alpha, as), __fmul_rn(dW[i], scale)));
             W[i] = w;
         }
-        Wt[((size_t)f * K + k) * SCG_WT_STRIDE + a] = w;
+        Wt[(size_t)k * WtLayout<N1>::SLOT_FLOATS + WtLayout<N1>::index(a, f)] = w;
         dW[i] = 0.f;
     }
     // the last block to finish zeroes cnt for the next window (every block has read it by then): no extra launch

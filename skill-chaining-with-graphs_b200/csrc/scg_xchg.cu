@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(XCHG_SLICE, 8) k_sync(const __grid_constant__ 
             w = __fadd_rn(w, __fmul_rn(__fmul_rn(top ? a.alpha_top : a.alpha, as), __fmul_rn(v, scale)));
             a.W[j] = w;
         }
-        a.Wt[((size_t)f * a.K + k) * SCG_WT_STRIDE + act] = w;
+        a.Wt[(size_t)k * WtLayout<N1>::SLOT_FLOATS + WtLayout<N1>::index(act, f)] = w;
         a.dW[j] = 0.f;
     }
     // the last CTA to finish zeroes cnt for the next window (every CTA read it when it published)

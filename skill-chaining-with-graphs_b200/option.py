@@ -89,7 +89,7 @@ class OptionSet:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         z = dict(dtype=torch.float32, device=self.device)
         self.W = torch.zeros((self.K_all, N_ACTIONS, self.F), **z)
-        self.Wt = torch.zeros((self.F, self.K_all, 8), **z)
+        self.Wt = torch.zeros((self.K_all, self.lib.scg_packed_slot_floats(self.order)), **z)   # packed pair layout
         self.theta = torch.zeros((self.K, N_PSI), **z)
         self._trace = torch.zeros((self.B, N_ACTIONS, self.F), **z)
         self._dW = torch.zeros((self.K_all, N_ACTIONS, self.F), **z)
