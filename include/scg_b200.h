@@ -203,7 +203,7 @@ typedef struct scg_agent {
                                         "terminated": s0 (4), delta_top, option bits (top_slots > 0 only) */
     float *trace;                    /* [B][A][F], as of the last flush */
     /* per-option state (device) */
-    float *W, *Wt, *theta, *dW;      /* [K][A][F], [F][K][8], [K][6], [K][A][F] */
+    float *W, *Wt, *theta, *dW;      /* [K][A][F], [K][scg_packed_slot_floats], [K][6], [K][A][F] */
     int32_t *cnt;                    /* [K] */
     scg_ctl_t *ctl;                  /* controller state */
     float *ex_xy; uint8_t *ex_label; /* [K][cap][2], [K][cap] example rings */

@@ -16,7 +16,7 @@
 //
 // Kernel design: one thread per env, work handed out per warp (32 envs) and interleaved over the
 // persistent CTAs so that every SM gets the same number of warps even at B = 65,536.  Each CTA stages
-// the map blob and, when it fits, the packed weights [F][K][8] into shared memory with bulk-TMA copies
+// the map blob and, when they fit, the packed weight slots in use into shared memory with bulk-TMA copies
 // (cp.async.bulk + mbarrier); lanes executing different options then read different banks.
 #include <stdlib.h>
 

@@ -7,9 +7,9 @@
 //
 // K2 design: one thread per env.  phi = cos(pi C s_hat) is never materialised: four sincospi
 // calls give z_j = exp(i pi s_hat_j), the multi-index loops keep running complex products, and
-// each feature is consumed by five FFMAs the moment it is formed (scg_q_one / scg_q_pair in
-// scg_common.cuh).  Weights are read from the packed [F][K][8] copy with two 16-byte loads per
-// feature, warp-uniform when the warp's envs execute the same option.  The contraction is
+// each pair of features is consumed by five two-wide FMAs the moment it is formed (scg_q_one / scg_q_pair
+// in scg_common.cuh).  Weights are read from the packed pair layout (WtLayout: 48 bytes per feature pair,
+// three 16-byte loads), warp-uniform when the warp's envs execute the same option.  The contraction is
 // (B x F).(F x 5): far too skinny for tcgen05 tiles, so it stays on the FP32 pipe.
 // Roofline: FP32, 18 F flop per (env, option).
 #include <algorithm>
