@@ -18,6 +18,8 @@
 
 #include <algorithm>
 
+#include <type_traits>
+
 #include "scg_common.cuh"
 
 template <int VEC> struct VecT;
@@ -178,6 +180,9 @@ __global__ void __launch_bounds__(NT) k_trace(int B, int K, const float4 *__rest
 // costs two 8-byte shared loads and two FP32 ops to form, and the dense trace crosses HBM once per
 // window: 8*A*F/T + 32 algorithmic bytes per env-step.
 #define SCG_WIN_TB 8   // steps per table block
+#ifndef SCG_WIN_PF
+#define SCG_WIN_PF 1
+#endif
 
 struct WinItem {   // a work item of the sweep: block `blk` of 8 steps of env `b`
     int b, blk;
@@ -193,11 +198,23 @@ struct WinCtlT {
     int nseg, pad;
 };
 
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
+// Single-block sweep (T <= 8): the scan warp sorts the window's steps by (segment, action) into a list, so that the main
+// phase walks plain index ranges with static register rows - one broadcast 16-byte load per step carries G_t, c_t and
+// the byte offset of the step's tables, and there is no bit-mask bookkeeping in the loop.
+struct WinCtlList {
+    float4 ent[SCG_WIN_TB + 1];        // (G_t, c_t, byte offset of step t's pair tables, -) in (segment, action, t) order
+    uint8_t rng[SCG_WIN_TB][8];        // [segment][action]: first list index of that action's steps; [5] = end
+    uint32_t seg_o[SCG_WIN_TB];
+    float scale, carry;
+    int nseg, pad;
+};
+
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF>
 __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl, float *dW, int K_all) {
     using V = typename VecT<VEC>::type;
-    using WinCtl = WinCtlT<MULTI ? SCG_WIN_MAX : SCG_WIN_TB>;   // (the small form keeps 8 CTAs per SM at order 3 with 4 options in use)
+    constexpr bool LIST = LISTP && !MULTI;
+    using WinCtl = std::conditional_t<LIST, WinCtlList, WinCtlT<MULTI ? SCG_WIN_MAX : SCG_WIN_TB>>;
     constexpr int F = N1 * N1 * N1 * N1;
     constexpr int AF = SCG_A * F;
     constexpr int NCHR = F / VEC;          // chunks per action row
@@ -236,18 +253,32 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         off23[j] = VEC == 4 ? NN * (int)sizeof(float2) + ((f0 % NN) / 4) * 16 : (NN + f0 % NN) * (int)sizeof(float2);
     }
     // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits,
-    // and the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4)
-    int e_tt[EPT], e_half[EPT];
-    float e_ca[EPT], e_cb[EPT], e_mul[EPT], e_add[EPT];
+    // the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4) folded into the
+    // digit coefficients (x = ca s0 + cb s1 + cc on the raw pair), and where the entry goes.
+    // REG: the threads of a CTA tile the steps' tables exactly (NT a multiple of the 2 NN entries of a step), so all of
+    // this is the same for every entry a thread builds, up to a constant step stride - scalars instead of arrays.
+    constexpr bool REG = NT % (2 * NN) == 0 && TABN % NT == 0;
+    constexpr int EN = REG ? 1 : EPT;
+    int e_tt[EN], e_half[EN], e_at[EN];
+    float e_ca[EN], e_cb[EN], e_cc[EN];
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) {
+    for (int k = 0; k < EN; ++k) {
         int idx = tid + k * NT;
         if (idx >= TABN) idx = TABN - 1;                 // duplicate work on the last entry, never out of range
         const int tt = idx / (2 * NN), rem = idx - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
         e_tt[k] = tt; e_half[k] = half;
-        e_mul[k] = half ? 0.25f : 1.f; e_add[k] = half ? 0.5f : 0.f;
-        e_ca[k] = (float)(ij / N1); e_cb[k] = (float)(ij % N1);
+        const float mul = half ? 0.25f : 1.f, add = half ? 0.5f : 0.f;
+        e_ca[k] = (float)(ij / N1) * mul; e_cb[k] = (float)(ij % N1) * mul;
+        e_cc[k] = (float)(ij / N1 + ij % N1) * add;
+        int at = idx;
+        if (VEC == 4 && half) {
+            const int g = ij >> 2, kk = ij & 3;
+            at = (tt * 2 + 1) * NN + (kk < 2 ? 2 * g + kk : NN / 2 + 2 * g + (kk - 2));
+        }
+        e_at[k] = at;
     }
+    auto ent_tt = [&](int k) { return REG ? e_tt[0] + k * (NT / (2 * NN)) : e_tt[REG ? 0 : k]; };
+    auto ent_at = [&](int k) { return REG ? e_at[0] + k * NT : e_at[REG ? 0 : k]; };
     for (int i = tid; i < K * AF; i += NTT) acc[i] = 0.f;
     if (tid == 0) {
         float p = 1.f;
@@ -267,14 +298,15 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     // prefetch registers
     float2 r_sv[EPT];                                    // state pair of the steps this thread builds entries for
     float2 r_dm = make_float2(0.f, 0.f);                 // (delta, meta) of step tid (first block of an env only)
-    V e[CH][SCG_A], e_nx[CH][SCG_A], d[CH][SCG_A];
+    V e[CH][SCG_A], d[CH][SCG_A];
+    V e_nx[L2PF ? 1 : CH][L2PF ? 1 : SCG_A];            // register prefetch of the next env's trace (!L2PF)
     uint32_t o_cur = 0;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
 #pragma unroll
         for (int r = 0; r < SCG_A; ++r) {
-            if constexpr (VEC == 4) { e[j][r] = vzero4(); e_nx[j][r] = vzero4(); d[j][r] = vzero4(); }
-            else { e[j][r] = 0.f; e_nx[j][r] = 0.f; d[j][r] = 0.f; }
+            if constexpr (VEC == 4) { e[j][r] = vzero4(); d[j][r] = vzero4(); }
+            else { e[j][r] = 0.f; d[j][r] = 0.f; }
         }
     }
 
@@ -282,12 +314,27 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         if (worker) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
-                const int t = min(it.blk * SCG_WIN_TB + e_tt[k], T - 1);
-                r_sv[k] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + e_half[k]);
+                const int t = min(it.blk * SCG_WIN_TB + ent_tt(k), T - 1);
+                r_sv[k] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + e_half[REG ? 0 : k]);
             }
         }
         if (it.blk == 0 && scan_warp && (tid & 31) < T)
             r_dm = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)(tid & 31) * B + it.b) * 2 + 1));
+    };
+    // The trace of an env is pulled into L2 two items ahead by one bulk-prefetch instruction (no registers, no shared
+    // memory); the item itself then loads it straight into the trace registers, an L2 hit whose latency the table build
+    // covers.  (Holding the next trace in registers instead cost 20 registers per thread - one CTA per SM at order 3.)
+    auto prefetch_trace = [&](int b) {
+        constexpr int BYTES = AF * (int)sizeof(float);
+        if constexpr (BYTES % 16 == 0) {
+            if (tid == NT - 1)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(trace + (size_t)b * AF), "n"(BYTES)
+                             : "memory");
+        } else {                                         // odd N1: the env's trace is only 4-byte aligned - line by line
+            const char *base = reinterpret_cast<const char *>(trace + (size_t)b * AF);
+            for (int ofs = tid * 128; ofs < BYTES; ofs += NT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ofs) : "memory");
+        }
     };
     auto load_trace = [&](int b) {
         const V *tp = reinterpret_cast<const V *>(trace + (size_t)b * AF);
@@ -295,7 +342,10 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         for (int j = 0; j < CH; ++j) {
             if (own[j]) {
 #pragma unroll
-                for (int r = 0; r < SCG_A; ++r) e_nx[j][r] = tp[r * NCHR + tid + j * NT];
+                for (int r = 0; r < SCG_A; ++r) {
+                    if constexpr (L2PF) e[j][r] = tp[r * NCHR + tid + j * NT];
+                    else e_nx[j][r] = tp[r * NCHR + tid + j * NT];
+                }
             }
         }
     };
@@ -305,19 +355,11 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         if (worker) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
-                const float s0 = fmaf(r_sv[k].x, e_mul[k], e_add[k]), s1 = fmaf(r_sv[k].y, e_mul[k], e_add[k]);
                 // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
-                const float x = fmaf(e_ca[k], s0, e_cb[k] * s1);
+                const int kc = REG ? 0 : k;
+                const float x = fmaf(e_ca[kc], r_sv[k].x, fmaf(e_cb[kc], r_sv[k].y, e_cc[kc]));
                 const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
-                const int idx = tid + k * NT;
-                if (idx < TABN) {
-                    int at = idx;
-                    if (VEC == 4 && e_half[k]) {
-                        const int ij = idx - (e_tt[k] * 2 + 1) * NN, g = ij >> 2, kk = ij & 3;
-                        at = (e_tt[k] * 2 + 1) * NN + (kk < 2 ? 2 * g + kk : NN / 2 + 2 * g + (kk - 2));
-                    }
-                    tb[at] = make_float2(__cosf(xr), __sinf(xr));
-                }
+                if (REG || tid + k * NT < TABN) tb[ent_at(k)] = make_float2(__cosf(xr), __sinf(xr));
             }
         }
         if (it.blk == 0 && scan_warp) {
@@ -340,7 +382,6 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             const bool dead = (dm >> t) != 0;                     // a termination at this step or later in the window
             const float cf = (act && !dead) ? glpow[__popc((am >> t) >> 1)] : 0.f;
             const float G = act ? D : 0.f;
-            if (t < T) cb.gc[t] = make_float2(G, cf);
             // segments: maximal runs of steps under the same option
             const unsigned before = am & ((1u << t) - 1u);
             const int prev = before ? 31 - __clz(before) : t;
@@ -349,17 +390,46 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             const int seg = __popc(chg & ((2u << t) - 1u));
             const int nseg = am ? __popc(chg) + 1 : 0;
             const bool nz = act && (G != 0.f || cf != 0.f);
-            for (int sgm = 0; sgm < nseg; ++sgm) {
-                const unsigned in_seg = __ballot_sync(FULL, act && seg == sgm);
-                const uint32_t os = __shfl_sync(FULL, o, __ffs(in_seg) - 1);
-                unsigned mine = 0;
+            if constexpr (!LIST) {
+                if (t < T) cb.gc[t] = make_float2(G, cf);
+                for (int sgm = 0; sgm < nseg; ++sgm) {
+                    const unsigned in_seg = __ballot_sync(FULL, act && seg == sgm);
+                    const uint32_t os = __shfl_sync(FULL, o, __ffs(in_seg) - 1);
+                    unsigned mine = 0;
 #pragma unroll
-                for (int r = 0; r < SCG_A; ++r) {
-                    const unsigned mr = __ballot_sync(FULL, nz && seg == sgm && a == (uint32_t)r);
-                    if (t == r) mine = mr;
+                    for (int r = 0; r < SCG_A; ++r) {
+                        const unsigned mr = __ballot_sync(FULL, nz && seg == sgm && a == (uint32_t)r);
+                        if (t == r) mine = mr;
+                    }
+                    if (t < SCG_A) cb.mask[sgm][t] = mine;
+                    if (t == 0) cb.seg_o[sgm] = os;
                 }
-                if (t < SCG_A) cb.mask[sgm][t] = mine;
-                if (t == 0) cb.seg_o[sgm] = os;
+            } else {
+                // counting sort of the contributing steps by (segment, action, t): segments are runs in time
+                uint32_t m[SCG_A], nzm = 0;
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) { m[r] = __ballot_sync(FULL, nz && a == (uint32_t)r); nzm |= m[r]; }
+                const unsigned below = (1u << t) - 1u;
+                for (int sgm = 0; sgm < nseg; ++sgm) {
+                    const unsigned in_seg = __ballot_sync(FULL, act && seg == sgm);
+                    const int first = __ffs(in_seg) - 1;
+                    const uint32_t os = __shfl_sync(FULL, o, first);
+                    const int base = __popc(nzm & ((1u << first) - 1u));
+                    int c_lane = base, c_own = base;          // list index where action `t` / this step's action starts
+                    uint32_t m_own = 0;
+#pragma unroll
+                    for (int r = 0; r < SCG_A; ++r) {
+                        const int pc = __popc(m[r] & in_seg);
+                        if (r < t) c_lane += pc;
+                        if ((uint32_t)r < a) c_own += pc;
+                        if ((uint32_t)r == a) m_own = m[r];
+                    }
+                    if (t <= SCG_A) cb.rng[sgm][t] = (uint8_t)c_lane;
+                    if (nz && seg == sgm)
+                        cb.ent[c_own + __popc(m_own & in_seg & below)] =
+                            make_float4(G, cf, __int_as_float(par * TABN * (int)sizeof(float2) + t * TSTRIDE), 0.f);
+                    if (t == 0) cb.seg_o[sgm] = os;
+                }
             }
             if (t == 0) {
                 cb.scale = dm ? 0.f : glpow[__popc(am)];
@@ -411,10 +481,11 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     WinItem cur = {(int)blockIdx.x, 0};
     if (cur.b < B) {
         load_rec(cur);
-        load_trace(cur.b);
+        if constexpr (!L2PF) load_trace(cur.b);
     }
     __syncthreads();                                     // accumulator zeroed, glpow ready
     WinItem nxt = advance(cur);
+    if (L2PF && nxt.b < B) prefetch_trace(nxt.b);
     if (cur.b < B) build(cur, 0, 0);
     if (nxt.b < B) load_rec(nxt);
     __syncthreads();
@@ -422,7 +493,10 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     int par = 0, epar = 0;
     while (cur.b < B) {
         const WinItem nx2 = advance(nxt);
-        if (cur.blk == 0) {
+        if constexpr (L2PF) {
+            if (cur.blk == 0) load_trace(cur.b);
+            if (nx2.blk == 0 && nx2.b < B) prefetch_trace(nx2.b);
+        } else if (cur.blk == 0) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
 #pragma unroll
@@ -432,11 +506,14 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         // next item's tables (into the other buffer), then the loads for the items after it
         if (nxt.b < B) build(nxt, par ^ 1, nxt.blk == 0 ? epar ^ 1 : epar);
         if (nx2.b < B) load_rec(nx2);
-        if (nxt.blk == 0 && nxt.b < B) load_trace(nxt.b);
+        if constexpr (!L2PF) {
+            if (nxt.blk == 0 && nxt.b < B) load_trace(nxt.b);
+        }
         // ---- main ----
         const WinCtl &cb = ctl[epar];
         const char *tb0 = reinterpret_cast<const char *>(tab + par * TABN);
-        const float2 *gc = cb.gc + cur.blk * SCG_WIN_TB;
+        [[maybe_unused]] const float2 *gc = nullptr;
+        if constexpr (!LIST) gc = cb.gc + cur.blk * SCG_WIN_TB;
         if (cur.blk == 0) {
             const float carry = cb.carry, scale = cb.scale;
             o_cur = cb.seg_o[0];
@@ -450,6 +527,65 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             }
         }
         const int nseg = cb.nseg;
+        auto change_option = [&](uint32_t so) {          // the env changed option inside the window (after a termination)
+            flush_d();
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) {
+                    if constexpr (VEC == 4) d[j][r] = vzero4(); else d[j][r] = 0.f;
+                }
+            }
+            o_cur = so;
+        };
+        // one step's contribution to row r of the owned chunks; tb: the step's pair tables
+        auto step_row = [&](const char *tb, float G, float c, V (&dd)[CH][SCG_A], V (&ee)[CH][SCG_A], int r) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {               // independent chunks: their loads and FMAs interleave
+                const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
+                V ph;
+                if constexpr (VEC == 4) {
+                    const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
+                    const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + (NN / 4) * 16);
+                    ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
+                                     fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
+                } else {
+                    const float2 q = *reinterpret_cast<const float2 *>(tb + off23[j]);
+                    ph = fmaf(p.x, q.x, -p.y * q.y);
+                }
+                dd[j][r] = vfma(G, ph, dd[j][r]);
+                ee[j][r] = vfma(c, ph, ee[j][r]);
+            }
+        };
+        if constexpr (LIST) {
+            const char *tbase = reinterpret_cast<const char *>(tab);
+            for (int sgm = 0; sgm < nseg; ++sgm) {
+                const uint2 rr = *reinterpret_cast<const uint2 *>(cb.rng[sgm]);
+                int lo = rr.x & 0xFF;
+                if (lo == (int)((rr.y >> 8) & 0xFF)) continue;         // no contributing step in this segment
+                const uint32_t so = cb.seg_o[sgm];
+                if (so != o_cur) change_option(so);
+#if SCG_WIN_PF
+                float4 en = cb.ent[lo];                  // the list is contiguous across the actions: always one ahead
+#endif
+#pragma unroll
+                for (int r = 0; r < SCG_A; ++r) {        // static register rows: no dynamic indexing, no switch
+                    const int hi = r < 3 ? (rr.x >> (8 * (r + 1))) & 0xFF : (rr.y >> (8 * (r - 3))) & 0xFF;
+#pragma unroll 1
+                    for (int i = lo; i < hi; ++i) {
+#if SCG_WIN_PF
+                        const float4 nx = cb.ent[i + 1];
+                        step_row(tbase + __float_as_int(en.z), en.x, en.y, d, e, r);
+                        en = nx;
+#else
+                        const float4 en = cb.ent[i];
+                        step_row(tbase + __float_as_int(en.z), en.x, en.y, d, e, r);
+#endif
+                    }
+                    lo = hi;
+                }
+            }
+        } else {
         for (int sgm = 0; sgm < nseg; ++sgm) {
             // this segment's steps inside this block, one bit mask per action
             uint32_t mk[SCG_A];
@@ -465,43 +601,18 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
             }
             if (!any) continue;
             const uint32_t so = cb.seg_o[sgm];
-            if (so != o_cur) {                           // the env changed option inside the window (after a termination)
-                flush_d();
+            if (so != o_cur) change_option(so);
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-#pragma unroll
-                    for (int r = 0; r < SCG_A; ++r) {
-                        if constexpr (VEC == 4) d[j][r] = vzero4(); else d[j][r] = 0.f;
-                    }
-                }
-                o_cur = so;
-            }
-#pragma unroll
-            for (int r = 0; r < SCG_A; ++r) {            // static register rows: no dynamic indexing, no switch
+            for (int r = 0; r < SCG_A; ++r) {
                 uint32_t mm = mk[r];
                 while (mm) {
                     const int tt = __ffs(mm) - 1;
                     mm &= mm - 1;
                     const float2 g2 = gc[tt];
-                    const char *tb = tb0 + tt * TSTRIDE;
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) {       // independent chunks: their loads and FMAs interleave
-                        const float2 p = *reinterpret_cast<const float2 *>(tb + off01[j]);
-                        V ph;
-                        if constexpr (VEC == 4) {
-                            const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
-                            const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + (NN / 4) * 16);
-                            ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
-                                             fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
-                        } else {
-                            const float2 q = *reinterpret_cast<const float2 *>(tb + off23[j]);
-                            ph = fmaf(p.x, q.x, -p.y * q.y);
-                        }
-                        d[j][r] = vfma(g2.x, ph, d[j][r]);
-                        e[j][r] = vfma(g2.y, ph, e[j][r]);
-                    }
+                    step_row(tb0 + tt * TSTRIDE, g2.x, g2.y, d, e, r);
                 }
             }
+        }
         }
         if (cur.blk == NBLK - 1) {
             flush_d();
@@ -715,20 +826,20 @@ static int ensure_partials(scg_ctx *ctx, int n) {
 }
 
 template <int N1>
-static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi) {
+static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi, bool list = true) {
     constexpr int NN = N1 * N1;
     return (((size_t)k_used * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
            (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) +
-           2 * (multi ? sizeof(WinCtlT<SCG_WIN_MAX>) : sizeof(WinCtlT<SCG_WIN_TB>)) + 36 * sizeof(float);
+           2 * (multi ? sizeof(WinCtlT<SCG_WIN_MAX>) : (list ? sizeof(WinCtlList) : sizeof(WinCtlT<SCG_WIN_TB>))) + 36 * sizeof(float);
 }
 
 // k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
 // the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                             float *dW, cudaStream_t st) {
-    const size_t smem = window_smem<N1>(ctx, k_used, MULTI);
-    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL>;
+    const size_t smem = window_smem<N1>(ctx, k_used, MULTI, LISTP);
+    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL, LISTP, L2PF>;
     constexpr int NTT = NT + (CTRL ? 32 : 0);
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
@@ -746,11 +857,11 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4
     return grid;
 }
 
-template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false>
+template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false, bool LISTP = true, bool L2PF = false>
 static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                            float *dW, cudaStream_t st) {
-    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
-    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL, LISTP, L2PF>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL, false, L2PF>(ctx, B, T, k_used, rec, trace, gl, dW, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
@@ -762,39 +873,29 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     if (T < 1 || T > SCG_WIN_MAX || k_used < 1 || k_used > ctx->K) return SCG_EINVAL;
     const float4 *r4 = reinterpret_cast<const float4 *>(rec);
     int grid = 0, rc;
-    static int win_ch3 = -1, win_ch5 = -1;   // tuning knobs: chunks per thread at orders 3 and 5
-    if (win_ch3 < 0) { const char *e = getenv("SCG_WIN_CH3"); win_ch3 = e ? atoi(e) : 1; }
-    if (win_ch5 < 0) { const char *e = getenv("SCG_WIN_CH5"); win_ch5 = e ? atoi(e) : 1; }
-    static int win_ctrl5 = -1;   // order 5: a 12th warp that only runs the per-env scan
-    if (win_ctrl5 < 0) { const char *e = getenv("SCG_WIN_CTRL5"); win_ctrl5 = e ? atoi(e) : 1; }
-    static int win_9cta3 = -1;
-    if (win_9cta3 < 0) { const char *e = getenv("SCG_WIN_9CTA3"); win_9cta3 = e ? atoi(e) : 0; }
-    static int win_2cta5 = -1;
-    if (win_2cta5 < 0) { const char *e = getenv("SCG_WIN_2CTA5"); win_2cta5 = e ? atoi(e) : 0; }   // measured: 80 registers + spills, 0.345 vs 0.258 ms/step: off
+    // tuning knobs (defaults = the measured best)
+    static int mode3 = -1, list5 = -1;
+    if (mode3 < 0) { const char *e = getenv("SCG_WIN_MODE3"); mode3 = e ? atoi(e) : 2; }
+    if (list5 < 0) { const char *e = getenv("SCG_WIN_LIST5"); list5 = e ? atoi(e) : 0; }
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
     switch (ctx->order) {
-        // <N1, floats per chunk, threads, chunks per thread>.  Register budget matters more than occupancy here: the
-        // order-3 sweep left uncapped takes 158 registers (6 CTAs / SM) and runs 0.157 ms; capped to 128 registers
-        // (8 CTAs / SM) 0.178 ms; 96 registers (9 CTAs) 0.178 ms.  Measured on B200 (order 3, B = 65,536): two warps per
-        // env with one chunk per thread 0.155 ms; one warp per env with two chunks per thread (SCG_WIN_CH3=2) has 18 %
-        // fewer instructions but only 8 warps/SM to hide the shared-memory latency: 0.159 ms.  Order 5: 2.27 vs 2.38 ms.
+        // <N1, floats per chunk, threads, chunks per thread, min CTAs per SM, scan warp, step lists, L2 prefetch>
         case 1: grid = launch_window_t<2, 4, 32, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 2: grid = launch_window_t<3, 1, 96, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 3:
-            if (win_ch3 == 1 && win_9cta3 && 9 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // nine CTAs per SM (<= 112 registers)
-                grid = launch_window_t<4, 4, 64, 1, 9>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_ch3 == 1) grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else grid = launch_window_t<4, 4, 32, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            // two warps per env.  With the next trace prefetched into L2 instead of registers the sweep needs 140
+            // registers (7 CTAs per SM) and loses nothing when squeezed to 128 (8 CTAs, while 8 accumulators fit)
+            if (mode3 == 2 && 8 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)
+                grid = launch_window_t<4, 4, 64, 1, 8, false, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (mode3 >= 1) grid = launch_window_t<4, 4, 64, 1, 1, false, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             break;
         case 4: grid = launch_window_t<5, 1, 640, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st); break;
         case 5:
-            if (win_ch5 == 2 && 2 * (window_smem<6>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two 6-warp CTAs, two chunks per thread
-                grid = launch_window_t<6, 4, 192, 2, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_ch5 == 2) grid = launch_window_t<6, 4, 192, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_2cta5 && 2 * (window_smem<6>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)   // two CTAs per SM (80 registers)
-                grid = launch_window_t<6, 4, 352, 1, 2>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else if (win_ctrl5) grid = launch_window_t<6, 4, 352, 1, 1, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
-            else grid = launch_window_t<6, 4, 352, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            // one CTA per SM: 11 work warps + a warp that only runs the per-env scan; next trace prefetched in registers
+            // (L2 prefetch: 1.98 vs 1.75 ms - one CTA cannot cover the L2 latency); bit-mask loop (step lists: 1.74 vs 1.70 ms)
+            if (list5) grid = launch_window_t<6, 4, 352, 1, 1, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else grid = launch_window_t<6, 4, 352, 1, 1, true, false>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             break;
         default: return SCG_ELIMIT;
     }
