@@ -209,7 +209,7 @@ struct WinCtlList {
     int nseg, pad;
 };
 
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF, bool SPLITP>
 __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, int K, int T, const float4 *__restrict__ rec, float *trace,
                                                float *__restrict__ partial, float gl, float *dW, int K_all) {
     using V = typename VecT<VEC>::type;
@@ -220,7 +220,12 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     constexpr int NCHR = F / VEC;          // chunks per action row
     constexpr int NN = N1 * N1;
     constexpr int TABN = SCG_WIN_TB * 2 * NN;             // entries of one table buffer
-    constexpr int EPT = (TABN + NT - 1) / NT;             // table entries built per thread
+    // SPLIT (two warps per env): warp 0 runs the per-env scan, warp 1 builds all the table entries - the two jobs take
+    // about as long, so neither warp waits for the other at the per-item barrier.  The 16 state pairs the entries need
+    // (8 steps x positions / velocities) are loaded by 16 lanes, one each, and handed round with shuffles.
+    constexpr bool SPLIT = SPLITP && !CTRL && !MULTI && NT == 64 && 2 * NN == 32;
+    constexpr int BT = SPLIT ? 32 : NT;                   // threads that build table entries
+    constexpr int EPT = (TABN + BT - 1) / BT;             // table entries built per builder thread
     constexpr int TSTRIDE = 2 * NN * (int)sizeof(float2); // bytes between the tables of consecutive steps
     static_assert(F % VEC == 0 && NT * CH >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
     static_assert(VEC == 1 || NN % VEC == 0, "a chunk shares its (c0, c1) digits");
@@ -236,6 +241,8 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     constexpr int NTT = NT + (CTRL ? 32 : 0);
     const bool scan_warp = CTRL ? (tid >= NT) : (tid < 32);
     const bool worker = tid < NT;
+    const bool builder = SPLIT ? tid >= 32 : worker;
+    const int bt = SPLIT ? tid - 32 : tid;                // builder index (SPLIT: lane = half * NN + ij)
     // thread t owns chunks t, t + NT, ... of every action row (each a coalesced access across the CTA)
     bool own[CH];
 #pragma unroll
@@ -257,13 +264,13 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     // digit coefficients (x = ca s0 + cb s1 + cc on the raw pair), and where the entry goes.
     // REG: the threads of a CTA tile the steps' tables exactly (NT a multiple of the 2 NN entries of a step), so all of
     // this is the same for every entry a thread builds, up to a constant step stride - scalars instead of arrays.
-    constexpr bool REG = NT % (2 * NN) == 0 && TABN % NT == 0;
+    constexpr bool REG = BT % (2 * NN) == 0 && TABN % BT == 0;
     constexpr int EN = REG ? 1 : EPT;
     int e_tt[EN], e_half[EN], e_at[EN];
     float e_ca[EN], e_cb[EN], e_cc[EN];
 #pragma unroll
     for (int k = 0; k < EN; ++k) {
-        int idx = tid + k * NT;
+        int idx = (builder ? bt : 0) + k * BT;
         if (idx >= TABN) idx = TABN - 1;                 // duplicate work on the last entry, never out of range
         const int tt = idx / (2 * NN), rem = idx - tt * 2 * NN, half = rem / NN, ij = rem - half * NN;
         e_tt[k] = tt; e_half[k] = half;
@@ -277,8 +284,8 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         }
         e_at[k] = at;
     }
-    auto ent_tt = [&](int k) { return REG ? e_tt[0] + k * (NT / (2 * NN)) : e_tt[REG ? 0 : k]; };
-    auto ent_at = [&](int k) { return REG ? e_at[0] + k * NT : e_at[REG ? 0 : k]; };
+    auto ent_tt = [&](int k) { return REG ? e_tt[0] + k * (BT / (2 * NN)) : e_tt[REG ? 0 : k]; };
+    auto ent_at = [&](int k) { return REG ? e_at[0] + k * BT : e_at[REG ? 0 : k]; };
     for (int i = tid; i < K * AF; i += NTT) acc[i] = 0.f;
     if (tid == 0) {
         float p = 1.f;
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     };
 
     // prefetch registers
-    float2 r_sv[EPT];                                    // state pair of the steps this thread builds entries for
+    float2 r_sv[SPLIT ? 1 : EPT];                        // state pair of the steps this thread builds entries for
     float2 r_dm = make_float2(0.f, 0.f);                 // (delta, meta) of step tid (first block of an env only)
     V e[CH][SCG_A], d[CH][SCG_A];
     V e_nx[L2PF ? 1 : CH][L2PF ? 1 : SCG_A];            // register prefetch of the next env's trace (!L2PF)
@@ -311,7 +318,12 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     }
 
     auto load_rec = [&](WinItem it) {                    // records of a work item -> registers
-        if (worker) {
+        if constexpr (SPLIT) {
+            if (tid >= 32 && tid < 32 + 2 * SCG_WIN_TB) {                 // lane l: step l / 2, pair l & 1
+                const int t = min((tid - 32) >> 1, T - 1);
+                r_sv[0] = __ldg(reinterpret_cast<const float2 *>(rec + ((size_t)t * B + it.b) * 2) + (tid & 1));
+            }
+        } else if (worker) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
                 const int t = min(it.blk * SCG_WIN_TB + ent_tt(k), T - 1);
@@ -352,14 +364,21 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     // registers -> pair tables (buffer `par`) and, for an env's first block, its control block (buffer `epar`)
     auto build = [&](WinItem it, int par, int epar) {
         float2 *tb = tab + par * TABN;
-        if (worker) {
+        if (builder) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
                 // exp(i pi x): exact reduction of x to [-1, 1], then the SFU (abs error ~4e-7)
                 const int kc = REG ? 0 : k;
-                const float x = fmaf(e_ca[kc], r_sv[k].x, fmaf(e_cb[kc], r_sv[k].y, e_cc[kc]));
+                float2 sv;
+                if constexpr (SPLIT) {                   // entry k of this lane is step k: its pair sits in lane 2k + half
+                    sv.x = __shfl_sync(0xffffffffu, r_sv[0].x, 2 * k + e_half[0]);
+                    sv.y = __shfl_sync(0xffffffffu, r_sv[0].y, 2 * k + e_half[0]);
+                } else {
+                    sv = r_sv[k];
+                }
+                const float x = fmaf(e_ca[kc], sv.x, fmaf(e_cb[kc], sv.y, e_cc[kc]));
                 const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
-                if (REG || tid + k * NT < TABN) tb[ent_at(k)] = make_float2(__cosf(xr), __sinf(xr));
+                if (REG || bt + k * BT < TABN) tb[ent_at(k)] = make_float2(__cosf(xr), __sinf(xr));
             }
         }
         if (it.blk == 0 && scan_warp) {
@@ -572,7 +591,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 for (int r = 0; r < SCG_A; ++r) {        // static register rows: no dynamic indexing, no switch
                     const int hi = r < 3 ? (rr.x >> (8 * (r + 1))) & 0xFF : (rr.y >> (8 * (r - 3))) & 0xFF;
 #pragma unroll 1
-                    for (int i = lo; i < hi; ++i) {
+                    for (int i = lo; i < hi; ++i) {      // (two steps per trip, to spare the copy: measured equal)
 #if SCG_WIN_PF
                         const float4 nx = cb.ent[i + 1];
                         step_row(tbase + __float_as_int(en.z), en.x, en.y, d, e, r);
@@ -835,11 +854,11 @@ static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi, bool list 
 
 // k_used: options that can appear in the window's records (ids 0 .. k_used-1): the CTA accumulator, the slabs and
 // the reduction only cover those, which is what lets two CTAs share an SM at order 5 while the chain is short
-template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF>
+template <int N1, int VEC, int NT, int CH, bool MULTI, int MINB, bool CTRL, bool LISTP, bool L2PF, bool SPLITP>
 static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                             float *dW, cudaStream_t st) {
     const size_t smem = window_smem<N1>(ctx, k_used, MULTI, LISTP);
-    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL, LISTP, L2PF>;
+    auto kern = k_window<N1, VEC, NT, CH, MULTI, MINB, CTRL, LISTP, L2PF, SPLITP>;
     constexpr int NTT = NT + (CTRL ? 32 : 0);
     static ScgKernelCfg cfgc = {};
     int per_sm = 0;
@@ -857,11 +876,11 @@ static int launch_window_tm(scg_ctx *ctx, int B, int T, int k_used, const float4
     return grid;
 }
 
-template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false, bool LISTP = true, bool L2PF = false>
+template <int N1, int VEC, int NT, int CH, int MINB = 1, bool CTRL = false, bool LISTP = true, bool L2PF = false, bool SPLITP = false>
 static int launch_window_t(scg_ctx *ctx, int B, int T, int k_used, const float4 *rec, float *trace, float gl,
                            float *dW, cudaStream_t st) {
-    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL, LISTP, L2PF>(ctx, B, T, k_used, rec, trace, gl, dW, st);
-    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL, false, L2PF>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    if (T <= SCG_WIN_TB) return launch_window_tm<N1, VEC, NT, CH, false, MINB, CTRL, LISTP, L2PF, SPLITP>(ctx, B, T, k_used, rec, trace, gl, dW, st);
+    return launch_window_tm<N1, VEC, NT, CH, true, MINB, CTRL, false, L2PF, false>(ctx, B, T, k_used, rec, trace, gl, dW, st);
 }
 
 int scg_prof_push(scg_ctx *ctx, int kind, cudaStream_t st, bool end);
@@ -875,7 +894,7 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
     int grid = 0, rc;
     // tuning knobs (defaults = the measured best)
     static int mode3 = -1, list5 = -1;
-    if (mode3 < 0) { const char *e = getenv("SCG_WIN_MODE3"); mode3 = e ? atoi(e) : 2; }
+    if (mode3 < 0) { const char *e = getenv("SCG_WIN_MODE3"); mode3 = e ? atoi(e) : 3; }
     if (list5 < 0) { const char *e = getenv("SCG_WIN_LIST5"); list5 = e ? atoi(e) : 0; }
     if ((rc = scg_prof_push(ctx, 1, st, false))) return rc;
     switch (ctx->order) {
@@ -885,7 +904,9 @@ int scg_launch_window(scg_ctx *ctx, int B, int T, int k_used, const float *rec, 
         case 3:
             // two warps per env.  With the next trace prefetched into L2 instead of registers the sweep needs 140
             // registers (7 CTAs per SM) and loses nothing when squeezed to 128 (8 CTAs, while 8 accumulators fit)
-            if (mode3 == 2 && 8 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)
+            if (mode3 == 3 && 8 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)
+                grid = launch_window_t<4, 4, 64, 1, 8, false, true, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
+            else if (mode3 >= 2 && 8 * (window_smem<4>(ctx, k_used, T > SCG_WIN_TB) + 1024) <= 227 * 1024)
                 grid = launch_window_t<4, 4, 64, 1, 8, false, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else if (mode3 >= 1) grid = launch_window_t<4, 4, 64, 1, 1, false, true, true>(ctx, B, T, k_used, r4, trace, gl, dW, st);
             else grid = launch_window_t<4, 4, 64, 1>(ctx, B, T, k_used, r4, trace, gl, dW, st);
