@@ -168,17 +168,20 @@ __global__ void __launch_bounds__(NT) k_trace(int B, int K, const float4 *__rest
 // one env at a time; thread t owns the same VEC features of all A rows of every env's trace (registers)
 // and of the CTA's dW accumulator (shared memory, [K][A*F], plain read-modify-write: ownership is
 // exclusive).  Work items are (env, block of 8 steps); per item:
-//   build  every thread forms a few entries of the pair tables P01[t][c0][c1] = exp(i pi (c0 s0 + c1 s1))
-//          and P23[t][c2][c3] = exp(i pi (c2 s2 + c3 s3)) with one sincospi each; for the env's first
-//          block one thread also runs the backward recursion G_t = delta_t + (done_t ? 0 : gl G_{t+1})
-//          and the trace coefficients c_t
+//   build  the pair tables P01[t][c0][c1] = exp(i pi (c0 s0 + c1 s1)) and P23[t][c2][c3] = exp(i pi (c2 s2 + c3 s3))
+//          of the NEXT item, one SFU sincos per entry; for an env's first block a scan warp also runs the backward
+//          recursion G_t = delta_t + (done_t ? 0 : gl G_{t+1}), the trace coefficients c_t and (windows of <= 8
+//          steps) sorts the contributing steps by (segment, action) into a list
 //   main   phi_f = Re(P01[f / N1^2] P23[f % N1^2]);  d[a_t][f] += G_t phi_f;  e[a_t][f] += c_t phi_f
 //          with d (the env's dW contribution, seeded with the carry-in gl G_0 e_start) and e in registers;
 //          d is added to the shared accumulator once per env (or when the option changes)
-// The tables are double-buffered and the records / traces of the following items are prefetched into
-// registers, so there is one barrier per item and no phase waits on a load it has just issued.  A feature
-// costs two 8-byte shared loads and two FP32 ops to form, and the dense trace crosses HBM once per
-// window: 8*A*F/T + 32 algorithmic bytes per env-step.
+// The tables are double-buffered and the records of the following items are prefetched into registers, so there is one
+// barrier per item and no phase waits on a load it has just issued.  The next trace is prefetched either into L2 by one
+// bulk-prefetch instruction (L2PF: order 3, where the 20 registers it frees buy two more CTAs per SM) or into registers
+// (order 5: one CTA per SM, nothing else would cover an L2 hit).  With two warps per env (order 3, SPLIT) warp 0 runs
+// the scan and warp 1 builds all the table entries, so neither waits for the other at the barrier; with many warps per
+// env (orders 4, 5) an extra warp does nothing but the scan (CTRL).  A feature costs two 8-byte shared loads and two
+// FP32 ops to form, and the dense trace crosses HBM once per window: 8*A*F/T + 32 algorithmic bytes per env-step.
 #define SCG_WIN_TB 8   // steps per table block
 #ifndef SCG_WIN_PF
 #define SCG_WIN_PF 1
