@@ -223,19 +223,29 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     constexpr int NCHR = F / VEC;          // chunks per action row
     constexpr int NN = N1 * N1;
     constexpr int TABN = SCG_WIN_TB * 2 * NN;             // entries of one table buffer
+    // Storage of one step's tables, in float2: P01 (NN entries) then P23 in two halves of 16-byte groups (entries
+    // (4g, 4g+1) of every group g of four, then entries (4g+2, 4g+3)).  DUP9 (order 5): the 9 groups of a half cannot
+    // sit in 8 distinct bank quads, and a quarter-warp reads 8 consecutive groups (mod 9) with one 16-byte load: 7 of 9
+    // quarters hit groups 0 and 8 together - two wavefronts (6.4 per load measured).  So a half is 16 slots: groups 0..7,
+    // then eight copies of group 8, copy m in the bank quad of group m; the thread that needs group 8 reads the copy in
+    // the quad its quarter leaves free.
+    constexpr bool DUP9 = VEC == 4 && NN / 4 == 9;
+    constexpr int HS = DUP9 ? 32 : NN / 2;                // float2 per half of P23
+    constexpr int TSZ = VEC == 4 ? NN + 2 * HS : 2 * NN;  // float2 per step
+    constexpr int TABS = SCG_WIN_TB * TSZ;                // float2 per table buffer
     // SPLIT (two warps per env): warp 0 runs the per-env scan, warp 1 builds all the table entries - the two jobs take
     // about as long, so neither warp waits for the other at the per-item barrier.  The 16 state pairs the entries need
     // (8 steps x positions / velocities) are loaded by 16 lanes, one each, and handed round with shuffles.
     constexpr bool SPLIT = SPLITP && !CTRL && !MULTI && NT == 64 && 2 * NN == 32;
     constexpr int BT = SPLIT ? 32 : NT;                   // threads that build table entries
     constexpr int EPT = (TABN + BT - 1) / BT;             // table entries built per builder thread
-    constexpr int TSTRIDE = 2 * NN * (int)sizeof(float2); // bytes between the tables of consecutive steps
+    constexpr int TSTRIDE = TSZ * (int)sizeof(float2);    // bytes between the tables of consecutive steps
     static_assert(F % VEC == 0 && NT * CH >= NCHR && NT >= 32 && SCG_WIN_MAX <= 32, "layout");
     static_assert(VEC == 1 || NN % VEC == 0, "a chunk shares its (c0, c1) digits");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *acc = reinterpret_cast<float *>(smem_raw);                                      // [K][AF]
-    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [2][TABN]
-    WinCtl *ctl = reinterpret_cast<WinCtl *>(tab + 2 * TABN);                              // [2]
+    float2 *tab = reinterpret_cast<float2 *>(acc + (((size_t)K * AF + 3) & ~(size_t)3));   // [2][TABS]
+    WinCtl *ctl = reinterpret_cast<WinCtl *>(tab + 2 * TABS);                              // [2]
     float *glpow = reinterpret_cast<float *>(ctl + 2);                                     // [36]: gl^n
 
     const int tid = threadIdx.x;
@@ -257,19 +267,27 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     for (int j = 0; j < CH; ++j) {
         const int f0 = (own[j] ? tid + j * NT : 0) * VEC;
         off01[j] = (f0 / NN) * (int)sizeof(float2);
-        // P23: scalar form one float2 per (c2, c3); vector form in two halves - entries (4g, 4g+1) of every group g of
-        // four, then entries (4g+2, 4g+3) - so that the 16-byte loads of a warp's NN/4 distinct groups are contiguous
-        // (order 5: 9 groups at a 32-byte stride collided three to a bank quad: 9.4 wavefronts per load; now 2)
-        off23[j] = VEC == 4 ? NN * (int)sizeof(float2) + ((f0 % NN) / 4) * 16 : (NN + f0 % NN) * (int)sizeof(float2);
+        // P23: scalar form one float2 per (c2, c3); vector form: the 16-byte slot of the chunk's group in the first half
+        // (the second half is HS float2 further on); DUP9: group 8 is read from the copy in the bank quad that the
+        // other seven lanes of this quarter-warp leave free
+        if constexpr (VEC == 4) {
+            const int c = own[j] ? tid + j * NT : 0;
+            int slot = c % (NN / 4);
+            if (DUP9 && slot == 8) slot = 8 + (8 * (c / 8) + 8) % 9;
+            off23[j] = NN * (int)sizeof(float2) + slot * 16;
+        } else {
+            off23[j] = (NN + f0 % NN) * (int)sizeof(float2);
+        }
     }
     // ... and, for the EPT table entries this thread builds: step within the block, which state pair, digits,
     // the affine map of the raw state pair to [0, 1] (positions: identity; velocities: (v + 2) / 4) folded into the
     // digit coefficients (x = ca s0 + cb s1 + cc on the raw pair), and where the entry goes.
     // REG: the threads of a CTA tile the steps' tables exactly (NT a multiple of the 2 NN entries of a step), so all of
     // this is the same for every entry a thread builds, up to a constant step stride - scalars instead of arrays.
-    constexpr bool REG = BT % (2 * NN) == 0 && TABN % BT == 0;
+    constexpr bool REG = BT % (2 * NN) == 0 && TABN % BT == 0 && !DUP9;
     constexpr int EN = REG ? 1 : EPT;
     int e_tt[EN], e_half[EN], e_at[EN];
+    bool e_dup[EN];                                      // DUP9: an entry of group 8 - stored eight times
     float e_ca[EN], e_cb[EN], e_cc[EN];
 #pragma unroll
     for (int k = 0; k < EN; ++k) {
@@ -280,12 +298,13 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         const float mul = half ? 0.25f : 1.f, add = half ? 0.5f : 0.f;
         e_ca[k] = (float)(ij / N1) * mul; e_cb[k] = (float)(ij % N1) * mul;
         e_cc[k] = (float)(ij / N1 + ij % N1) * add;
-        int at = idx;
+        int at = tt * TSZ + rem;
         if (VEC == 4 && half) {
             const int g = ij >> 2, kk = ij & 3;
-            at = (tt * 2 + 1) * NN + (kk < 2 ? 2 * g + kk : NN / 2 + 2 * g + (kk - 2));
+            at = tt * TSZ + NN + (kk >> 1) * HS + 2 * g + (kk & 1);
         }
         e_at[k] = at;
+        e_dup[k] = DUP9 && half && (ij >> 2) == 8;
     }
     auto ent_tt = [&](int k) { return REG ? e_tt[0] + k * (BT / (2 * NN)) : e_tt[REG ? 0 : k]; };
     auto ent_at = [&](int k) { return REG ? e_at[0] + k * BT : e_at[REG ? 0 : k]; };
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
     };
     // registers -> pair tables (buffer `par`) and, for an env's first block, its control block (buffer `epar`)
     auto build = [&](WinItem it, int par, int epar) {
-        float2 *tb = tab + par * TABN;
+        float2 *tb = tab + par * TABS;
         if (builder) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
@@ -381,7 +400,16 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 }
                 const float x = fmaf(e_ca[kc], sv.x, fmaf(e_cb[kc], sv.y, e_cc[kc]));
                 const float xr = 3.14159265358979f * fmaf(-2.f, rintf(0.5f * x), x);
-                if (REG || bt + k * BT < TABN) tb[ent_at(k)] = make_float2(__cosf(xr), __sinf(xr));
+                if (REG || bt + k * BT < TABN) {
+                    const float2 v = make_float2(__cosf(xr), __sinf(xr));
+                    tb[ent_at(k)] = v;
+                    if constexpr (DUP9) {
+                        if (e_dup[kc]) {
+#pragma unroll
+                            for (int mq = 1; mq < 8; ++mq) tb[ent_at(k) + 2 * mq] = v;
+                        }
+                    }
+                }
             }
         }
         if (it.blk == 0 && scan_warp) {
@@ -449,7 +477,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                     if (t <= SCG_A) cb.rng[sgm][t] = (uint8_t)c_lane;
                     if (nz && seg == sgm)
                         cb.ent[c_own + __popc(m_own & in_seg & below)] =
-                            make_float4(G, cf, __int_as_float(par * TABN * (int)sizeof(float2) + t * TSTRIDE), 0.f);
+                            make_float4(G, cf, __int_as_float(par * TABS * (int)sizeof(float2) + t * TSTRIDE), 0.f);
                     if (t == 0) cb.seg_o[sgm] = os;
                 }
             }
@@ -533,7 +561,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
         }
         // ---- main ----
         const WinCtl &cb = ctl[epar];
-        const char *tb0 = reinterpret_cast<const char *>(tab + par * TABN);
+        const char *tb0 = reinterpret_cast<const char *>(tab + par * TABS);
         [[maybe_unused]] const float2 *gc = nullptr;
         if constexpr (!LIST) gc = cb.gc + cur.blk * SCG_WIN_TB;
         if (cur.blk == 0) {
@@ -568,7 +596,7 @@ __global__ void __launch_bounds__(NT + (CTRL ? 32 : 0), MINB) k_window(int B, in
                 V ph;
                 if constexpr (VEC == 4) {
                     const float4 q01 = *reinterpret_cast<const float4 *>(tb + off23[j]);
-                    const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + (NN / 4) * 16);
+                    const float4 q23 = *reinterpret_cast<const float4 *>(tb + off23[j] + HS * (int)sizeof(float2));
                     ph = make_float4(fmaf(p.x, q01.x, -p.y * q01.y), fmaf(p.x, q01.z, -p.y * q01.w),
                                      fmaf(p.x, q23.x, -p.y * q23.y), fmaf(p.x, q23.z, -p.y * q23.w));
                 } else {
@@ -851,7 +879,7 @@ template <int N1>
 static size_t window_smem(const scg_ctx *ctx, int k_used, bool multi, bool list = true) {
     constexpr int NN = N1 * N1;
     return (((size_t)k_used * SCG_A * ctx->F + 3) & ~(size_t)3) * sizeof(float) +
-           (size_t)2 * SCG_WIN_TB * 2 * NN * sizeof(float2) +
+           (size_t)2 * SCG_WIN_TB * (N1 == 6 ? NN + 64 : 2 * NN) * sizeof(float2) +
            2 * (multi ? sizeof(WinCtlT<SCG_WIN_MAX>) : (list ? sizeof(WinCtlList) : sizeof(WinCtlT<SCG_WIN_TB>))) + 36 * sizeof(float);
 }
 
