@@ -55,6 +55,7 @@ class PinballMap:
         offs[1:] = np.cumsum([len(p) for p in self.polygons])
         self._handle = C.c_void_p()
         lib = _lib.load()
+        grid_n = int(grid_n) or int(os.environ.get("SCG_GRID_N", "0"))      # 0: the library default (64)
         check(lib.scg_map_create(ptr(verts), ptr(offs), len(self.polygons), self.ball_r, self.target[0],
                                  self.target[1], self.target[2], ptr(self.starts), len(self.starts),
                                  int(grid_n), C.byref(self._handle)))
