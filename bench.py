@@ -422,10 +422,11 @@ def run_ours(args):
     brk["measured_total_us"] = e2e_ms * 1e3 / args.steps
     resid = brk["measured_total_us"] - sum(v for k, v in brk.items() if k != "measured_total_us")
     brk["host_and_launch_latency_us"] = max(resid, 0.0)
-    if resid < 0:      # the pieces are timed one by one AFTER the end-to-end blocks, on later env states: they need not add up
+    if resid < 0:      # the pieces overlap in the pipelined host step (and are timed after the end-to-end blocks)
         brk["pieces_exceed_total_by_us"] = -resid
-    brk["note"] = ("copies are PCIe-bound and cannot overlap the step (the caller needs the results before it can supply the "
-                   "next inputs); the sweep / apply chain of a full window must finish before the next step's Q evaluation")
+    brk["note"] = ("pieces timed one by one; scg_agent_step_host pipelines them over 2 parts of the batch (copy in / step / copy "
+                   "out on three streams), so they add up to more than the total; the sweep / apply chain of a full window "
+                   "must finish before the next step's Q evaluation")
     # informational: the same loop for a caller that needs the state only once per sync interval (run_host)
     Ts = args.sync_interval
     hw = dict(s=ag.s.cpu().numpy().copy(), a=ag.action.cpu().numpy().copy())

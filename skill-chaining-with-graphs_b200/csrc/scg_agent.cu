@@ -38,6 +38,7 @@ struct StepArgs {
     int k_stage;      // options whose weights are staged to shared memory (ids 0 .. k_stage-1 are the ones in use)
     int wait_first;   // 1: the previous launch may have written the weights - wait for it before staging them
     int n_steps;      // consecutive steps run by this launch (records go to consecutive slabs of the window)
+    int b_begin, b_end;   // envs [b_begin, b_end) are stepped by this launch (b_begin a multiple of 32; normally 0, B)
     float4 *rec;  // this step's slab of the window: [B][2]
     uint8_t *ev;  // this step's slab of the event bytes: [B]
     float2 *pos;  // this step's slab of option start positions: [B]
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     const uint32_t amask = g.ctl->active_mask;
     const int gest = min(n_act, K - 1);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int n_tiles = (g.B + 31) >> 5;
+    const int n_tiles = (args.b_end - args.b_begin + 31) >> 5;
     constexpr unsigned FULL = 0xffffffffu;
     // warp-granular work, interleaved over CTAs: tile i goes to CTA i % grid, warp i / grid.  The warp stays
     // converged through the whole tile (lanes past the batch end compute on a clamped index and skip stores).
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) k_agent_step(const __grid_cons
     // steps of every env with the env's state in registers: one load and one store of the per-env state, one
     // staging of the map and the weights and one launch per window instead of per step.
     for (int tile = w * gridDim.x + blockIdx.x; tile < n_tiles; tile += gridDim.x * nw) {
-        const bool valid = tile * 32 + lane < g.B;
-        const int b = valid ? tile * 32 + lane : g.B - 1;
+        const bool valid = args.b_begin + tile * 32 + lane < args.b_end;
+        const int b = valid ? args.b_begin + tile * 32 + lane : args.b_end - 1;
         const uint32_t env = g.env_offset + (uint32_t)b;
         float sx = g.x[b], sy = g.y[b], svx = g.vx[b], svy = g.vy[b];
         // (ids poked in from outside are clamped: an out-of-range option or action must not index past the tables)
@@ -380,7 +381,7 @@ static int launch_step_tt(const StepArgs &args, size_t smem, cudaStream_t st) {
     if (rcc) return rcc;
     if (per_sm < 1) return SCG_ELIMIT;
     constexpr int WPC = NTH / 32;                       // warps (tiles in flight) per CTA
-    const int n_tiles = (args.ag.B + 31) / 32;
+    const int n_tiles = (args.b_end - args.b_begin + 31) / 32;
     // enough CTAs for one warp per tile if they all fit at once, else every resident slot
     int grid = (n_tiles + WPC - 1) / WPC;
     if (grid > SCG_NUM_SMS) {   // same number of CTAs on every SM: as many rounds of 148 as the tiles need, if resident
@@ -461,8 +462,11 @@ extern "C" int scg_agent_flush(scg_ctx_t *ctx, scg_agent_t *ag, void *stream) {
 
 // n consecutive steps (1 <= n <= win_cap - win_len) in one launch; a full window is swept right away unless the
 // caller defers that (defer_flush) to queue something of its own first
+// b_begin/b_end: step only those envs and leave the bookkeeping to the call that steps the last part (b_end == B):
+// scg_agent_step_host pipelines a step over parts of the batch
 static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, int n, void *stream,
-                       bool defer_flush = false) {
+                       bool defer_flush = false, int b_begin = 0, int b_end = -1) {
+    if (b_end < 0) b_end = ag->B;
     cudaStream_t st = (cudaStream_t)stream;
     // promotions happen on the device (scg_agent_manage); the host learns of them from the mirror, without waiting
     if (ctx->h_ctl) ag->n_active = std::max(ag->n_active, std::min((int)ctx->h_ctl->n_active, ag->K - 1));
@@ -478,6 +482,8 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     args.pos = reinterpret_cast<float2 *>(ag->ev_pos) + (size_t)ag->ev_len * ag->B;
     args.top = ag->win_top ? ag->win_top + (size_t)ag->win_len * ag->B * 8 : nullptr;
     args.n_steps = n;
+    args.b_begin = b_begin;
+    args.b_end = b_end;
     // weights go to shared memory when two CTAs per SM still fit next to the map, or one big CTA
     static int big = -1;
     if (big < 0) { const char *e = getenv("SCG_STEP_BIG_CTA"); big = e ? atoi(e) : 1; }
@@ -491,6 +497,7 @@ static int agent_steps(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, in
     DISPATCH_ORDER(ag->order, rc = launch_step_n<N1>(args, mode, pair, st));
     if (rc) return rc;
     if ((rc = scg_prof_push(ctx, 0, st, true))) return rc;
+    if (b_end < ag->B) return 0;
     std::swap(ag->x, ag->x2); std::swap(ag->y, ag->y2);
     std::swap(ag->vx, ag->vx2); std::swap(ag->vy, ag->vy2);
     ag->step += n;
@@ -552,6 +559,11 @@ static int copy_rows(void *const *dst, const void *const *src, int rows, size_t 
     return 0;
 }
 
+// One step through host buffers.  The three phases - state and action in, the step kernel, results out - are a chain
+// for any one env but not across envs, so the batch is cut into parts (multiples of 32 envs) and pipelined: part p+1
+// is copied in while part p is stepped and part p-1 is copied out (PCIe is full duplex; copies in and copies out have
+// a stream each, the kernels stay on the caller's stream, events order the three).  Rows of the SoA blocks are moved
+// with one pitched copy per block.  SCG_HOST_PARTS (default 2; 1 = the plain sequence).
 extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag, const float *h_state_soa,
                                    const int *h_action, float *h_state2_soa, float *h_reward, int *h_flags,
                                    int *h_action2, float *h_delta, void *stream) {
@@ -559,32 +571,84 @@ extern "C" int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_age
         !h_delta)
         return SCG_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)ag->B * sizeof(float);
+    const int B = ag->B;
+    const size_t n = (size_t)B * sizeof(float);
     int rc;
-    {
-        void *dst[4] = {ag->x, ag->y, ag->vx, ag->vy};
-        const void *src[4] = {h_state_soa, h_state_soa + ag->B, h_state_soa + 2 * (size_t)ag->B, h_state_soa + 3 * (size_t)ag->B};
-        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyHostToDevice, st))) return rc;
-    }
-    SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
-    ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
     if ((rc = check_agent(map, ctx, ag))) return rc;
-    if (ag->B == 0) return 0;
-    if ((rc = agent_steps(map, ctx, ag, 1, stream, /*defer_flush=*/true))) return rc;
-    {   // the step swapped the buffers: x..vy is the new state
-        void *dst[4] = {h_state2_soa, h_state2_soa + ag->B, h_state2_soa + 2 * (size_t)ag->B, h_state2_soa + 3 * (size_t)ag->B};
-        const void *src[4] = {ag->x, ag->y, ag->vx, ag->vy};
-        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+    static int parts_env = -1;
+    if (parts_env < 0) { const char *e = getenv("SCG_HOST_PARTS"); parts_env = e ? atoi(e) : 2; }
+    // pitched copies need the SoA blocks back to back on both sides (they are in the Python layer: [4][B] tensors)
+    auto rows4 = [&](const void *a, const void *b, const void *c, const void *d) {
+        return (const char *)b == (const char *)a + n && (const char *)c == (const char *)a + 2 * n && (const char *)d == (const char *)a + 3 * n;
+    };
+    const bool blocks = rows4(ag->x, ag->y, ag->vx, ag->vy) && rows4(ag->x2, ag->y2, ag->vx2, ag->vy2) &&
+                        rows4(ag->reward, ag->flags, ag->action, ag->delta) && rows4(h_reward, h_flags, h_action2, h_delta);
+    int parts = std::max(1, std::min(parts_env, SCG_HOST_PARTS_MAX));
+    if (!blocks || B < 64 * parts || (ctx->prof_on && (ctx->prof_mask & 1))) parts = 1;
+    if (parts == 1) {
+        {
+            void *dst[4] = {ag->x, ag->y, ag->vx, ag->vy};
+            const void *src[4] = {h_state_soa, h_state_soa + B, h_state_soa + 2 * (size_t)B, h_state_soa + 3 * (size_t)B};
+            if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyHostToDevice, st))) return rc;
+        }
+        SCG_CUDA_OK(cudaMemcpyAsync(ag->action, h_action, n, cudaMemcpyHostToDevice, st));
+        ag->carry_valid = 0;   // state and action came from outside: Q_o(s, a) must be evaluated
+        if (B == 0) return 0;
+        if ((rc = agent_steps(map, ctx, ag, 1, stream, /*defer_flush=*/true))) return rc;
+        {   // the step swapped the buffers: x..vy is the new state
+            void *dst[4] = {h_state2_soa, h_state2_soa + B, h_state2_soa + 2 * (size_t)B, h_state2_soa + 3 * (size_t)B};
+            const void *src[4] = {ag->x, ag->y, ag->vx, ag->vy};
+            if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+        }
+        {   // reward, flags, next action, TD error: one copy when both sides keep them back to back
+            void *dst[4] = {h_reward, h_flags, h_action2, h_delta};
+            const void *src[4] = {ag->reward, ag->flags, ag->action, ag->delta};
+            if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
+        }
+        // The results do not depend on the trace sweep: when this step filled the window, the sweep is queued behind the
+        // copies and the host only waits for the copies, so the sweep overlaps the caller's next host-side work and H2D.
+        if (!ctx->host_ev) SCG_CUDA_OK(cudaEventCreateWithFlags(&ctx->host_ev, cudaEventDisableTiming));
+        SCG_CUDA_OK(cudaEventRecord(ctx->host_ev, st));
+        if (ag->win_len >= ag->win_cap && (rc = scg_agent_flush(ctx, ag, stream))) return rc;
+        SCG_CUDA_OK(cudaEventSynchronize(ctx->host_ev));
+        return 0;
     }
-    {   // reward, flags, next action, TD error: one copy when both sides keep them back to back
-        void *dst[4] = {h_reward, h_flags, h_action2, h_delta};
-        const void *src[4] = {ag->reward, ag->flags, ag->action, ag->delta};
-        if ((rc = copy_rows(dst, src, 4, n, cudaMemcpyDeviceToHost, st))) return rc;
-    }
-    // The results do not depend on the trace sweep: when this step filled the window, the sweep is queued behind the
-    // copies and the host only waits for the copies, so the sweep overlaps the caller's next host-side work and H2D.
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->host_st[i]) SCG_CUDA_OK(cudaStreamCreateWithFlags(&ctx->host_st[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * SCG_HOST_PARTS_MAX + 1; ++i)
+        if (!ctx->host_evs[i]) SCG_CUDA_OK(cudaEventCreateWithFlags(&ctx->host_evs[i], cudaEventDisableTiming));
     if (!ctx->host_ev) SCG_CUDA_OK(cudaEventCreateWithFlags(&ctx->host_ev, cudaEventDisableTiming));
-    SCG_CUDA_OK(cudaEventRecord(ctx->host_ev, st));
+    cudaStream_t s_in = ctx->host_st[0], s_out = ctx->host_st[1];
+    cudaEvent_t *ev_in = ctx->host_evs, *ev_step = ctx->host_evs + SCG_HOST_PARTS_MAX, ev_entry = ctx->host_evs[2 * SCG_HOST_PARTS_MAX];
+    // whatever the caller queued on its stream (a sweep, the controller) stays ahead of the copies in
+    SCG_CUDA_OK(cudaEventRecord(ev_entry, st));
+    SCG_CUDA_OK(cudaStreamWaitEvent(s_in, ev_entry, 0));
+    ag->carry_valid = 0;       // state and action came from outside: Q_o(s, a) must be evaluated
+    // the step writes the new state to x2 .. vy2 (the buffers are swapped by the call that steps the last part)
+    float *d_new = ag->x2;
+    float *d_out = ag->reward;
+    const int per = ((B + parts - 1) / parts + 31) & ~31;
+    for (int p = 0; p < parts; ++p) {
+        const int b0 = p * per, b1 = std::min(B, b0 + per);
+        if (b0 >= b1) { parts = p; break; }
+        const size_t w = (size_t)(b1 - b0) * sizeof(float);
+        SCG_CUDA_OK(cudaMemcpy2DAsync(ag->x + b0, n, h_state_soa + b0, n, w, 4, cudaMemcpyHostToDevice, s_in));
+        SCG_CUDA_OK(cudaMemcpyAsync(ag->action + b0, h_action + b0, w, cudaMemcpyHostToDevice, s_in));
+        SCG_CUDA_OK(cudaEventRecord(ev_in[p], s_in));
+    }
+    for (int p = 0; p < parts; ++p) {
+        const int b0 = p * per, b1 = std::min(B, b0 + per);
+        const size_t w = (size_t)(b1 - b0) * sizeof(float);
+        SCG_CUDA_OK(cudaStreamWaitEvent(st, ev_in[p], 0));
+        if ((rc = agent_steps(map, ctx, ag, 1, stream, /*defer_flush=*/true, b0, b1))) return rc;
+        SCG_CUDA_OK(cudaEventRecord(ev_step[p], st));
+        SCG_CUDA_OK(cudaStreamWaitEvent(s_out, ev_step[p], 0));
+        SCG_CUDA_OK(cudaMemcpy2DAsync(h_state2_soa + b0, n, d_new + b0, n, w, 4, cudaMemcpyDeviceToHost, s_out));
+        SCG_CUDA_OK(cudaMemcpy2DAsync(h_reward + b0, n, d_out + b0, n, w, 4, cudaMemcpyDeviceToHost, s_out));
+    }
+    SCG_CUDA_OK(cudaEventRecord(ctx->host_ev, s_out));
+    // The results do not depend on the trace sweep: when this step filled the window, the sweep is queued behind the
+    // step and the host only waits for the copies, so the sweep overlaps the caller's next host-side work and H2D.
     if (ag->win_len >= ag->win_cap && (rc = scg_agent_flush(ctx, ag, stream))) return rc;
     SCG_CUDA_OK(cudaEventSynchronize(ctx->host_ev));
     return 0;

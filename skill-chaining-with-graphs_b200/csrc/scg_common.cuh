@@ -102,6 +102,7 @@ struct scg_map {
     size_t stage_cap;
 };
 
+#define SCG_HOST_PARTS_MAX 4
 struct scg_ctx {
     int order, K, F;
     int n_partials;      // CTAs of the trace kernel
@@ -113,6 +114,9 @@ struct scg_ctx {
     int rec_capacity;
     int win_grid;        // CTAs of the window kernel (0 = not configured yet)
     cudaEvent_t host_ev; // "results copied" marker of scg_agent_step_host
+    // scg_agent_step_host pipelines a step over parts of the batch: copies in on host_st[0], copies out on host_st[1]
+    cudaStream_t host_st[2];
+    cudaEvent_t host_evs[2 * SCG_HOST_PARTS_MAX + 1];   // [part] copied in, [MAX + part] stepped, [2 MAX] entry marker
     // controller (scg_ctl.cu)
     scg_ctl_t *h_ctl;          // host-mapped mirror of the device controller state (scg_agent_poll), allocated on first use
     scg_ctl_t *d_hctl;         // its device alias

@@ -988,6 +988,8 @@ extern "C" int scg_ctx_destroy(scg_ctx_t *c) {
     if (c->d_red) cudaFree(c->d_red);
     if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->host_ev) cudaEventDestroy(c->host_ev);
+    for (int i = 0; i < 2; ++i) if (c->host_st[i]) cudaStreamDestroy(c->host_st[i]);
+    for (int i = 0; i < 2 * SCG_HOST_PARTS_MAX + 1; ++i) if (c->host_evs[i]) cudaEventDestroy(c->host_evs[i]);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->d_ring) cudaFree(c->d_ring);
     for (int i = 0; i < 2 * c->prof_cap; ++i) cudaEventDestroy(c->prof_ev[i]);

@@ -78,6 +78,23 @@ def test_step_bit_exact(scg, torch, name, near, cull):
         assert (okind != 0).mean() > 0.2      # the case really exercises collisions
 
 
+@pytest.mark.parametrize("grid_n", [8, 32, 128])
+def test_step_bit_exact_at_other_grid_resolutions(scg, torch, grid_n):
+    """The broad-phase grid only prunes: every resolution gives the oracle's bits (collisions, flags, next states)."""
+    omap = oracle.PinballMap.from_name("hard")
+    gmap = scg.PinballMap.from_name("hard", grid_n=grid_n)
+    assert gmap.grid()[0] == grid_n
+    B = 20000
+    S, A = _states(omap, B, seed=5, near_walls=True)
+    env = scg.PinballEnv(gmap, B, cull=True)
+    env.reset(states=S)
+    ns, r, done, hit = env.step(torch.as_tensor(A).cuda())
+    ons, orr, ofl = step_batched(omap, S, A)
+    assert np.array_equal(env.flags.cpu().numpy(), ofl)
+    assert np.array_equal(ns.cpu().numpy().view(np.uint32), ons.view(np.uint32))
+    assert np.array_equal(r.cpu().numpy(), orr)
+
+
 def test_step_goal_and_bounds_cases(scg, torch):
     omap = oracle.PinballMap.from_name("easy")
     gmap = scg.PinballMap.from_name("easy")
