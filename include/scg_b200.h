@@ -281,7 +281,9 @@ int scg_xchg_sync_top(scg_xchg_t *x, int order, int K, int K_opt, float *W, floa
 /* HOST-buffer variant of scg_agent_step: the call a user makes who keeps state and actions in
  * host (NumPy) arrays, as with the oracle's SkillChainAgent.  Copies state [4][B] and action [B]
  * host->device, runs the fused step, copies next state, reward, flags, next action and TD error
- * device->host and waits for them.  Traces and weights stay resident on the device. */
+ * device->host and waits for them.  Traces and weights stay resident on the device.  When the SoA blocks are
+ * back to back on both sides the step is pipelined over parts of the batch (copy in / step / copy out on three
+ * streams; environment SCG_HOST_PARTS, default 2, 1 = one part); results are identical. */
 int scg_agent_step_host(const scg_map_t *map, scg_ctx_t *ctx, scg_agent_t *ag,
                         const float *h_state_soa, const int *h_action, float *h_state2_soa,
                         float *h_reward, int *h_flags, int *h_action2, float *h_delta, void *stream);
