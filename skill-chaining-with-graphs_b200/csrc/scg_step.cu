@@ -134,7 +134,7 @@ extern "C" int scg_map_create(const float *verts, const int *poly_start, int n_p
         }
         n_cand += (int)l.size();
     }
-    if (n_cand >= (1 << 24)) {
+    if (n_cand >= (1 << 23)) {
         scg_map_destroy(m);
         return SCG_ELIMIT;
     }
@@ -175,7 +175,14 @@ extern "C" int scg_map_create(const float *verts, const int *poly_start, int n_p
     int pos = 0;
     for (int c = 0; c < G * G; ++c) {
         m->h_cell_start[c] = pos;
-        cells[c] = ((uint32_t)pos << 8) | (uint32_t)lists[c].size();
+        // bit 31: the goal test can succeed for a ball in this cell (the cell, grown by 0.003 for the extra move after a
+        // bounce on the last substep, reaches the target disc): elsewhere the kernel skips the test (same result)
+        const int ci = c / G, cj = c % G;
+        const double mg = 0.003;
+        const double ddx = std::max(std::max((double)ci / G - mg - (double)tx, (double)tx - ((double)(ci + 1) / G + mg)), 0.0);
+        const double ddy = std::max(std::max((double)cj / G - mg - (double)ty, (double)ty - ((double)(cj + 1) / G + mg)), 0.0);
+        const bool goal_near = ddx * ddx + ddy * ddy <= (double)tr * (double)tr * 1.0001 + 1e-9;
+        cells[c] = (goal_near ? 0x80000000u : 0u) | ((uint32_t)pos << 8) | (uint32_t)lists[c].size();
         for (int ed : lists[c]) {
             m->h_cand[pos] = ed;
             cand[pos++] = (uint16_t)ed;

@@ -89,11 +89,14 @@ __device__ __forceinline__ void pinball_step(const StepMap &m, float &x, float &
         x = __fadd_rn(x, __fmul_rn(vx, m.h));
         y = __fadd_rn(y, __fmul_rn(vy, m.h));
         int nhit = 0, first = -1;
-        bool in_grid = kCull && (x >= 0.f) && (x < 1.f) && (y >= 0.f) && (y < 1.f);
+        // cell of (x, y): floor(x G) is exact (G is a power of two), and 0 <= x < 1 is 0 <= floor(x G) < G
+        const int ci = __float2int_rd(x * m.gf), cj = __float2int_rd(y * m.gf);
+        const bool in_grid = kCull && (unsigned)ci < (unsigned)m.G && (unsigned)cj < (unsigned)m.G;
+        bool goal_near = true;
         if (in_grid) {
-            int ci = (int)(x * m.gf), cj = (int)(y * m.gf);  // exact: G is a power of two
-            uint32_t cell = m.cells[ci * m.G + cj];
-            int cnt = cell & 0xFF, start = cell >> 8;
+            const uint32_t cell = m.cells[ci * m.G + cj];
+            goal_near = (cell >> 31) != 0u;      // set by scg_map_create where the goal test can succeed
+            const int cnt = cell & 0xFF, start = (cell >> 8) & 0x7FFFFF;
 #pragma unroll 1   // lists are short (0-4 edges): the unrolled-by-4 prologue cost more than it saved
             for (int j = 0; j < cnt; ++j) {
                 int e = m.cand[start + j];
@@ -131,10 +134,12 @@ __device__ __forceinline__ void pinball_step(const StepMap &m, float &x, float &
             kind = 2;
             ids = __float_as_int(m.eb[first].w);
         }
-        float gx = __fsub_rn(x, m.tx), gy = __fsub_rn(y, m.ty);
-        if (__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)) < m.tr2) {
-            done = true;
-            break;
+        if (goal_near) {
+            float gx = __fsub_rn(x, m.tx), gy = __fsub_rn(y, m.ty);
+            if (__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)) < m.tr2) {
+                done = true;
+                break;
+            }
         }
     }
     if (done) {
