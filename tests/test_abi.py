@@ -44,6 +44,21 @@ def test_version_error_strings_and_argument_checks_without_gpu():
     assert lib.scg_agent_step(None, None, None, None) == -1
 
 
+def test_packed_weight_slot_sizes():
+    """The packed copy is [K][scg_packed_slot_floats(order)]: pairs of features x 12 floats, padded so that consecutive
+    slots start 16 bytes apart modulo 128 (lanes on different slots then read different shared-memory banks)."""
+    import skill_chaining_with_graphs_b200 as scg
+    lib = scg.load_library()
+    for order in range(1, 6):
+        n1 = order + 1
+        pairs = n1 ** 3 * ((n1 + 1) // 2)
+        floats = lib.scg_packed_slot_floats(order)
+        assert floats * 4 >= pairs * 48 and floats * 4 - pairs * 48 < 128
+        assert (floats * 4) % 128 == 16 and floats % 4 == 0
+    assert lib.scg_packed_slot_floats(0) == 0 and lib.scg_packed_slot_floats(6) == 0
+    assert lib.scg_packed_slot_floats(3) == 1540 and lib.scg_packed_slot_floats(5) == 7780
+
+
 def test_agent_struct_matches_header_field_order():
     from skill_chaining_with_graphs_b200._lib import AgentStruct
     src = open(HEADER).read()
