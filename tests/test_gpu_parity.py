@@ -188,6 +188,39 @@ def test_features_match_oracle(scg, torch, order):
     assert np.abs(phi - ophi).max() < 2e-5
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_packed_weights_follow_the_documented_layout(scg, torch, order):
+    """include/scg_b200.h: a slot holds its features in pairs over the last multi-index digit, 12 floats per pair
+    (w0a w1a w2a w3a | w0b w1b w2b w3b | w4a w4b 0 0); an odd N1 pairs its last feature with a phantom of weight 0.
+    apply keeps the packed copy current in the same layout."""
+    K, B = 3, 64
+    n1 = order + 1
+    F, NP = n1 ** 4, (n1 + 1) // 2
+    rng = np.random.default_rng(order)
+    gset = scg.OptionSet(K, order, B, gamma=0.97, seed=5)
+    W = rng.standard_normal((K, 5, F)).astype(np.float32)
+
+    def packed(W):
+        slot = gset.lib.scg_packed_slot_floats(order)
+        out = np.zeros((K, slot), np.float32)
+        for f in range(F):
+            row, c3 = divmod(f, n1)
+            p, h = row * NP + c3 // 2, c3 & 1
+            out[:, p * 12 + h * 4: p * 12 + h * 4 + 4] = W[:, :4, f]
+            out[:, p * 12 + 8 + h] = W[:, 4, f]
+        return out
+
+    gset.set_weights(W)
+    assert np.array_equal(gset.Wt.cpu().numpy(), packed(W))
+    # an apply with a known delta: W changes and the packed copy follows
+    gset._dW.copy_(torch.as_tensor(rng.standard_normal((K, 5, F)).astype(np.float32)).cuda())
+    gset._cnt.fill_(4)
+    gset.window_steps = 4
+    gset.apply()
+    assert not np.array_equal(gset.W.cpu().numpy(), W)
+    assert np.array_equal(gset.Wt.cpu().numpy(), packed(gset.W.cpu().numpy()))
+
+
 @pytest.mark.parametrize("order,K", [(3, 1), (3, 4), (5, 8), (2, 3)])
 def test_q_select_td_match_oracle(scg, torch, order, K):
     omap = oracle.PinballMap.from_name("easy")
